@@ -1,0 +1,185 @@
+/* stage_b200.h — C ABI of libstage_b200.so: the B200 (sm_100a) implementation of the STAGE forward hot path
+ * of jayleicn/TVQAplus.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; all tensors are fp32, row-major, contiguous,
+ *    16-byte aligned; masks are fp32 {0,1}
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, never synchronises,
+ *    never allocates or frees device memory and keeps no pointer after it returns
+ *  - return value 0 = success; non-zero = STAGE_E_* code, text via stage_last_error() (thread-local)
+ *  - inputs are const, outputs are fully overwritten
+ *
+ * Each entry point names the reference interface (file:line in jayleicn/TVQAplus) it stands in for.
+ */
+#ifndef STAGE_B200_H_
+#define STAGE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAGE_ABI_VERSION 1
+#define STAGE_HSZ 128          /* opt.hsz the kernels are specialised for (config.py:103) */
+#define STAGE_MAX_SEQ 128      /* longest token/region axis one encoder tile holds */
+#define STAGE_MAX_CONV 4       /* n_conv per encoder block (config.py:108,114 default 2) */
+#define STAGE_MAX_KSIZE 15     /* depthwise kernel size (config.py:109,115 default 7 / 5) */
+
+enum {
+  STAGE_OK = 0,
+  STAGE_E_BADARG = 1,      /* null / misaligned pointer, non-positive size */
+  STAGE_E_UNSUPPORTED = 2, /* shape outside what the kernels are specialised for */
+  STAGE_E_LAUNCH = 3,      /* cudaGetLastError() after launch */
+  STAGE_E_DEVICE = 4       /* a kernel raised the device-side error flag (bounded wait timed out) */
+};
+
+int stage_abi_version(void);
+const char* stage_last_error(void);
+/* Reads and clears the device-side error flag (synchronises the stream). 0 = clean. */
+int stage_check_device_error(void* stream);
+
+/* ---- weight packing ------------------------------------------------------------------------------------------
+ * nn.Linear / 1x1 Conv1d weights W[N,K] (row-major fp32, as stored in the reference state_dict, e.g.
+ * model/stage.py:88,110,117,136 and model/cnn.py:27) are split into fp16 (hi, lo) pairs and laid out as the
+ * shared-memory operand image the tcgen05 kernels bulk-copy.  `kc` is the K-chunk (32 or 64) the consuming kernel
+ * streams.  Re-run after every optimizer step (key the cache on the parameter version). */
+size_t stage_packed_weight_bytes(int n, int k, int kc);
+int stage_pack_weight(const float* w, int n, int k, int kc, void* packed, void* stream);
+
+/* ---- row-wise Linear with fused prologue / epilogue -------------------------------------------------------------
+ * y = LN_out( act( LN_in( l2norm?(x) ) W^T + b ) ), each piece optional.  Stands in for the nn.Sequential stacks
+ * bert_word_encoding_fc / vid_fc / input_embedding (model/stage.py:85-91,98-104,115-120) and F.normalize at
+ * model/stage.py:256, and for LinearWrapper (model/stage.py:15-32).  n <= 304, k % 4 == 0. */
+typedef struct {
+  int64_t m;             /* rows */
+  int k, n;              /* in / out features */
+  int kc;                /* K-chunk the weight was packed with */
+  int l2norm_in;         /* 1: x <- x / max(||x||_2, 1e-12) first */
+  int relu;              /* 1: ReLU after bias */
+  const float* x;        /* [m,k] */
+  const void* w_packed;  /* stage_pack_weight(W[n,k]) */
+  const float* bias;     /* [n] */
+  const float* ln_in_g;  /* [k] or NULL */
+  const float* ln_in_b;
+  const float* ln_out_g; /* [n] or NULL */
+  const float* ln_out_b;
+  float* y;              /* [m,n] */
+} StageLinearArgs;
+int stage_linear_fwd(const StageLinearArgs* a, void* stream);
+
+/* ---- EncoderBlock (model/encoder.py:9-52, model/cnn.py:6-47, model/position_encoding.py:33-43,
+ *      model/self_attention.py:19-71) ---------------------------------------------------------------------------
+ * x + pe -> n_conv x [LN -> depthwise conv(k, zero pad k/2) -> pointwise 128x128 -> ReLU -> + residual]
+ *        -> (heads>0: LN -> MHA -> + residual) -> LN.
+ * out_mode 0: y[n_seq,L,128].  out_mode 1: masked max-pool over L (mask_logits + max, model/stage.py:503):
+ * y[n_seq,128].  L <= 128. */
+typedef struct {
+  int64_t n_seq;
+  int L;
+  int n_conv, ksize, n_heads;
+  int out_mode;
+  const float* x;      /* [n_seq,L,128] */
+  const float* mask;   /* [n_seq,L] (needed for out_mode 1 and n_heads > 0) */
+  const float* pe;     /* [>=L,128] position-encoding buffer */
+  const float* ln_g[STAGE_MAX_CONV];
+  const float* ln_b[STAGE_MAX_CONV];
+  const float* dw_w[STAGE_MAX_CONV];   /* depthwise weight [128,1,k] */
+  const float* dw_b[STAGE_MAX_CONV];
+  const void* pw_packed[STAGE_MAX_CONV]; /* stage_pack_weight(pointwise [128,128], kc=64) */
+  const float* pw_b[STAGE_MAX_CONV];
+  const float* attn_ln_g;   /* heads > 0 only */
+  const float* attn_ln_b;
+  const void* attn_w_packed[4]; /* linears.0..3 */
+  const float* attn_b[4];
+  const float* final_ln_g;
+  const float* final_ln_b;
+  float* y;
+  float* workspace;    /* heads > 0: n_seq*L*128*4 floats; else may be NULL */
+} StageEncoderArgs;
+int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream);
+
+/* ---- fused QA<->context attention + fusion MLPs ------------------------------------------------------------------
+ * StructuredAttention (model/context_query_attention.py:35-101) for both streams, qa_ctx_attention +
+ * c2q_down_projection (model/stage.py:365-387,133-138) and concat_fc (model/stage.py:107-113,276-279):
+ * one CTA per (example, frame), looping over the 5 answers; S, P, U, both mixed tensors stay in TMEM / smem.
+ * Lq <= 128, Ls <= 112, R <= 32. */
+typedef struct {
+  int n, t, lq, ls, r;
+  float scale;                 /* opt.scale (config.py:67) */
+  const float* a_embed;        /* [n,5,lq,128] */
+  const float* a_mask;         /* [n,5,lq] */
+  const float* sub_embed;      /* [n,t,ls,128] */
+  const float* sub_mask;       /* [n,t,ls] */
+  const float* vid_embed;      /* [n,t,r,128] */
+  const float* vid_mask;       /* [n,t,r] */
+  const float* c2q_ln_g;       /* [384] */
+  const float* c2q_ln_b;
+  const void* c2q_w_packed;    /* [128,384], kc=32 */
+  const float* c2q_b;
+  const float* cat_ln_g;       /* [384] */
+  const float* cat_ln_b;
+  const void* cat_w_packed;    /* [128,384], kc=32 */
+  const float* cat_b;
+  const float* cat_out_ln_g;   /* [128] */
+  const float* cat_out_ln_b;
+  float* statement;            /* [n,5,t,lq,128] */
+  float* statement_mask;       /* [n,5,t,lq]  (the vid mixed_mask, model/stage.py:280-282) */
+  float* vid_raw_s;            /* optional [n,5,t,lq,r] (other_outputs["vid_raw_s"], model/stage.py:273) */
+  float* sub_raw_s;            /* optional [n,5,t,lq,ls] */
+  float* vid_norm_s;           /* optional [n,5,t,lq,r]  masked softmax weights */
+  float* sub_norm_s;           /* optional [n,5,t,lq,ls] */
+  float* att_vid;              /* optional [n,5,t,lq,128] U = P.ctx (StructuredAttention's A) */
+  float* att_sub;              /* optional */
+  float* mixed_vid;            /* optional [n,5,t,lq,128] c2q output */
+  float* mixed_sub;            /* optional */
+} StageCqaArgs;
+int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream);
+
+/* ---- span + answer heads -------------------------------------------------------------------------------------------
+ * residual_temporal_predictor, mask, softmax over frames, best (st<=ed) span, span-local / global masked max,
+ * classifier (model/stage.py:469-537, 439-467; model/model_utils.py:78-121), eval branch, t_iter layers >= 1
+ * skipped (they never reach the outputs, model/stage.py:515-518). */
+typedef struct {
+  int n, t;
+  int add_local, extra_span_length;
+  const float* max_statement;      /* [n*5,t,128] */
+  const float* statement_mask;     /* [n,5,t,lq]: max_statement_mask = (sum over lq != 0) */
+  int lq;
+  const float* ts_mask;            /* [n,t] */
+  const float* proj_ln_g; const float* proj_ln_b; const float* proj_w; const float* proj_b; /* cls_projection_layers.0 */
+  const float* st_ln_g; const float* st_ln_b; const float* st_w; const float* st_b;       /* temporal_scoring_st_layers.0 */
+  const float* ed_ln_g; const float* ed_ln_b; const float* ed_w; const float* ed_b;
+  const float* cls_ln_g; const float* cls_ln_b; const float* cls_w; const float* cls_b;   /* classifier */
+  float* t_scores;     /* [n,5,t,2] masked raw logits */
+  float* t_probs;      /* [n,5,t,2] softmax over t */
+  int32_t* spans;      /* [n*5,2] predicted (st, ed) inclusive */
+  float* span_conf;    /* [n*5] p_st*p_ed of the chosen span */
+  float* answer;       /* [n,5] */
+  float* workspace;    /* n*5*t*128 floats (encoded max_statement) */
+} StageHeadArgs;
+int stage_span_head_fwd(const StageHeadArgs* a, void* stream);
+
+/* ---- best span search on its own (find_max_triples topN=1, model/model_utils.py:92-121) -------------------------- */
+int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, int32_t* spans, float* conf,
+                        void* stream);
+
+/* ---- mask_logits (model/model_utils.py:14-15): y = x*m + (1-m)*(-1e10), m broadcast over the last `inner` elems ---- */
+int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream);
+
+/* ---- UMMA layout probe (test-only; pins the descriptor conventions the kernels rely on) ------------------------------ */
+typedef struct {
+  const uint8_t* a_img; const uint8_t* b_img;
+  uint32_t a_bytes, b_bytes;
+  uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
+  uint32_t a_mn, b_mn;
+  uint32_t k_steps, n, use_bulk;
+  float* d_out; /* [128,n] */
+} StageProbeArgs;
+int stage_umma_probe(const StageProbeArgs* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAGE_B200_H_ */

@@ -1,0 +1,123 @@
+"""ctypes binding of ``libstage_b200.so`` (C ABI declared in ``include/stage_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstage_b200.so")
+
+MAX_CONV = 4
+
+_f = C.c_void_p  # device pointers travel as integers
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("m", C.c_int64), ("k", C.c_int), ("n", C.c_int), ("kc", C.c_int), ("l2norm_in", C.c_int),
+                ("relu", C.c_int), ("x", _f), ("w_packed", _f), ("bias", _f), ("ln_in_g", _f), ("ln_in_b", _f),
+                ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f)]
+
+
+class EncoderArgs(C.Structure):
+    _fields_ = [("n_seq", C.c_int64), ("L", C.c_int), ("n_conv", C.c_int), ("ksize", C.c_int), ("n_heads", C.c_int),
+                ("out_mode", C.c_int), ("x", _f), ("mask", _f), ("pe", _f),
+                ("ln_g", _f * MAX_CONV), ("ln_b", _f * MAX_CONV), ("dw_w", _f * MAX_CONV), ("dw_b", _f * MAX_CONV),
+                ("pw_packed", _f * MAX_CONV), ("pw_b", _f * MAX_CONV),
+                ("attn_ln_g", _f), ("attn_ln_b", _f), ("attn_w_packed", _f * 4), ("attn_b", _f * 4),
+                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f), ("workspace", _f)]
+
+
+class CqaArgs(C.Structure):
+    _fields_ = [("n", C.c_int), ("t", C.c_int), ("lq", C.c_int), ("ls", C.c_int), ("r", C.c_int), ("scale", C.c_float),
+                ("a_embed", _f), ("a_mask", _f), ("sub_embed", _f), ("sub_mask", _f), ("vid_embed", _f), ("vid_mask", _f),
+                ("c2q_ln_g", _f), ("c2q_ln_b", _f), ("c2q_w_packed", _f), ("c2q_b", _f),
+                ("cat_ln_g", _f), ("cat_ln_b", _f), ("cat_w_packed", _f), ("cat_b", _f),
+                ("cat_out_ln_g", _f), ("cat_out_ln_b", _f),
+                ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
+                ("vid_norm_s", _f), ("sub_norm_s", _f), ("att_vid", _f), ("att_sub", _f),
+                ("mixed_vid", _f), ("mixed_sub", _f)]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("n", C.c_int), ("t", C.c_int), ("add_local", C.c_int), ("extra_span_length", C.c_int),
+                ("max_statement", _f), ("statement_mask", _f), ("lq", C.c_int), ("ts_mask", _f),
+                ("proj_ln_g", _f), ("proj_ln_b", _f), ("proj_w", _f), ("proj_b", _f),
+                ("st_ln_g", _f), ("st_ln_b", _f), ("st_w", _f), ("st_b", _f),
+                ("ed_ln_g", _f), ("ed_ln_b", _f), ("ed_w", _f), ("ed_b", _f),
+                ("cls_ln_g", _f), ("cls_ln_b", _f), ("cls_w", _f), ("cls_b", _f),
+                ("t_scores", _f), ("t_probs", _f), ("spans", _f), ("span_conf", _f), ("answer", _f), ("workspace", _f)]
+
+
+class ProbeArgs(C.Structure):
+    _fields_ = [("a_img", _f), ("b_img", _f), ("a_bytes", C.c_uint32), ("b_bytes", C.c_uint32),
+                ("a_lbo", C.c_uint32), ("a_sbo", C.c_uint32), ("a_step", C.c_uint32),
+                ("b_lbo", C.c_uint32), ("b_sbo", C.c_uint32), ("b_step", C.c_uint32),
+                ("a_mn", C.c_uint32), ("b_mn", C.c_uint32),
+                ("k_steps", C.c_uint32), ("n", C.c_uint32), ("use_bulk", C.c_uint32), ("d_out", _f)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check the .so exports everything the header declares
+SYMBOLS = {
+    "stage_abi_version": (C.c_int, []),
+    "stage_last_error": (C.c_char_p, []),
+    "stage_check_device_error": (C.c_int, [C.c_void_p]),
+    "stage_packed_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "stage_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "stage_encoder_block_fwd": (C.c_int, [C.POINTER(EncoderArgs), C.c_void_p]),
+    "stage_cqa_fused_fwd": (C.c_int, [C.POINTER(CqaArgs), C.c_void_p]),
+    "stage_span_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "stage_find_max_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_mask_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "stage_umma_probe": (C.c_int, [C.POINTER(ProbeArgs), C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "tvqaplus_b200: %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the STAGE kernels)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        if l.stage_abi_version() != 1:
+            raise RuntimeError("tvqaplus_b200: ABI version mismatch in %s" % LIB_PATH)
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().stage_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, (msg or b"").decode()))
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a CUDA fp32/int tensor (None stays NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("tvqaplus_b200: expected a CUDA tensor (no CPU path exists)")
+    if not t.is_contiguous():
+        raise RuntimeError("tvqaplus_b200: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check_device_error() -> None:
+    check(lib().stage_check_device_error(current_stream()), "stage_check_device_error")
