@@ -2,7 +2,8 @@
 //
 // Image = n_chunks blocks of `chunk_bytes`; block c holds K columns [c*KC, (c+1)*KC) as
 //     [hi part | lo part], each part = (KC/8) k8-slabs of LBO_B = NPAD*16 bytes; inside a slab row n owns 16 bytes
-//     (8 consecutive k).  NPAD = N rounded up to 16; rows >= N and columns >= K are zero.
+//     (8 consecutive k).  NPAD is the consuming kernel's N tile (128 for N <= 128, 304 for N <= 304); rows >= N and
+//     columns >= K are zero.
 // A block is exactly the shared-memory image of one pipeline stage, so a stage load is ONE cp.async.bulk.
 #pragma once
 #include "umma.cuh"
@@ -18,7 +19,7 @@ struct PackGeom {
 __host__ __device__ inline PackGeom pack_geom(int n, int k, int kc) {
   PackGeom g;
   g.n = n; g.k = k; g.kc = kc;
-  g.npad = round_up(n, 16);
+  g.npad = n <= 128 ? 128 : 304;
   g.kpad = round_up(k, kc);
   g.n_chunks = g.kpad / kc;
   g.lbo = static_cast<uint32_t>(g.npad) * 16u;

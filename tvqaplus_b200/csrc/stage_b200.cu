@@ -3,8 +3,26 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include "probe.cuh"
+#include "pack.cuh"
+#include "linear.cuh"
+#define STG_HAVE_PACK 1
+#define STG_HAVE_LINEAR 1
 
 using namespace stg;
+
+namespace {
+template <int NPAD, int KC, int STAGES>
+static int launch_linear(const LinearDev& d, cudaStream_t s) {
+  using Cfg = LinearCfg<NPAD, KC, STAGES>;
+  int rc = set_smem(linear_kernel<NPAD, KC, STAGES>, Cfg::SMEM_BYTES, "linear");
+  if (rc) return rc;
+  const long long tiles = (d.m + 127) / 128;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  linear_kernel<NPAD, KC, STAGES><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(d);
+  return check_launch("linear");
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -40,6 +58,42 @@ int stage_umma_probe(const StageProbeArgs* a, void* stream) {
   if (rc) return rc;
   umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("umma_probe");
+}
+
+size_t stage_packed_weight_bytes(int n, int k, int kc) {
+  if (n <= 0 || n > 304 || k <= 0 || (kc != 32 && kc != 64)) return 0;
+  PackGeom g = pack_geom(n, k, kc);
+  return static_cast<size_t>(g.n_chunks) * g.chunk_bytes;
+}
+
+int stage_pack_weight(const float* w, int n, int k, int kc, void* packed, void* stream) {
+  STG_REQUIRE(w && packed, STAGE_E_BADARG, "pack_weight: null pointer");
+  STG_REQUIRE(n > 0 && n <= 304 && k > 0 && (kc == 32 || kc == 64), STAGE_E_UNSUPPORTED, "pack_weight: n=%d k=%d kc=%d", n, k, kc);
+  STG_REQUIRE(aligned16(packed), STAGE_E_BADARG, "pack_weight: packed buffer not 16-byte aligned");
+  PackGeom g = pack_geom(n, k, kc);
+  const int total = (g.kpad / 8) * g.npad;
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, static_cast<uint8_t*>(packed));
+  return check_launch("pack_weight");
+}
+
+int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
+  STG_REQUIRE(a && a->x && a->w_packed && a->bias && a->y, STAGE_E_BADARG, "linear: null pointer");
+  STG_REQUIRE(a->m > 0 && a->k > 0 && a->n > 0, STAGE_E_BADARG, "linear: m=%lld k=%d n=%d", (long long)a->m, a->k, a->n);
+  STG_REQUIRE(a->k % 4 == 0, STAGE_E_UNSUPPORTED, "linear: k=%d must be a multiple of 4", a->k);
+  STG_REQUIRE(a->n <= 304, STAGE_E_UNSUPPORTED, "linear: n=%d > 304", a->n);
+  STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->w_packed), STAGE_E_BADARG, "linear: pointers must be 16-byte aligned");
+  STG_REQUIRE((a->ln_in_g == nullptr) == (a->ln_in_b == nullptr) && (a->ln_out_g == nullptr) == (a->ln_out_b == nullptr),
+              STAGE_E_BADARG, "linear: LayerNorm gamma/beta must come in pairs");
+  const int want_kc = a->n <= 128 ? 64 : 32;
+  STG_REQUIRE(a->kc == want_kc, STAGE_E_UNSUPPORTED, "linear: weight for n=%d must be packed with kc=%d", a->n, want_kc);
+  PackGeom g = pack_geom(a->n, a->k, a->kc);
+  LinearDev d;
+  d.x = a->x; d.w = static_cast<const uint8_t*>(a->w_packed); d.bias = a->bias;
+  d.ln_in_g = a->ln_in_g; d.ln_in_b = a->ln_in_b; d.ln_out_g = a->ln_out_g; d.ln_out_b = a->ln_out_b;
+  d.y = a->y; d.m = a->m; d.k = a->k; d.n = a->n; d.n_chunks = g.n_chunks; d.l2norm_in = a->l2norm_in; d.relu = a->relu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->n <= 128) return launch_linear<128, 64, 3>(d, s);
+  return launch_linear<304, 32, 3>(d, s);
 }
 
 // ---- not built yet (filled in as the kernels land) ----
