@@ -5,7 +5,9 @@
 #include "probe.cuh"
 #include "pack.cuh"
 #include "linear.cuh"
+#include "encoder.cuh"
 #define STG_HAVE_PACK 1
+#define STG_HAVE_ENCODER 1
 #define STG_HAVE_LINEAR 1
 
 using namespace stg;
@@ -22,6 +24,16 @@ static int launch_linear(const LinearDev& d, cudaStream_t s) {
   return check_launch("linear");
 }
 
+template <int KS>
+static int launch_encoder(const EncDev& d, cudaStream_t s) {
+  int rc = set_smem(encoder_kernel<KS>, EncCfg::SMEM_BYTES, "encoder");
+  if (rc) return rc;
+  const int G = 128 / d.L;
+  const long long tiles = (d.n_seq + G - 1) / G;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  encoder_kernel<KS><<<grid, EncCfg::THREADS, EncCfg::SMEM_BYTES, s>>>(d);
+  return check_launch("encoder");
+}
 }  // namespace
 
 extern "C" {
@@ -94,6 +106,34 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->n <= 128) return launch_linear<128, 64, 3>(d, s);
   return launch_linear<304, 32, 3>(d, s);
+}
+
+int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
+  STG_REQUIRE(a && a->x && a->pe && a->y && a->final_ln_g && a->final_ln_b, STAGE_E_BADARG, "encoder: null pointer");
+  STG_REQUIRE(a->n_seq > 0 && a->L > 0, STAGE_E_BADARG, "encoder: n_seq=%lld L=%d", (long long)a->n_seq, a->L);
+  STG_REQUIRE(a->L <= STAGE_MAX_SEQ, STAGE_E_UNSUPPORTED, "encoder: L=%d > %d", a->L, STAGE_MAX_SEQ);
+  STG_REQUIRE(a->n_conv >= 1 && a->n_conv <= STAGE_MAX_CONV, STAGE_E_UNSUPPORTED, "encoder: n_conv=%d", a->n_conv);
+  STG_REQUIRE(a->n_heads == 0, STAGE_E_UNSUPPORTED, "encoder: self-attention (n_heads=%d) is not built yet", a->n_heads);
+  STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
+  STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->pe), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
+  EncDev d;
+  d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;
+  d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode;
+  for (int i = 0; i < STAGE_MAX_CONV; ++i) {
+    const bool on = i < a->n_conv;
+    if (on) STG_REQUIRE(a->ln_g[i] && a->ln_b[i] && a->dw_w[i] && a->dw_b[i] && a->pw_packed[i] && a->pw_b[i], STAGE_E_BADARG,
+                        "encoder: conv %d has a null weight", i);
+    d.ln_g[i] = on ? a->ln_g[i] : nullptr; d.ln_b[i] = on ? a->ln_b[i] : nullptr;
+    d.dw_w[i] = on ? a->dw_w[i] : nullptr; d.dw_b[i] = on ? a->dw_b[i] : nullptr;
+    d.pw[i] = on ? static_cast<const uint8_t*>(a->pw_packed[i]) : nullptr; d.pw_b[i] = on ? a->pw_b[i] : nullptr;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a->ksize) {
+    case 3: return launch_encoder<3>(d, s);
+    case 5: return launch_encoder<5>(d, s);
+    case 7: return launch_encoder<7>(d, s);
+    default: return fail(STAGE_E_UNSUPPORTED, "encoder: kernel_size=%d (built: 3, 5, 7)", a->ksize);
+  }
 }
 
 // ---- not built yet (filled in as the kernels land) ----

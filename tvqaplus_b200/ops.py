@@ -57,3 +57,40 @@ def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, n: i
                         ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y))
     check(lib().stage_linear_fwd(C.byref(a), current_stream()), "stage_linear_fwd")
     return y
+
+
+def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
+    a = (C.c_void_p * n)()
+    for i, v in enumerate(vals):
+        a[i] = v
+    return a
+
+
+def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: torch.Tensor, convs: Sequence[dict],
+                      final_ln, ksize: int, *, n_heads: int = 0, attn: Optional[dict] = None,
+                      out_mode: int = 0) -> torch.Tensor:
+    """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
+    pw_packed, pw_b); final_ln = (g, b).  out_mode 1 returns the masked max-pool (n_seq, 128)."""
+    x = _f32(x)
+    n_seq, L, D = x.shape
+    if D != HSZ:
+        raise RuntimeError("tvqaplus_b200: hidden size %d != %d" % (D, HSZ))
+    if pe.shape[0] < L:
+        raise RuntimeError("tvqaplus_b200: sequence length %d exceeds the position-encoding table (%d)" % (L, pe.shape[0]))
+    y = torch.empty((n_seq, L, D) if out_mode == 0 else (n_seq, D), dtype=torch.float32, device=x.device)
+    keep = [_f32(c[k]) for c in convs for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")]  # keep contiguous copies alive
+    it = iter(keep)
+    cols = {k: [] for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")}
+    for _ in convs:
+        for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b"):
+            cols[k].append(ptr(next(it)))
+    mask_c = _f32(mask) if mask is not None else None
+    a = _lib.EncoderArgs(n_seq=n_seq, L=L, n_conv=len(convs), ksize=ksize, n_heads=n_heads, out_mode=out_mode,
+                         x=ptr(x), mask=ptr(mask_c), pe=ptr(_f32(pe)),
+                         ln_g=_arr(cols["ln_g"]), ln_b=_arr(cols["ln_b"]), dw_w=_arr(cols["dw_w"]),
+                         dw_b=_arr(cols["dw_b"]), pw_packed=_arr([ptr(c["pw_packed"]) for c in convs]),
+                         pw_b=_arr(cols["pw_b"]),
+                         attn_ln_g=None, attn_ln_b=None, attn_w_packed=_arr([], 4), attn_b=_arr([], 4),
+                         final_ln_g=ptr(_f32(final_ln[0])), final_ln_b=ptr(_f32(final_ln[1])), y=ptr(y), workspace=None)
+    check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
+    return y
