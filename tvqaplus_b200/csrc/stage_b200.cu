@@ -6,7 +6,9 @@
 #include "pack.cuh"
 #include "linear.cuh"
 #include "encoder.cuh"
+#include "cqa.cuh"
 #define STG_HAVE_PACK 1
+#define STG_HAVE_CQA 1
 #define STG_HAVE_ENCODER 1
 #define STG_HAVE_LINEAR 1
 
@@ -134,6 +136,36 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
     case 7: return launch_encoder<7>(d, s);
     default: return fail(STAGE_E_UNSUPPORTED, "encoder: kernel_size=%d (built: 3, 5, 7)", a->ksize);
   }
+}
+
+int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
+  STG_REQUIRE(a && a->a_embed && a->a_mask && a->sub_embed && a->sub_mask && a->vid_embed && a->vid_mask, STAGE_E_BADARG,
+              "cqa: null input (single-stream models are not built yet)");
+  STG_REQUIRE(a->c2q_ln_g && a->c2q_ln_b && a->c2q_w_packed && a->c2q_b && a->cat_ln_g && a->cat_ln_b && a->cat_w_packed &&
+                  a->cat_b && a->cat_out_ln_g && a->cat_out_ln_b, STAGE_E_BADARG, "cqa: null weight");
+  STG_REQUIRE(a->statement && a->statement_mask, STAGE_E_BADARG, "cqa: null output");
+  STG_REQUIRE(a->n > 0 && a->t > 0 && a->lq > 0 && a->ls > 0 && a->r > 0, STAGE_E_BADARG, "cqa: non-positive size");
+  STG_REQUIRE(a->lq <= 128 && a->ls <= CqaCfg::LS_MAX && a->r <= CqaCfg::R_MAX, STAGE_E_UNSUPPORTED,
+              "cqa: lq=%d ls=%d r=%d exceed the tile (128, %d, %d)", a->lq, a->ls, a->r, CqaCfg::LS_MAX, CqaCfg::R_MAX);
+  STG_REQUIRE(aligned16(a->a_embed) && aligned16(a->sub_embed) && aligned16(a->vid_embed) && aligned16(a->statement) &&
+                  aligned16(a->c2q_w_packed) && aligned16(a->cat_w_packed), STAGE_E_BADARG, "cqa: pointers must be 16-byte aligned");
+  CqaDev d;
+  d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r;
+  d.ls_pad = round_up(a->ls, 16); d.r_pad = round_up(a->r, 16); d.scale = a->scale;
+  d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
+  d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask;
+  d.c2q_g = a->c2q_ln_g; d.c2q_b = a->c2q_ln_b; d.c2q_w = static_cast<const uint8_t*>(a->c2q_w_packed); d.c2q_bias = a->c2q_b;
+  d.cat_g = a->cat_ln_g; d.cat_b = a->cat_ln_b; d.cat_w = static_cast<const uint8_t*>(a->cat_w_packed); d.cat_bias = a->cat_b;
+  d.out_g = a->cat_out_ln_g; d.out_b = a->cat_out_ln_b;
+  d.statement = a->statement; d.statement_mask = a->statement_mask;
+  d.vid_raw_s = a->vid_raw_s; d.sub_raw_s = a->sub_raw_s; d.vid_norm_s = a->vid_norm_s; d.sub_norm_s = a->sub_norm_s;
+  d.att_vid = a->att_vid; d.att_sub = a->att_sub; d.mixed_vid = a->mixed_vid; d.mixed_sub = a->mixed_sub;
+  int rc = set_smem(cqa_kernel, CqaCfg::SMEM_BYTES, "cqa");
+  if (rc) return rc;
+  const int frames = a->n * a->t;
+  const int grid = frames < num_sms() ? frames : num_sms();
+  cqa_kernel<<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(d);
+  return check_launch("cqa");
 }
 
 // ---- not built yet (filled in as the kernels land) ----

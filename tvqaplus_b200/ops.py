@@ -94,3 +94,40 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: torch.T
                          final_ln_g=ptr(_f32(final_ln[0])), final_ln_b=ptr(_f32(final_ln[1])), y=ptr(y), workspace=None)
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
     return y
+
+
+def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
+                  want: Sequence[str] = ()) -> dict:
+    """Fused StructuredAttention x2 + c2q_down_projection x2 + concat_fc (stage_cqa_fused_fwd).
+
+    a_embed (N,5,Lq,128), a_mask (N,5,Lq), sub_embed (N,T,Ls,128), sub_mask (N,T,Ls), vid_embed (N,T,R,128),
+    vid_mask (N,T,R).  ``w`` holds c2q_ln_g/b, c2q_w_packed (kc=32), c2q_b, cat_ln_g/b, cat_w_packed (kc=32), cat_b,
+    cat_out_ln_g/b.  ``want`` lists optional extra outputs: vid_raw_s, sub_raw_s, vid_norm_s, sub_norm_s, att_vid,
+    att_sub, mixed_vid, mixed_sub.  Returns dict with ``statement`` (N,5,T,Lq,128), ``statement_mask`` (N,5,T,Lq).
+    """
+    a_embed, a_mask = _f32(a_embed), _f32(a_mask)
+    sub_embed, sub_mask, vid_embed, vid_mask = _f32(sub_embed), _f32(sub_mask), _f32(vid_embed), _f32(vid_mask)
+    N, A, Lq, D = a_embed.shape
+    T, Ls = sub_embed.shape[1:3]
+    R = vid_embed.shape[2]
+    if A != 5 or D != HSZ:
+        raise RuntimeError("tvqaplus_b200: a_embed must be (N,5,Lq,128)")
+    dev = a_embed.device
+    out = {"statement": torch.empty(N, 5, T, Lq, D, dtype=torch.float32, device=dev),
+           "statement_mask": torch.empty(N, 5, T, Lq, dtype=torch.float32, device=dev)}
+    shapes = {"vid_raw_s": (N, 5, T, Lq, R), "sub_raw_s": (N, 5, T, Lq, Ls), "vid_norm_s": (N, 5, T, Lq, R),
+              "sub_norm_s": (N, 5, T, Lq, Ls), "att_vid": (N, 5, T, Lq, D), "att_sub": (N, 5, T, Lq, D),
+              "mixed_vid": (N, 5, T, Lq, D), "mixed_sub": (N, 5, T, Lq, D)}
+    for k in want:
+        out[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+    a = _lib.CqaArgs(n=N, t=T, lq=Lq, ls=Ls, r=R, scale=float(scale),
+                     a_embed=ptr(a_embed), a_mask=ptr(a_mask), sub_embed=ptr(sub_embed), sub_mask=ptr(sub_mask),
+                     vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask),
+                     c2q_ln_g=ptr(w["c2q_ln_g"]), c2q_ln_b=ptr(w["c2q_ln_b"]), c2q_w_packed=ptr(w["c2q_w_packed"]),
+                     c2q_b=ptr(w["c2q_b"]), cat_ln_g=ptr(w["cat_ln_g"]), cat_ln_b=ptr(w["cat_ln_b"]),
+                     cat_w_packed=ptr(w["cat_w_packed"]), cat_b=ptr(w["cat_b"]),
+                     cat_out_ln_g=ptr(w["cat_out_ln_g"]), cat_out_ln_b=ptr(w["cat_out_ln_b"]),
+                     statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
+                     **{k: ptr(out.get(k)) for k in shapes})
+    check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
+    return out
