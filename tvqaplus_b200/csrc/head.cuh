@@ -1,0 +1,207 @@
+// Span + answer heads (fp32 CUDA-core kernel, warp-shuffle reductions): one CTA per (example, answer) row.
+//   y_t   = x_t + relu(Lin128(LN(x_t)))                              residual_temporal_predictor  (stage.py:478)
+//   st/ed = Lin1(LN(y_t)) ; masked with ts_label_mask                (stage.py:479-481,521)
+//   p     = softmax over frames ; best (st <= ed) = argmax p_st*p_ed (model_utils.py:92-121, O(T) prefix-max scan)
+//   local = masked max over frames [st-E, ed+1+E), global = masked max over all frames          (stage.py:449-466)
+//   answer = Lin1(LN([local, global]))                               classifier                   (stage.py:536)
+// The whole head is ~0.05 GFLOP per example; what matters is that it removes the reference's device->host sync
+// (numpy argsort of T*T products per row) and reproduces the -1e10 / LayerNorm corner cases exactly.
+//
+// Tie rule of the span search: among equal fp32 products the larger flat index st*T+ed wins (the reference takes the
+// last element of an ascending argsort; numpy's default sort is not stable, so ties are not defined there).
+#pragma once
+#include "umma.cuh"
+
+namespace stg {
+
+struct HeadDev {
+  int n, t, lq, add_local, extra;
+  const float* max_statement;   // [n*5, t, 128]
+  const float* statement_mask;  // [n,5,t,lq]
+  const float* ts_mask;         // [n,t]
+  const float *proj_g, *proj_b, *proj_w, *proj_bias;
+  const float *st_g, *st_b, *st_w, *st_bias;
+  const float *ed_g, *ed_b, *ed_w, *ed_bias;
+  const float *cls_g, *cls_b, *cls_w, *cls_bias;
+  float* t_scores; float* t_probs; int* spans; float* span_conf; float* answer; float* enc;
+};
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, int tid) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+// LayerNorm of one 128-vector held as 4 values per lane
+__device__ __forceinline__ float4 ln128(float4 v, float4 g, float4 b) {
+  const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+  const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
+  const float var = warp_sum((a * a + c * c) + (d * d + e * e)) * (1.f / 128.f);
+  const float rs = 1.f / sqrtf(var + 1e-5f);
+  return make_float4(a * rs * g.x + b.x, c * rs * g.y + b.y, d * rs * g.z + b.z, e * rs * g.w + b.w);
+}
+
+__global__ void __launch_bounds__(256, 1) head_kernel(HeadDev p) {
+  extern __shared__ __align__(16) float hs[];
+  float* Wt = hs;                      // [128 k][128 c] transposed projection weight
+  float* lnv = Wt + 128 * 128;         // [8 warps][128] LN(x) staging
+  float* sc = lnv + 8 * 128;           // [t][2] masked scores, then probabilities
+  float* fm = sc + 2 * p.t;            // [t] frame mask (max_statement_mask)
+  float* feat = fm + p.t;              // [256] classifier input
+  __shared__ float red[8];
+  __shared__ int span_sh[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = blockIdx.x;          // n*5 + a
+  const int n_i = row / 5;
+  const int T = p.t;
+
+  for (int i = tid; i < 128 * 128; i += 256) {
+    const int c = i >> 7, k = i & 127;
+    Wt[k * 128 + c] = __ldg(p.proj_w + i);
+  }
+  for (int t = tid; t < T; t += 256) {
+    const float* m = p.statement_mask + (static_cast<size_t>(row) * T + t) * p.lq;
+    float s = 0.f;
+    for (int l = 0; l < p.lq; ++l) s += __ldg(m + l);
+    fm[t] = (s != 0.f) ? 1.f : 0.f;
+  }
+  __syncthreads();
+
+  const float4 pg = __ldg(reinterpret_cast<const float4*>(p.proj_g) + lane), pb = __ldg(reinterpret_cast<const float4*>(p.proj_b) + lane);
+  const float4 pbias = __ldg(reinterpret_cast<const float4*>(p.proj_bias) + lane);
+  const float4 sg = __ldg(reinterpret_cast<const float4*>(p.st_g) + lane), sb = __ldg(reinterpret_cast<const float4*>(p.st_b) + lane);
+  const float4 sw = __ldg(reinterpret_cast<const float4*>(p.st_w) + lane);
+  const float4 eg = __ldg(reinterpret_cast<const float4*>(p.ed_g) + lane), eb = __ldg(reinterpret_cast<const float4*>(p.ed_b) + lane);
+  const float4 ew = __ldg(reinterpret_cast<const float4*>(p.ed_w) + lane);
+  const float st_bias = __ldg(p.st_bias), ed_bias = __ldg(p.ed_bias);
+
+  // ---- per frame: residual projection + st/ed logits (warp per frame, lane = 4 channels)
+  for (int t = warp; t < T; t += 8) {
+    const size_t off = (static_cast<size_t>(row) * T + t) * 128;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p.max_statement + off) + lane);
+    const float4 l = ln128(x, pg, pb);
+    __syncwarp();
+    *reinterpret_cast<float4*>(lnv + warp * 128 + lane * 4) = l;
+    __syncwarp();
+    float4 acc = pbias;
+#pragma unroll 8
+    for (int k = 0; k < 128; ++k) {
+      const float a = lnv[warp * 128 + k];
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * 128 + lane * 4);
+      acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
+    }
+    const float4 y = make_float4(x.x + fmaxf(acc.x, 0.f), x.y + fmaxf(acc.y, 0.f), x.z + fmaxf(acc.z, 0.f), x.w + fmaxf(acc.w, 0.f));
+    *reinterpret_cast<float4*>(p.enc + off + lane * 4) = y;
+    const float4 ls = ln128(y, sg, sb), le = ln128(y, eg, eb);
+    const float s_st = warp_sum((ls.x * sw.x + ls.y * sw.y) + (ls.z * sw.z + ls.w * sw.w)) + st_bias;
+    const float s_ed = warp_sum((le.x * ew.x + le.y * ew.y) + (le.z * ew.z + le.w * ew.w)) + ed_bias;
+    if (lane == 0) {
+      const float m = __ldg(p.ts_mask + static_cast<size_t>(n_i) * T + t);
+      const float off_m = (1.f - m) * STG_NEG;
+      const float a0 = s_st * m + off_m, a1 = s_ed * m + off_m;  // mask_logits
+      sc[2 * t] = a0; sc[2 * t + 1] = a1;
+      p.t_scores[(static_cast<size_t>(row) * T + t) * 2] = a0;
+      p.t_scores[(static_cast<size_t>(row) * T + t) * 2 + 1] = a1;
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax over frames for st (c=0) and ed (c=1)
+  for (int c = 0; c < 2; ++c) {
+    float mx = -3.0e38f;
+    for (int t = tid; t < T; t += 256) mx = fmaxf(mx, sc[2 * t + c]);
+    mx = block_reduce(mx, true, red, tid);
+    float s = 0.f;
+    for (int t = tid; t < T; t += 256) {
+      const float e = expf(sc[2 * t + c] - mx);
+      sc[2 * t + c] = e;
+      s += e;
+    }
+    s = block_reduce(s, false, red, tid);
+    for (int t = tid; t < T; t += 256) {
+      const float pr = sc[2 * t + c] / s;
+      sc[2 * t + c] = pr;
+      p.t_probs[(static_cast<size_t>(row) * T + t) * 2 + c] = pr;
+    }
+  }
+  __syncthreads();
+
+  // ---- best span: max over st <= ed of p_st*p_ed via prefix max (ties: larger st, then larger ed)
+  if (tid == 0) {
+    float pm = -1.f, best = -1.f;
+    int pi = 0, bs = 0, be = 0;
+    for (int j = 0; j < T; ++j) {
+      const float a = sc[2 * j];
+      if (a >= pm) { pm = a; pi = j; }
+      const float v = pm * sc[2 * j + 1];
+      if (v > best || (v == best && (pi > bs || (pi == bs && j > be)))) { best = v; bs = pi; be = j; }
+    }
+    span_sh[0] = bs; span_sh[1] = be;
+    p.spans[2 * row] = bs; p.spans[2 * row + 1] = be;
+    p.span_conf[row] = best;
+  }
+  __syncthreads();
+
+  // ---- span-local and global masked max over frames (thread = channel; threads 128.. do the global one)
+  {
+    const int c = tid & 127;
+    int lo = 0, hi = T;
+    if (tid < 128) {
+      lo = span_sh[0] - p.extra; if (lo < 0) lo = 0;
+      hi = span_sh[1] + 1 + p.extra; if (hi > T) hi = T;
+    }
+    float mx = -3.0e38f;
+    for (int t = lo; t < hi; ++t) {
+      const float m = fm[t];
+      const float v = p.enc[(static_cast<size_t>(row) * T + t) * 128 + c] * m + (1.f - m) * STG_NEG;
+      mx = fmaxf(mx, v);
+    }
+    if (p.add_local) feat[tid] = mx; else if (tid >= 128) feat[c] = mx;
+  }
+  __syncthreads();
+
+  // ---- classifier: LN(feat) . w + b
+  {
+    const int F = p.add_local ? 256 : 128;
+    const float v = tid < F ? feat[tid] : 0.f;
+    const float mean = block_reduce(v, false, red, tid) / static_cast<float>(F);
+    const float d = tid < F ? v - mean : 0.f;
+    const float var = block_reduce(d * d, false, red, tid) / static_cast<float>(F);
+    const float rs = 1.f / sqrtf(var + 1e-5f);
+    const float term = tid < F ? (d * rs * __ldg(p.cls_g + tid) + __ldg(p.cls_b + tid)) * __ldg(p.cls_w + tid) : 0.f;
+    const float tot = block_reduce(term, false, red, tid);
+    if (tid == 0) p.answer[row] = tot + __ldg(p.cls_bias);
+  }
+}
+
+__global__ void find_max_span_kernel(const float* __restrict__ p_st, const float* __restrict__ p_ed, int rows, int T,
+                                     int* __restrict__ spans, float* __restrict__ conf) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float pm = -1.f, best = -1.f;
+  int pi = 0, bs = 0, be = 0;
+  for (int j = 0; j < T; ++j) {
+    const float a = p_st[static_cast<size_t>(r) * T + j];
+    if (a >= pm) { pm = a; pi = j; }
+    const float v = pm * p_ed[static_cast<size_t>(r) * T + j];
+    if (v > best || (v == best && (pi > bs || (pi == bs && j > be)))) { best = v; bs = pi; be = j; }
+  }
+  spans[2 * r] = bs; spans[2 * r + 1] = be;
+  conf[r] = best;
+}
+
+__global__ void mask_logits_kernel(const float* __restrict__ x, const float* __restrict__ m, long long outer, int inner,
+                                   float* __restrict__ y) {
+  const long long total = outer * inner;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float mm = m[i / inner];
+    y[i] = x[i] * mm + (1.f - mm) * STG_NEG;
+  }
+}
+
+}  // namespace stg

@@ -7,7 +7,9 @@
 #include "linear.cuh"
 #include "encoder.cuh"
 #include "cqa.cuh"
+#include "head.cuh"
 #define STG_HAVE_PACK 1
+#define STG_HAVE_HEAD 1
 #define STG_HAVE_CQA 1
 #define STG_HAVE_ENCODER 1
 #define STG_HAVE_LINEAR 1
@@ -166,6 +168,47 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   const int grid = frames < num_sms() ? frames : num_sms();
   cqa_kernel<<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(d);
   return check_launch("cqa");
+}
+
+int stage_span_head_fwd(const StageHeadArgs* a, void* stream) {
+  STG_REQUIRE(a && a->max_statement && a->statement_mask && a->ts_mask && a->t_scores && a->t_probs && a->spans &&
+                  a->span_conf && a->answer && a->workspace, STAGE_E_BADARG, "span_head: null pointer");
+  STG_REQUIRE(a->proj_ln_g && a->proj_ln_b && a->proj_w && a->proj_b && a->st_ln_g && a->st_ln_b && a->st_w && a->st_b &&
+                  a->ed_ln_g && a->ed_ln_b && a->ed_w && a->ed_b && a->cls_ln_g && a->cls_ln_b && a->cls_w && a->cls_b,
+              STAGE_E_BADARG, "span_head: null weight");
+  STG_REQUIRE(a->n > 0 && a->t > 0 && a->lq > 0, STAGE_E_BADARG, "span_head: n=%d t=%d lq=%d", a->n, a->t, a->lq);
+  STG_REQUIRE(a->t <= 8192, STAGE_E_UNSUPPORTED, "span_head: t=%d > 8192", a->t);
+  STG_REQUIRE(aligned16(a->max_statement) && aligned16(a->workspace), STAGE_E_BADARG, "span_head: pointers must be 16-byte aligned");
+  HeadDev d;
+  d.n = a->n; d.t = a->t; d.lq = a->lq; d.add_local = a->add_local; d.extra = a->extra_span_length;
+  d.max_statement = a->max_statement; d.statement_mask = a->statement_mask; d.ts_mask = a->ts_mask;
+  d.proj_g = a->proj_ln_g; d.proj_b = a->proj_ln_b; d.proj_w = a->proj_w; d.proj_bias = a->proj_b;
+  d.st_g = a->st_ln_g; d.st_b = a->st_ln_b; d.st_w = a->st_w; d.st_bias = a->st_b;
+  d.ed_g = a->ed_ln_g; d.ed_b = a->ed_ln_b; d.ed_w = a->ed_w; d.ed_bias = a->ed_b;
+  d.cls_g = a->cls_ln_g; d.cls_b = a->cls_ln_b; d.cls_w = a->cls_w; d.cls_bias = a->cls_b;
+  d.t_scores = a->t_scores; d.t_probs = a->t_probs; d.spans = a->spans; d.span_conf = a->span_conf; d.answer = a->answer;
+  d.enc = a->workspace;
+  const size_t smem = (128 * 128 + 8 * 128 + 3 * static_cast<size_t>(a->t) + 256) * sizeof(float);
+  int rc = set_smem(head_kernel, smem, "span_head");
+  if (rc) return rc;
+  head_kernel<<<a->n * 5, 256, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  return check_launch("span_head");
+}
+
+int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, int32_t* spans, float* conf, void* stream) {
+  STG_REQUIRE(p_st && p_ed && spans && conf, STAGE_E_BADARG, "find_max_span: null pointer");
+  STG_REQUIRE(rows > 0 && t > 0, STAGE_E_BADARG, "find_max_span: rows=%d t=%d", rows, t);
+  find_max_span_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p_st, p_ed, rows, t, spans, conf);
+  return check_launch("find_max_span");
+}
+
+int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream) {
+  STG_REQUIRE(x && mask && y, STAGE_E_BADARG, "mask_logits: null pointer");
+  STG_REQUIRE(outer > 0 && inner > 0, STAGE_E_BADARG, "mask_logits: outer=%lld inner=%d", (long long)outer, inner);
+  const long long total = outer * inner;
+  const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  mask_logits_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, mask, outer, inner, y);
+  return check_launch("mask_logits");
 }
 
 // ---- not built yet (filled in as the kernels land) ----

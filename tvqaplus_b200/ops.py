@@ -131,3 +131,56 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
                      **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
     return out
+
+
+def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local: bool, extra_span_length: int) -> dict:
+    """Span + answer heads, eval branch (stage_span_head_fwd).
+
+    max_statement (N*5, T, 128), statement_mask (N,5,T,Lq), ts_mask (N,T).  ``w``: proj_/st_/ed_/cls_ + ln_g, ln_b, w, b.
+    Returns t_scores (N,5,T,2) masked raw logits, t_probs, spans (N*5,2) int32 inclusive, span_conf, answer (N,5),
+    encoded (N,5,T,128)."""
+    max_statement, statement_mask, ts_mask = _f32(max_statement), _f32(statement_mask), _f32(ts_mask)
+    N, _, T, Lq = statement_mask.shape
+    dev = max_statement.device
+    o = dict(t_scores=torch.empty(N, 5, T, 2, dtype=torch.float32, device=dev),
+             t_probs=torch.empty(N, 5, T, 2, dtype=torch.float32, device=dev),
+             spans=torch.empty(N * 5, 2, dtype=torch.int32, device=dev),
+             span_conf=torch.empty(N * 5, dtype=torch.float32, device=dev),
+             answer=torch.empty(N, 5, dtype=torch.float32, device=dev),
+             encoded=torch.empty(N, 5, T, HSZ, dtype=torch.float32, device=dev))
+    keep = {k: _f32(v) for k, v in w.items()}
+    a = _lib.HeadArgs(n=N, t=T, add_local=int(add_local), extra_span_length=int(extra_span_length),
+                      max_statement=ptr(max_statement), statement_mask=ptr(statement_mask), lq=Lq, ts_mask=ptr(ts_mask),
+                      **{"%s_%s" % (grp, f): ptr(keep["%s_%s" % (grp, f)])
+                         for grp in ("proj", "st", "ed", "cls") for f in ("ln_g", "ln_b", "w", "b")},
+                      t_scores=ptr(o["t_scores"]), t_probs=ptr(o["t_probs"]), spans=ptr(o["spans"]),
+                      span_conf=ptr(o["span_conf"]), answer=ptr(o["answer"]), workspace=ptr(o["encoded"]))
+    check(lib().stage_span_head_fwd(C.byref(a), current_stream()), "stage_span_head_fwd")
+    return o
+
+
+def find_max_span(p_st: torch.Tensor, p_ed: torch.Tensor):
+    """Best (st <= ed) pair maximising p_st[st]*p_ed[ed] per row (stage_find_max_span)."""
+    p_st, p_ed = _f32(p_st), _f32(p_ed)
+    rows, T = p_st.shape
+    spans = torch.empty(rows, 2, dtype=torch.int32, device=p_st.device)
+    conf = torch.empty(rows, dtype=torch.float32, device=p_st.device)
+    check(lib().stage_find_max_span(ptr(p_st), ptr(p_ed), rows, T, ptr(spans), ptr(conf), current_stream()),
+          "stage_find_max_span")
+    return spans, conf
+
+
+def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """x*m + (1-m)*(-1e10) with m broadcast over the trailing axes of x it lacks (stage_mask_logits)."""
+    x = _f32(x)
+    mask = _f32(mask)
+    while mask.dim() > 0 and mask.shape[-1] == 1 and mask.dim() == x.dim():
+        mask = mask.squeeze(-1)
+    if tuple(x.shape[:mask.dim()]) != tuple(mask.shape):
+        mask = mask.expand(x.shape[:mask.dim()]).contiguous()
+    outer = mask.numel()
+    inner = x.numel() // max(1, outer)
+    y = torch.empty_like(x)
+    check(lib().stage_mask_logits(ptr(x), ptr(mask.contiguous()), outer, inner, ptr(y), current_stream()),
+          "stage_mask_logits")
+    return y
