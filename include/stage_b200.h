@@ -75,14 +75,21 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream);
  *        -> (heads>0: LN -> MHA -> + residual) -> LN.
  * out_mode 0: y[n_seq,L,128].  out_mode 1: masked max-pool over L (mask_logits + max, model/stage.py:503):
  * y[n_seq,128].  L <= 128. */
+#define STAGE_ENC_NO_PE 1        /* skip the position-encoding add */
+#define STAGE_ENC_NO_RESIDUAL 2  /* x <- act(conv(x)) instead of x <- x + act(conv(LN x)) */
+#define STAGE_ENC_NO_FINAL_LN 4  /* skip the closing LayerNorm */
+#define STAGE_ENC_NO_RELU 8      /* pointwise conv without ReLU (DepthwiseSeparableConv(relu=False), model/cnn.py:45-46) */
+/* a conv whose ln_g/ln_b are NULL takes its input without LayerNorm (plain DepthwiseSeparableConv, model/cnn.py:37-47;
+ * with them and NO_PE|NO_RESIDUAL|NO_FINAL_LN it is ConvLinear, model/stage.py:35-52) */
 typedef struct {
   int64_t n_seq;
   int L;
   int n_conv, ksize, n_heads;
   int out_mode;
+  int flags;           /* STAGE_ENC_* bits; 0 = the full EncoderBlock */
   const float* x;      /* [n_seq,L,128] */
   const float* mask;   /* [n_seq,L] (needed for out_mode 1 and n_heads > 0) */
-  const float* pe;     /* [>=L,128] position-encoding buffer */
+  const float* pe;     /* [>=L,128] position-encoding buffer (NULL with STAGE_ENC_NO_PE) */
   const float* ln_g[STAGE_MAX_CONV];
   const float* ln_b[STAGE_MAX_CONV];
   const float* dw_w[STAGE_MAX_CONV];   /* depthwise weight [128,1,k] */

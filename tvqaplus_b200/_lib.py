@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstage_b200.so")
 
 MAX_CONV = 4
+ENC_NO_PE, ENC_NO_RESIDUAL, ENC_NO_FINAL_LN, ENC_NO_RELU = 1, 2, 4, 8
 
 _f = C.c_void_p  # device pointers travel as integers
 
@@ -24,7 +25,7 @@ class LinearArgs(C.Structure):
 
 class EncoderArgs(C.Structure):
     _fields_ = [("n_seq", C.c_int64), ("L", C.c_int), ("n_conv", C.c_int), ("ksize", C.c_int), ("n_heads", C.c_int),
-                ("out_mode", C.c_int), ("x", _f), ("mask", _f), ("pe", _f),
+                ("out_mode", C.c_int), ("flags", C.c_int), ("x", _f), ("mask", _f), ("pe", _f),
                 ("ln_g", _f * MAX_CONV), ("ln_b", _f * MAX_CONV), ("dw_w", _f * MAX_CONV), ("dw_b", _f * MAX_CONV),
                 ("pw_packed", _f * MAX_CONV), ("pw_b", _f * MAX_CONV),
                 ("attn_ln_g", _f), ("attn_ln_b", _f), ("attn_w_packed", _f * 4), ("attn_b", _f * 4),

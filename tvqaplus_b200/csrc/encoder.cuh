@@ -43,7 +43,7 @@ struct EncDev {
   const float* fin_b;
   float* y;
   long long n_seq;
-  int L, n_conv, out_mode;
+  int L, n_conv, out_mode, flags;
 };
 
 #define STG_NEG (-1e10f)
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
         const int g = r / L, pos = r - g * L;
         const long long grow = (seq0 + g) * L + pos;
         float4 a = __ldg(reinterpret_cast<const float4*>(p.x + grow * 128) + lane);
-        float4 e = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(p.flags & STAGE_ENC_NO_PE)) e = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
         v = make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
         if (p.mask != nullptr) m = __ldg(p.mask + grow);
       }
@@ -124,8 +125,9 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
 
       // ---- phase 2: depthwise conv over LN(x) (LN applied on the fly) -> split-fp16 A image.  lane = 4 channels
       {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g[ci]) + lane);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b[ci]) + lane);
+        const bool idn = (p.ln_g[ci] == nullptr);  // no LayerNorm in front of this conv
+        const float4 g4 = idn ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(reinterpret_cast<const float4*>(p.ln_g[ci]) + lane);
+        const float4 b4 = idn ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.ln_b[ci]) + lane);
         const float4 db = __ldg(reinterpret_cast<const float4*>(p.dw_b[ci]) + lane);
         float wt[4][KS];
 #pragma unroll
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
             const int q = r + j - P;
             if (q >= s0 && q < s0 + L && q < 128) {
               const float4 v = *reinterpret_cast<const float4*>(X + q * EncCfg::XS + lane * 4);
-              const float mu = row_mean[q], rs = row_rstd[q];
+              const float mu = idn ? 0.f : row_mean[q], rs = idn ? 1.f : row_rstd[q];
               o0 = fmaf(wt[0][j], (v.x - mu) * rs * g4.x + b4.x, o0);
               o1 = fmaf(wt[1][j], (v.y - mu) * rs * g4.y + b4.y, o1);
               o2 = fmaf(wt[2][j], (v.z - mu) * rs * g4.z + b4.z, o2);
@@ -202,10 +204,10 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
           for (int j = 0; j < 16; j += 4) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(p.pw_b[ci] + cb + c0 + j));
             float4 xv = *reinterpret_cast<float4*>(xr + c0 + j);
-            xv.x += fmaxf(v[j] + bb.x, 0.f);
-            xv.y += fmaxf(v[j + 1] + bb.y, 0.f);
-            xv.z += fmaxf(v[j + 2] + bb.z, 0.f);
-            xv.w += fmaxf(v[j + 3] + bb.w, 0.f);
+            float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+            if (!(p.flags & STAGE_ENC_NO_RELU)) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
+            if (p.flags & STAGE_ENC_NO_RESIDUAL) xv = dv;
+            else xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
             *reinterpret_cast<float4*>(xr + c0 + j) = xv;
           }
         }
@@ -216,8 +218,9 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
 
     // ---- final LayerNorm (+ store or masked max-pool)
     {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.fin_g) + lane);
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.fin_b) + lane);
+      const bool fin = !(p.flags & STAGE_ENC_NO_FINAL_LN);
+      const float4 g4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_g) + lane) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 b4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_b) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int rr = 0; rr < 16; ++rr) {
         const int r = warp * 16 + rr;
         float4 v = *reinterpret_cast<const float4*>(X + r * EncCfg::XS + lane * 4);
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
         const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
         const float rs = 1.f / sqrtf(var + 1e-5f);
         float4 o = make_float4(a * rs * g4.x + b4.x, b * rs * g4.y + b4.y, c * rs * g4.z + b4.z, d * rs * g4.w + b4.w);
+        if (!fin) o = v;
         if (p.out_mode == 0) {
           if (r < n_valid) {
             const int g = r / L, pos = r - g * L;

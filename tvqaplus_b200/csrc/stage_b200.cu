@@ -113,19 +113,21 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
 }
 
 int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
-  STG_REQUIRE(a && a->x && a->pe && a->y && a->final_ln_g && a->final_ln_b, STAGE_E_BADARG, "encoder: null pointer");
+  STG_REQUIRE(a && a->x && a->y, STAGE_E_BADARG, "encoder: null pointer");
+  STG_REQUIRE((a->flags & STAGE_ENC_NO_PE) || a->pe, STAGE_E_BADARG, "encoder: null position-encoding table");
+  STG_REQUIRE((a->flags & STAGE_ENC_NO_FINAL_LN) || (a->final_ln_g && a->final_ln_b), STAGE_E_BADARG, "encoder: null final LayerNorm");
   STG_REQUIRE(a->n_seq > 0 && a->L > 0, STAGE_E_BADARG, "encoder: n_seq=%lld L=%d", (long long)a->n_seq, a->L);
   STG_REQUIRE(a->L <= STAGE_MAX_SEQ, STAGE_E_UNSUPPORTED, "encoder: L=%d > %d", a->L, STAGE_MAX_SEQ);
   STG_REQUIRE(a->n_conv >= 1 && a->n_conv <= STAGE_MAX_CONV, STAGE_E_UNSUPPORTED, "encoder: n_conv=%d", a->n_conv);
   STG_REQUIRE(a->n_heads == 0, STAGE_E_UNSUPPORTED, "encoder: self-attention (n_heads=%d) is not built yet", a->n_heads);
   STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
-  STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->pe), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
+  STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
   EncDev d;
   d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;
-  d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode;
+  d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode; d.flags = a->flags;
   for (int i = 0; i < STAGE_MAX_CONV; ++i) {
     const bool on = i < a->n_conv;
-    if (on) STG_REQUIRE(a->ln_g[i] && a->ln_b[i] && a->dw_w[i] && a->dw_b[i] && a->pw_packed[i] && a->pw_b[i], STAGE_E_BADARG,
+    if (on) STG_REQUIRE((a->ln_g[i] == nullptr) == (a->ln_b[i] == nullptr) && a->dw_w[i] && a->dw_b[i] && a->pw_packed[i] && a->pw_b[i], STAGE_E_BADARG,
                         "encoder: conv %d has a null weight", i);
     d.ln_g[i] = on ? a->ln_g[i] : nullptr; d.ln_b[i] = on ? a->ln_b[i] : nullptr;
     d.dw_w[i] = on ? a->dw_w[i] : nullptr; d.dw_b[i] = on ? a->dw_b[i] : nullptr;

@@ -1,0 +1,23 @@
+"""Cache of split-fp16 weight images, keyed on the parameter's storage and version counter so an optimizer step (or
+``load_state_dict``) invalidates it; kernels otherwise read parameter storage in place."""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Tuple
+
+import torch
+
+from .. import ops
+
+_cache: Dict[int, Tuple[tuple, torch.Tensor, "weakref.ref"]] = {}
+
+
+def packed(param: torch.Tensor, kc: int) -> torch.Tensor:
+    key = id(param)
+    tag = (param.data_ptr(), param._version, kc, str(param.device), tuple(param.shape))
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is param:
+        return hit[1]
+    img = ops.pack_weight(param.detach(), kc)
+    _cache[key] = (tag, img, weakref.ref(param, lambda _r, k=key: _cache.pop(k, None)))
+    return img

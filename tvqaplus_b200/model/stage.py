@@ -1,0 +1,304 @@
+"""STAGE (reference model/stage.py:55-806) on hand-written sm_100a kernels.
+
+Same constructor (``STAGE(opt)``), ``forward(batch)`` contract, sub-module names and ``state_dict`` keys as the reference,
+so ``main.py`` / ``inference.py`` can import this class instead of ``model.stage.STAGE``.  The eval / inference forward is
+eight kernel launches (csrc/*.cuh):
+
+    linear x2 (text)  ->  encoder        a_embed   (5N, Lq, 128)
+    linear x2 (text)  ->  encoder        sub_embed (N*T, Ls, 128)
+    linear x2 (vid)   ->  encoder        vid_embed (N*T, R, 128)
+    cqa_fused                            statement (N, 5, T, Lq, 128)   [S, P, U, both mixed tensors never leave the SM]
+    encoder (cls, masked max-pool)       max_statement (5N*T, 128)
+    span_head                            t_scores, spans, answer        [no device->host sync]
+
+What is not built yet raises ``NotImplementedError`` (never a silent CPU path): train-mode forward (dropout, autograd,
+``get_att_loss``), single-stream models, ``add_non_visual``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ._packing import packed
+from .cnn import DepthwiseSeparableConv
+from .context_query_attention import StructuredAttention
+from .encoder import StackedEncoder, _no_train_dropout
+from .model_utils import find_max_triples  # noqa: F401  (re-exported like the reference module does)
+
+
+def _ln_pair(ln: nn.LayerNorm):
+    return (ln.weight, ln.bias)
+
+
+class LinearWrapper(nn.Module):
+    """[LayerNorm] -> Dropout -> Linear [-> ReLU] over the last axis (reference model/stage.py:15-32); the Sequential is
+    called ``conv`` there and here, so keys are ``conv.0.*`` (LayerNorm) and ``conv.2.*`` (Linear)."""
+
+    def __init__(self, in_hsz, out_hsz, layer_norm=True, dropout=0.1, relu=True):
+        super().__init__()
+        self.relu = relu
+        self.p = dropout
+        mods = ([nn.LayerNorm(in_hsz)] if layer_norm else []) + [nn.Dropout(dropout), nn.Linear(in_hsz, out_hsz)]
+        self.conv = nn.Sequential(*mods)
+
+    def forward(self, x):
+        _no_train_dropout(self, self.p)
+        lin = self.conv[-1]
+        ln = self.conv[0] if isinstance(self.conv[0], nn.LayerNorm) else None
+        return ops.linear_fwd(x, packed(lin.weight, ops.kc_for(lin.out_features)), lin.bias, lin.out_features,
+                              ln_in=_ln_pair(ln) if ln is not None else None, relu=self.relu)
+
+
+class ConvLinear(nn.Module):
+    """[LayerNorm] -> Dropout -> DepthwiseSeparableConv (reference model/stage.py:35-52)."""
+
+    def __init__(self, in_hsz, out_hsz, kernel_size=3, layer_norm=True, dropout=0.1, relu=True):
+        super().__init__()
+        self.p = dropout
+        self.kernel_size = kernel_size
+        mods = ([nn.LayerNorm(in_hsz)] if layer_norm else []) + [
+            nn.Dropout(dropout), DepthwiseSeparableConv(in_ch=in_hsz, out_ch=out_hsz, k=kernel_size, dim=1, relu=relu)]
+        self.conv = nn.Sequential(*mods)
+
+    def forward(self, x):
+        _no_train_dropout(self, self.p)
+        dws = self.conv[-1]
+        ln = self.conv[0] if isinstance(self.conv[0], nn.LayerNorm) else None
+        return ops.encoder_block_fwd(x, None, None, [dws.conv_args(ln)], None, self.kernel_size,
+                                     conv_only=ln is None, pre_ln_only=ln is not None, relu=dws.relu)
+
+
+class STAGE(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.inference_mode = False
+        self.sub_flag = opt.sub_flag
+        self.vfeat_flag = opt.vfeat_flag
+        self.vfeat_size = opt.vfeat_size
+        self.t_iter = opt.t_iter
+        self.extra_span_length = opt.extra_span_length
+        self.add_local = opt.add_local
+        self.use_sup_att = opt.use_sup_att
+        self.num_negatives = opt.num_negatives
+        self.negative_pool_size = opt.negative_pool_size
+        self.num_hard = opt.num_hard
+        self.drop_topk = opt.drop_topk
+        self.margin = opt.margin
+        self.att_loss_type = opt.att_loss_type
+        self.scale = opt.scale
+        self.alpha = opt.alpha
+        self.dropout = opt.dropout
+        self.hsz = opt.hsz
+        self.bsz = None
+        self.num_seg = None
+        self.num_a = 5
+        self.flag_cnt = self.sub_flag + self.vfeat_flag
+        self.wd_size = opt.embedding_size
+        self.bridge_hsz = 300
+        if self.hsz != ops.HSZ:
+            raise NotImplementedError("tvqaplus_b200: kernels are specialised for hsz=128 (config.py:103 default)")
+        if getattr(opt, "add_non_visual", False):
+            raise NotImplementedError("tvqaplus_b200: add_non_visual is not built (no void vectors exist in the reference either)")
+
+        p = self.dropout
+        # Module creation order follows the reference (model/stage.py:85-186) so that default initialisation under the
+        # same torch seed yields the same weights.
+        self.bert_word_encoding_fc = nn.Sequential(nn.LayerNorm(self.wd_size), nn.Dropout(p),
+                                                   nn.Linear(self.wd_size, self.bridge_hsz), nn.ReLU(True),
+                                                   nn.LayerNorm(self.bridge_hsz))
+        if self.vfeat_flag:
+            self.vid_fc = nn.Sequential(nn.LayerNorm(self.vfeat_size), nn.Dropout(p),
+                                        nn.Linear(self.vfeat_size, self.bridge_hsz), nn.ReLU(True),
+                                        nn.LayerNorm(self.bridge_hsz))
+        if self.flag_cnt == 2:
+            self.concat_fc = nn.Sequential(nn.LayerNorm(3 * self.hsz), nn.Dropout(p), nn.Linear(3 * self.hsz, self.hsz),
+                                           nn.ReLU(True), nn.LayerNorm(self.hsz))
+        self.input_embedding = nn.Sequential(nn.Dropout(p), nn.Linear(self.bridge_hsz, self.hsz), nn.ReLU(True),
+                                             nn.LayerNorm(self.hsz))
+        self.input_encoder = StackedEncoder(n_blocks=opt.input_encoder_n_blocks, n_conv=opt.input_encoder_n_conv,
+                                            kernel_size=opt.input_encoder_kernel_size,
+                                            num_heads=opt.input_encoder_n_heads, hidden_size=self.hsz, dropout=p)
+        self.str_attn = StructuredAttention(dropout=p, scale=opt.scale, add_void=opt.add_non_visual)
+        self.c2q_down_projection = nn.Sequential(nn.LayerNorm(3 * self.hsz), nn.Dropout(p),
+                                                 nn.Linear(3 * self.hsz, self.hsz), nn.ReLU(True))
+        self.cls_encoder = StackedEncoder(n_blocks=opt.cls_encoder_n_blocks, n_conv=opt.cls_encoder_n_conv,
+                                          kernel_size=opt.cls_encoder_kernel_size, num_heads=opt.cls_encoder_n_heads,
+                                          hidden_size=self.hsz, dropout=p)
+        self.cls_projection_layers = nn.ModuleList(
+            [LinearWrapper(self.hsz, self.hsz, layer_norm=True, dropout=p, relu=True)] +
+            [ConvLinear(self.hsz, self.hsz, kernel_size=3, layer_norm=True, dropout=p, relu=True)
+             for _ in range(self.t_iter)])
+        self.temporal_scoring_st_layers = nn.ModuleList(
+            [LinearWrapper(self.hsz, 1, layer_norm=True, dropout=p, relu=False) for _ in range(self.t_iter + 1)])
+        self.temporal_scoring_ed_layers = nn.ModuleList(
+            [LinearWrapper(self.hsz, 1, layer_norm=True, dropout=p, relu=False) for _ in range(self.t_iter + 1)])
+        self.temporal_criterion = nn.CrossEntropyLoss(reduction="sum")
+        self.classifier = LinearWrapper(self.hsz * 2 if self.add_local else self.hsz, 1, layer_norm=True, dropout=p,
+                                        relu=False)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, batch):
+        if self.inference_mode:
+            return self.forward_main(batch)
+        out, att_loss, att_predictions, temporal_loss, temporal_predictions, _ = self.forward_main(batch)
+        return out, att_loss, att_predictions, temporal_loss, temporal_predictions
+
+    def forward_main(self, batch):
+        """batch: the edict ``prepare_inputs`` builds (tvqa_dataset.py:631-688); see the reference docstring
+        (model/stage.py:200-219).  Eval returns ``(out, att_loss, att_predictions, temporal_loss, softmax(t_scores),
+        other_outputs)``; ``inference_mode`` returns the prediction dict (model/stage.py:297-312)."""
+        if self.training:
+            raise NotImplementedError(
+                "tvqaplus_b200: only the eval / inference forward is built (no dropout, autograd or attention loss yet); "
+                "call model.eval()")
+        if self.flag_cnt != 2:
+            raise NotImplementedError("tvqaplus_b200: single-stream models (sub-only / vfeat-only) are not built yet")
+        with torch.no_grad():
+            return self._forward_eval(batch)
+
+    def _text_fc(self, x):
+        fc, emb = self.bert_word_encoding_fc, self.input_embedding
+        h = ops.linear_fwd(x, packed(fc[2].weight, 32), fc[2].bias, self.bridge_hsz, ln_in=_ln_pair(fc[0]), relu=True,
+                           ln_out=_ln_pair(fc[4]))
+        return ops.linear_fwd(h, packed(emb[1].weight, 64), emb[1].bias, self.hsz, relu=True, ln_out=_ln_pair(emb[3]))
+
+    def _vid_fc(self, x):
+        fc, emb = self.vid_fc, self.input_embedding
+        h = ops.linear_fwd(x, packed(fc[2].weight, 32), fc[2].bias, self.bridge_hsz, ln_in=_ln_pair(fc[0]), relu=True,
+                           ln_out=_ln_pair(fc[4]), l2norm_in=True)  # F.normalize of model/stage.py:256 fused in
+        return ops.linear_fwd(h, packed(emb[1].weight, 64), emb[1].bias, self.hsz, relu=True, ln_out=_ln_pair(emb[3]))
+
+    @classmethod
+    def base_encoder(cls, data, data_mask, init_encoder, downsize_encoder, input_encoder):
+        """Raw features -> (N, L, hsz) embeddings; ``init_encoder`` / ``downsize_encoder`` are the bound fused
+        projections (``_text_fc`` / ``_vid_fc`` already contain ``input_embedding``)."""
+        h = init_encoder(data)
+        if downsize_encoder is not None:
+            h = downsize_encoder(h)
+        return input_encoder(h, data_mask)
+
+    def _cqa_weights(self):
+        c2q, cat = self.c2q_down_projection, self.concat_fc
+        return dict(c2q_ln_g=c2q[0].weight, c2q_ln_b=c2q[0].bias, c2q_w_packed=packed(c2q[2].weight, 32), c2q_b=c2q[2].bias,
+                    cat_ln_g=cat[0].weight, cat_ln_b=cat[0].bias, cat_w_packed=packed(cat[2].weight, 32), cat_b=cat[2].bias,
+                    cat_out_ln_g=cat[4].weight, cat_out_ln_b=cat[4].bias)
+
+    def _head_weights(self):
+        w = {}
+        for key, mod in (("proj", self.cls_projection_layers[0]), ("st", self.temporal_scoring_st_layers[0]),
+                         ("ed", self.temporal_scoring_ed_layers[0]), ("cls", self.classifier)):
+            w[key + "_ln_g"], w[key + "_ln_b"] = mod.conv[0].weight, mod.conv[0].bias
+            w[key + "_w"], w[key + "_b"] = mod.conv[2].weight, mod.conv[2].bias
+        return w
+
+    def _forward_eval(self, batch):
+        self.bsz = bsz = len(batch.qid)
+        num_a, hsz = self.num_a, self.hsz
+        qas_mask = batch.qas_mask.float()
+        a_embed = self.base_encoder(batch.qas_bert.view(bsz * num_a, -1, self.wd_size), qas_mask.view(bsz * num_a, -1),
+                                    self._text_fc, None, self.input_encoder)
+        Lq = a_embed.shape[1]
+        a_embed = a_embed.view(bsz, num_a, Lq, hsz)
+
+        T, Ls = batch.sub_bert.shape[1:3]
+        sub_mask = batch.sub_mask.float()
+        sub_embed = self.base_encoder(batch.sub_bert.view(bsz * T, Ls, -1), sub_mask.view(bsz * T, Ls),
+                                      self._text_fc, None, self.input_encoder).view(bsz, T, Ls, hsz)
+        R = batch.vid.shape[2]
+        vid_mask = batch.vid_mask.float()
+        vid_embed = self.base_encoder(batch.vid.view(bsz * T, R, -1), vid_mask.view(bsz * T, R),
+                                      self._vid_fc, None, self.input_encoder).view(bsz, T, R, hsz)
+
+        need_raw = self.inference_mode
+        cq = ops.cqa_fused_fwd(a_embed, qas_mask.view(bsz, num_a, Lq), sub_embed, sub_mask, vid_embed, vid_mask,
+                               self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else ())
+        other_outputs = {"vid_raw_s": cq.get("vid_raw_s")}
+        out, target, t_scores, t_probs = self.classfier_head_multi_proposal(
+            cq["statement"], cq["statement_mask"], batch.target, batch.ts_label, batch.ts_label_mask,
+            extra_span_length=self.extra_span_length)
+        other_outputs["temporal_scores"] = t_scores
+
+        if self.inference_mode:
+            return {"answer": out, "t_scores": t_probs,
+                    "att_predictions": self.get_att_prediction(
+                        scores=other_outputs["vid_raw_s"], object_vocab=batch.eval_object_word_ids, words=batch.qas,
+                        vid_names=batch.vid_name, qids=batch.qid, img_indices=batch.image_indices, boxes=batch.boxes,
+                        start_indices=batch.anno_st_idx) if self.vfeat_flag else None}
+        temporal_loss = self.get_ts_loss(t_scores, batch.ts_label, batch.target)
+        return out, 0, None, temporal_loss, t_probs, other_outputs
+
+    # ------------------------------------------------------------------------------------------------ heads
+    def classfier_head_multi_proposal(self, statement, statement_mask, targets, ts_labels, ts_labels_mask,
+                                      max_num_proposal=1, ce_prob_thd=0.01, iou_thd=0.5, extra_span_length=3):
+        """statement (N,5,Li,Lqa,D), statement_mask (N,5,Li,Lqa) -> answer scores (N,5), targets, masked span logits
+        (N,5,Li,2) [+ their softmax over Li].  cls_encoder + masked max-pool is one kernel, everything after it another
+        (eval branch of the reference, model/stage.py:484-537 with get_proposals :439-467)."""
+        bsz, num_a, num_img, num_words = statement_mask.shape
+        max_statement = self.cls_encoder(statement.view(bsz * num_a * num_img, num_words, -1),
+                                         statement_mask.view(bsz * num_a * num_img, num_words), pool=True)
+        head = ops.span_head_fwd(max_statement.view(bsz * num_a, num_img, -1), statement_mask, ts_labels_mask.float(),
+                                 self._head_weights(), add_local=self.add_local, extra_span_length=extra_span_length)
+        self._last_spans = head["spans"]
+        return head["answer"], targets, head["t_scores"], head["t_probs"]
+
+    def residual_temporal_predictor(self, layer_idx, input_tensor):
+        """(N, L, D) -> (x + proj(x), cat[st, ed] (N, L, 2)) — module-level form of model/stage.py:469-482."""
+        x = input_tensor + self.cls_projection_layers[layer_idx](input_tensor)
+        st = self.temporal_scoring_st_layers[layer_idx](x)
+        ed = self.temporal_scoring_ed_layers[layer_idx](x)
+        return x, torch.cat([st, ed], dim=2)
+
+    def qa_ctx_attention(self, qa_embed, ctx_embed, qa_mask, ctx_mask, noun_mask, non_visual_vectors):
+        """One stream of model/stage.py:365-387 on its own: (mixed, mixed_mask, raw_s, s_normalized)."""
+        if noun_mask is not None or non_visual_vectors is not None:
+            raise NotImplementedError("tvqaplus_b200: noun_mask / non_visual_vectors are not built")
+        u_a, raw_s, s_mask, s_norm = self.str_attn(qa_embed, ctx_embed, qa_mask, ctx_mask)
+        num_img = ctx_mask.shape[2]
+        qa_rep = qa_embed.expand(-1, -1, num_img, -1, -1)
+        c2q = self.c2q_down_projection
+        mixed = ops.linear_fwd(torch.cat([qa_rep, u_a, qa_rep * u_a], dim=-1), packed(c2q[2].weight, 64), c2q[2].bias,
+                               self.hsz, ln_in=_ln_pair(c2q[0]), relu=True)
+        return mixed, (s_mask.sum(-1) != 0).float(), raw_s, s_norm
+
+    def get_ts_loss(self, temporal_scores, ts_labels, answer_indices):
+        """Mean of the start / end cross-entropies (sum over examples) on the ground-truth answer's row
+        (model/stage.py:539-555)."""
+        rows = torch.arange(len(answer_indices), dtype=torch.long, device=temporal_scores.device)
+        ca = temporal_scores[rows, answer_indices.to(temporal_scores.device)]
+        st = F.cross_entropy(ca[:, :, 0], ts_labels["st"].to(ca.device), reduction="sum")
+        ed = F.cross_entropy(ca[:, :, 1], ts_labels["ed"].to(ca.device), reduction="sum")
+        return (st + ed) / 2.0
+
+    # ------------------------------------------------------------------------------------------------ inference post-processing
+    def get_att_prediction(self, scores, object_vocab, words, vid_names, qids, img_indices, boxes, start_indices,
+                           score_thd=0.2):
+        """Per (question, answer, annotated frame, object word): regions whose cosine score >= ``score_thd``, ascending
+        (model/stage.py:748-806).  ONE device->host copy of ``scores`` instead of one per word."""
+        if not self.vfeat_flag or scores is None or boxes is None:
+            return None
+        s = scores.detach().cpu().numpy()
+        w = words.cpu().numpy()
+        vocab = set(int(v) for v in object_vocab)
+        preds = []
+        for b in range(len(s)):
+            st0 = start_indices[b]
+            per_q = {}
+            for a in range(self.num_a):
+                cur = []
+                obj_pos = [i for i, wid in enumerate(w[b, a].tolist()) if wid in vocab]
+                for local_i, img_boxes in enumerate(boxes[b]):
+                    gi = local_i + st0
+                    for wi in obj_pos:
+                        row = s[b, a, gi, wi]
+                        keep = np.nonzero(row >= score_thd)[0]
+                        order = keep[np.argsort(row[keep])]
+                        cur.append({"pred": [float(row[i]) for i in order], "bbox": [img_boxes[i] for i in order],
+                                    "word": int(w[b, a, wi]), "qid": int(qids[b]), "vid_name": vid_names[b],
+                                    "img_idx": img_indices[b][gi]})
+                per_q[a] = cur
+            preds.append(per_q)
+        return preds

@@ -66,32 +66,42 @@ def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
     return a
 
 
-def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: torch.Tensor, convs: Sequence[dict],
-                      final_ln, ksize: int, *, n_heads: int = 0, attn: Optional[dict] = None,
-                      out_mode: int = 0) -> torch.Tensor:
+def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optional[torch.Tensor], convs: Sequence[dict],
+                      final_ln, ksize: int, *, n_heads: int = 0, attn: Optional[dict] = None, out_mode: int = 0,
+                      conv_only: bool = False, pre_ln_only: bool = False, relu: bool = True,
+                      skip_final_ln: bool = False) -> torch.Tensor:
     """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
-    pw_packed, pw_b); final_ln = (g, b).  out_mode 1 returns the masked max-pool (n_seq, 128)."""
+    pw_packed, pw_b); final_ln = (g, b).  out_mode 1 returns the masked max-pool (n_seq, 128).
+
+    ``conv_only``: just the depthwise-separable convs (no PE / LayerNorm / residual) — DepthwiseSeparableConv;
+    ``pre_ln_only``: LayerNorm -> conv without PE / residual / final LN — ConvLinear."""
     x = _f32(x)
     n_seq, L, D = x.shape
     if D != HSZ:
         raise RuntimeError("tvqaplus_b200: hidden size %d != %d" % (D, HSZ))
-    if pe.shape[0] < L:
+    flags = 0
+    if conv_only or pre_ln_only:
+        flags |= _lib.ENC_NO_PE | _lib.ENC_NO_RESIDUAL | _lib.ENC_NO_FINAL_LN
+    if not relu:
+        flags |= _lib.ENC_NO_RELU
+    if skip_final_ln:
+        flags |= _lib.ENC_NO_FINAL_LN
+    if not (flags & _lib.ENC_NO_PE) and pe.shape[0] < L:
         raise RuntimeError("tvqaplus_b200: sequence length %d exceeds the position-encoding table (%d)" % (L, pe.shape[0]))
     y = torch.empty((n_seq, L, D) if out_mode == 0 else (n_seq, D), dtype=torch.float32, device=x.device)
-    keep = [_f32(c[k]) for c in convs for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")]  # keep contiguous copies alive
-    it = iter(keep)
-    cols = {k: [] for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")}
-    for _ in convs:
-        for k in ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b"):
-            cols[k].append(ptr(next(it)))
+    names = ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")
+    keep = [[_f32(c[k]) if c.get(k) is not None else None for k in names] for c in convs]  # keep contiguous copies alive
+    cols = {k: [ptr(row[i]) for row in keep] for i, k in enumerate(names)}
     mask_c = _f32(mask) if mask is not None else None
+    pe_c = _f32(pe) if pe is not None else None
+    fin = (_f32(final_ln[0]), _f32(final_ln[1])) if final_ln is not None else (None, None)
     a = _lib.EncoderArgs(n_seq=n_seq, L=L, n_conv=len(convs), ksize=ksize, n_heads=n_heads, out_mode=out_mode,
-                         x=ptr(x), mask=ptr(mask_c), pe=ptr(_f32(pe)),
+                         flags=flags, x=ptr(x), mask=ptr(mask_c), pe=ptr(pe_c),
                          ln_g=_arr(cols["ln_g"]), ln_b=_arr(cols["ln_b"]), dw_w=_arr(cols["dw_w"]),
                          dw_b=_arr(cols["dw_b"]), pw_packed=_arr([ptr(c["pw_packed"]) for c in convs]),
                          pw_b=_arr(cols["pw_b"]),
                          attn_ln_g=None, attn_ln_b=None, attn_w_packed=_arr([], 4), attn_b=_arr([], 4),
-                         final_ln_g=ptr(_f32(final_ln[0])), final_ln_b=ptr(_f32(final_ln[1])), y=ptr(y), workspace=None)
+                         final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y), workspace=None)
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
     return y
 
@@ -184,3 +194,18 @@ def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     check(lib().stage_mask_logits(ptr(x), ptr(mask.contiguous()), outer, inner, ptr(y), current_stream()),
           "stage_mask_logits")
     return y
+
+
+def attention_only_fwd(c_embed, c_mask, q_embed, q_mask, scale: float) -> dict:
+    """StructuredAttention alone for one stream: C (N,5,Lq,128), Q (N,T,Lr,128) -> att (N,5,T,Lq,128),
+    raw_s / norm_s (N,5,T,Lq,Lr).  Runs the fused kernel with the query tensor in the `sub` slot and stops after
+    U = P.Q (no projection weights needed)."""
+    raise NotImplementedError("tvqaplus_b200: attention-only mode of the CQA kernel is not built yet")
+
+
+def mha_fwd(x, mask, attn: dict, n_heads: int, residual: bool = False):
+    raise NotImplementedError("tvqaplus_b200: the multi-head self-attention kernel (n_heads > 0) is not built yet")
+
+
+def layernorm_pool_fwd(x, mask, ln, pool: bool = False):
+    raise NotImplementedError("tvqaplus_b200: the multi-head self-attention kernel (n_heads > 0) is not built yet")
