@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — QA-examples/s of the STAGE forward hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one eval forward (`--add_local`, both streams) over one synthetic batch of BASELINE configs[1]
+(batch 32, T=300 frames, R=20 regions, Lq=Ls=100 tokens, H=128, dense masks = the throughput shape of SURVEY.md §8d).
+Prints ONE JSON line (rank 0):
+  value     examples/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the public module call with HOST (pinned) inputs: every step uploads its inputs
+            host->device and reads answer + span probabilities back, copies inside the timed region (double-buffered
+            on a copy stream)
+  roofline  the dominant kernel (cqa_kernel) timed live on its own stream: algorithmic FLOPs / duration vs the measured
+            tensor peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (same torch ops as the reference) on the host cores, bounded sample
+`--impl reference` times only that CPU port (all host threads), one example per step.
+Inputs (3.3 GB / batch) are far larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "QA-examples/sec forward (synthetic T=300,R=20,L=100,H=128)"
+SHAPE = dict(T=300, R=20, Lq=100, Ls=100)
+H = 128
+
+
+def alg_flops_cqa(n_ex, T, R, Lq, Ls):
+    """Algorithmic FLOPs of a7+a8+a9: S and U for both streams + three 384->128 projections."""
+    n_st = 5 * T * Lq
+    return n_ex * (4 * H * n_st * (Ls + R) + 3 * (2 * 3 * H * H) * n_st)
+
+
+def alg_flops_total(n_ex, T, R, Lq, Ls, k_in=7, k_cls=5, n_conv=2):
+    n_qa, n_sub, n_vid, n_st = 5 * Lq, T * Ls, T * R, 5 * T * Lq
+    f = 2 * 768 * 300 * (n_qa + n_sub) + 2 * 300 * 300 * n_vid + 2 * 300 * H * (n_qa + n_sub + n_vid)
+    f += n_conv * (2 * k_in * H + 2 * H * H) * (n_qa + n_sub + n_vid)
+    f += 4 * H * n_st * (Ls + R) + 3 * (2 * 3 * H * H) * n_st + n_conv * (2 * k_cls * H + 2 * H * H) * n_st
+    f += (2 * H * H + 4 * H) * 5 * T
+    return n_ex * f
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", 1416.1)), hbm=float(d.get("hbm_gbs", 6458.1)), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def make_host_batch(N, pin):
+    """Dense synthetic batch of configs[1] on the host (pinned for the e2e leg)."""
+    from oracle import stage_oracle as O
+    T, R, Lq, Ls = SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"]
+    g = torch.Generator().manual_seed(2018)
+
+    def rnd(*shape):
+        t = torch.empty(*shape, pin_memory=pin)
+        t.normal_(generator=g)
+        return t
+
+    b = O.Batch(qid=list(range(N)), vid_name=["syn"] * N, qas_bert=rnd(N, 5, Lq, 768), sub_bert=rnd(N, T, Ls, 768),
+                vid=rnd(N, T, R, 300), qas_mask=torch.ones(N, 5, Lq), sub_mask=torch.ones(N, T, Ls),
+                vid_mask=torch.ones(N, T, R), ts_label_mask=torch.ones(N, T), target=torch.randint(0, 5, (N,), generator=g),
+                ts_label={"st": torch.randint(0, T // 2, (N,), generator=g), "ed": torch.randint(T // 2, T, (N,), generator=g)},
+                qas=torch.ones(N, 5, Lq, dtype=torch.long), att_labels=None, anno_st_idx=[0] * N, q_l=[Lq // 2] * N,
+                image_indices=None, boxes=None, use_hard_negatives=False, eval_object_word_ids=None)
+    if pin:
+        for k in ("qas_mask", "sub_mask", "vid_mask", "ts_label_mask"):
+            b[k] = b[k].pin_memory()
+    return b
+
+
+TENSOR_KEYS = ("qas_bert", "sub_bert", "vid", "qas_mask", "sub_mask", "vid_mask", "ts_label_mask", "target")
+
+
+def to_device(b, dev, non_blocking=False, into=None):
+    from oracle import stage_oracle as O
+    out = O.Batch(b)
+    for k in TENSOR_KEYS:
+        if into is not None:
+            into[k].copy_(b[k], non_blocking=non_blocking)
+            out[k] = into[k]
+        else:
+            out[k] = b[k].to(dev, non_blocking=non_blocking)
+    out["ts_label"] = {k: v.to(dev) for k, v in b["ts_label"].items()} if into is None else into["ts_label"]
+    return out
+
+
+def cpu_port(n_ex, steps, warmup, threads):
+    """Times the CPU oracle port (torch fp32 ops in the reference's order) — the reference's own CPU path restated."""
+    from oracle import stage_oracle as O
+    from tvqaplus_b200.model import STAGE
+    torch.set_num_threads(threads)
+    opt = O.default_opt()
+    torch.manual_seed(2018)
+    sd = STAGE(opt).state_dict()
+    batch = O.make_synthetic_batch(n_ex, SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"], seed=2018, dense=True)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.stage_forward(sd, opt, batch)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="examples per GPU per step (configs[1]: 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    config = dict(workload="configs[1]: eval forward, add_local, sub+vfeat, batch=%d/GPU, T=300, R=20, Lq=Ls=100, H=128, dense masks"
+                  % args.batch, global_batch=args.batch * world, per_gpu_batch=args.batch, parallelism="dp%d (replicas, no collective)" % world,
+                  l2="inputs (3.3 GB/batch) exceed the 126 MB L2; no flush needed")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        W = max(1, min(args.warmup, 2))
+        times = cpu_port(1, args.steps, W, cores)
+        v = 1.0 / statistics.mean(times)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "examples/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": W, "ms_per_step": 1e3 * statistics.mean(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": dict(config, sample="1 example of the configs[1] shape per step"),
+                          "cpu_baseline": {"value": v, "unit": "examples/s", "cores": cores, "kind": "port",
+                                           "sample": "CPU oracle port (torch fp32, reference op order), 1 example/step, %d steps" % args.steps},
+                          "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    from oracle import stage_oracle as O
+    from tvqaplus_b200 import _lib, ops
+    from tvqaplus_b200.model import STAGE
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the STAGE kernels)")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.lib()
+    opt = O.default_opt()
+    torch.manual_seed(2018)
+    model = STAGE(opt).to(dev).eval()
+    N = args.batch
+    host = make_host_batch(N, pin=not args.no_e2e)
+    dbatch = to_device(host, dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for _ in range(args.warmup):
+        model(dbatch)
+    ops.LAUNCHES = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            out = model(dbatch)
+        e1.record()
+        barrier()
+    launches = ops.LAUNCHES
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    _lib.check_device_error()
+    value = N * world * args.steps / (ms_total * 1e-3)
+
+    # ---------------------------------------------------------------- end-to-end (host buffers, copies inside)
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        main_stream = torch.cuda.current_stream()
+        bufs = [{k: torch.empty_like(dbatch[k]) for k in TENSOR_KEYS} for _ in range(2)]
+        for b in bufs:
+            b["ts_label"] = dbatch["ts_label"]
+        res_host = [dict(a=torch.empty(N, 5).pin_memory(), p=torch.empty(N, 5, SHAPE["T"], 2).pin_memory()) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        h2d = sum(host[k].numel() * host[k].element_size() for k in TENSOR_KEYS)
+        d2h = res_host[0]["a"].numel() * 4 + res_host[0]["p"].numel() * 4
+
+        def run_e2e(steps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(copy_stream):
+                s0.record()
+                to_device(host, dev, non_blocking=True, into=bufs[0])
+                ready[0].record()
+            for i in range(steps):
+                cur = i % 2
+                if i + 1 < steps:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(freed[1 - cur])
+                        to_device(host, dev, non_blocking=True, into=bufs[1 - cur])
+                        ready[1 - cur].record()
+                main_stream.wait_event(ready[cur])
+                b = O.Batch(host)
+                b.update(bufs[cur])
+                ans, _, _, _, probs = model(b)
+                res_host[cur]["a"].copy_(ans, non_blocking=True)
+                res_host[cur]["p"].copy_(probs, non_blocking=True)
+                freed[cur].record()
+            s1.record()
+            torch.cuda.synchronize()
+            return s0.elapsed_time(s1)
+
+        run_e2e(2)
+        barrier()
+        ms_e2e = max_over_ranks(run_e2e(args.steps))
+        barrier()
+        e2e = {"value": N * world * args.steps / (ms_e2e * 1e-3), "unit": "examples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "note": "pinned host inputs, double-buffered H2D on a copy stream, answer + span probs read back every step"}
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0 timing, own stream)
+    T, R, Lq, Ls = SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"]
+    with torch.no_grad():
+        a_embed = model.base_encoder(dbatch.qas_bert.view(N * 5, Lq, 768), dbatch.qas_mask.view(N * 5, Lq), model._text_fc, None, model.input_encoder).view(N, 5, Lq, H)
+        sub_embed = model.base_encoder(dbatch.sub_bert.view(N * T, Ls, 768), dbatch.sub_mask.view(N * T, Ls), model._text_fc, None, model.input_encoder).view(N, T, Ls, H)
+        vid_embed = model.base_encoder(dbatch.vid.view(N * T, R, 300), dbatch.vid_mask.view(N * T, R), model._vid_fc, None, model.input_encoder).view(N, T, R, H)
+        w = model._cqa_weights()
+        ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        k0.record()
+        for _ in range(reps):
+            ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale)
+        k1.record()
+        torch.cuda.synchronize()
+    cqa_ms = k0.elapsed_time(k1) / reps
+    pk = peaks()
+    achieved = alg_flops_cqa(N, T, R, Lq, Ls) / (cqa_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "cqa_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "cqa_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops"], "traffic": traffic, "ms_per_launch": cqa_ms, "peak_source": pk["src"] + " bf16 sustained",
+                "note": "algorithmic FLOPs (a7+a8+a9, %.1f GFLOP/example); executed tensor FLOPs are 3x (split-fp16) on 128-row tiles"
+                        % (alg_flops_cqa(1, T, R, Lq, Ls) / 1e9),
+                "step_share": cqa_ms / (ms_total / args.steps)}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times = cpu_port(2, 3, 1, cores)
+        cpu = {"value": 2.0 / statistics.mean(times), "unit": "examples/s", "cores": cores, "kind": "port",
+               "sample": "CPU oracle port (torch fp32, reference op order), batch of 2 configs[1] examples, 1 warm-up + 3 timed"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (split-fp16 x3 tensor-core GEMMs, fp32 accumulate)", "data": "synthetic",
+                "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu,
+                "alg_tflops_whole_path": alg_flops_total(N * world, T, R, Lq, Ls) * args.steps / (ms_total * 1e-3) / 1e12}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

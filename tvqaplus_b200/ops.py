@@ -14,6 +14,12 @@ from . import _lib
 from ._lib import check, current_stream, lib, ptr
 
 HSZ = 128
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -39,6 +45,7 @@ def pack_weight(w: torch.Tensor, kc: Optional[int] = None) -> torch.Tensor:
         raise RuntimeError("tvqaplus_b200: unsupported weight shape %s" % (tuple(w.shape),))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     check(lib().stage_pack_weight(ptr(w), n, k, kc, ptr(out), current_stream()), "stage_pack_weight")
+    _count()
     out._stage_kc = kc  # type: ignore[attr-defined]
     return out
 
@@ -56,6 +63,7 @@ def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, n: i
                         ln_out_g=ptr(_f32(ln_out[0])) if ln_out else None,
                         ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y))
     check(lib().stage_linear_fwd(C.byref(a), current_stream()), "stage_linear_fwd")
+    _count()
     return y
 
 
@@ -103,6 +111,7 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
                          attn_ln_g=None, attn_ln_b=None, attn_w_packed=_arr([], 4), attn_b=_arr([], 4),
                          final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y), workspace=None)
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
+    _count()
     return y
 
 
@@ -140,6 +149,7 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
                      statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
                      **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
+    _count()
     return out
 
 
@@ -166,6 +176,7 @@ def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local:
                       t_scores=ptr(o["t_scores"]), t_probs=ptr(o["t_probs"]), spans=ptr(o["spans"]),
                       span_conf=ptr(o["span_conf"]), answer=ptr(o["answer"]), workspace=ptr(o["encoded"]))
     check(lib().stage_span_head_fwd(C.byref(a), current_stream()), "stage_span_head_fwd")
+    _count()
     return o
 
 
@@ -177,6 +188,7 @@ def find_max_span(p_st: torch.Tensor, p_ed: torch.Tensor):
     conf = torch.empty(rows, dtype=torch.float32, device=p_st.device)
     check(lib().stage_find_max_span(ptr(p_st), ptr(p_ed), rows, T, ptr(spans), ptr(conf), current_stream()),
           "stage_find_max_span")
+    _count()
     return spans, conf
 
 
@@ -193,6 +205,7 @@ def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     y = torch.empty_like(x)
     check(lib().stage_mask_logits(ptr(x), ptr(mask.contiguous()), outer, inner, ptr(y), current_stream()),
           "stage_mask_logits")
+    _count()
     return y
 
 
