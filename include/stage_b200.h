@@ -111,7 +111,15 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream);
  * StructuredAttention (model/context_query_attention.py:35-101) for both streams, qa_ctx_attention +
  * c2q_down_projection (model/stage.py:365-387,133-138) and concat_fc (model/stage.py:107-113,276-279):
  * one CTA per (example, frame), looping over the 5 answers; S, P, U, both mixed tensors stay in TMEM / smem.
- * Lq <= 128, Ls <= 112, R <= 32. */
+ * Lq <= 128, Ls <= 112, R <= 48.
+ *
+ * Weights are prepared once per parameter version with stage_cqa_prepare_weights (LayerNorm(384) folded into the
+ * Linear that follows it, split-fp16 images); the forward needs a caller-owned workspace for the operand images. */
+size_t stage_cqa_weight_blob_bytes(void);
+int stage_cqa_prepare_weights(const float* c2q_ln_g, const float* c2q_ln_b, const float* c2q_w /*[128,384]*/,
+                              const float* c2q_b, const float* cat_ln_g, const float* cat_ln_b,
+                              const float* cat_w /*[128,384]*/, const float* cat_b, void* wblob, void* stream);
+size_t stage_cqa_workspace_bytes(int n, int t, int lq);
 typedef struct {
   int n, t, lq, ls, r;
   float scale;                 /* opt.scale (config.py:67) */
@@ -121,16 +129,10 @@ typedef struct {
   const float* sub_mask;       /* [n,t,ls] */
   const float* vid_embed;      /* [n,t,r,128] */
   const float* vid_mask;       /* [n,t,r] */
-  const float* c2q_ln_g;       /* [384] */
-  const float* c2q_ln_b;
-  const void* c2q_w_packed;    /* [128,384], kc=32 */
-  const float* c2q_b;
-  const float* cat_ln_g;       /* [384] */
-  const float* cat_ln_b;
-  const void* cat_w_packed;    /* [128,384], kc=32 */
-  const float* cat_b;
-  const float* cat_out_ln_g;   /* [128] */
+  const void* wblob;           /* stage_cqa_prepare_weights output */
+  const float* cat_out_ln_g;   /* [128] concat_fc.4 */
   const float* cat_out_ln_b;
+  void* workspace;             /* stage_cqa_workspace_bytes(n, t, lq) bytes, 128-byte aligned */
   float* statement;            /* [n,5,t,lq,128] */
   float* statement_mask;       /* [n,5,t,lq]  (the vid mixed_mask, model/stage.py:280-282) */
   float* vid_raw_s;            /* optional [n,5,t,lq,r] (other_outputs["vid_raw_s"], model/stage.py:273) */

@@ -50,12 +50,12 @@ def oracle(a, am, s, sm, v, vm, sd, scale):
 
 def run_gpu(a, am, s, sm, v, vm, sd, scale, want):
     dev = torch.device("cuda:0")
-    w = dict(c2q_ln_g=sd["c2q_down_projection.0.weight"].to(dev), c2q_ln_b=sd["c2q_down_projection.0.bias"].to(dev),
-             c2q_w_packed=ops.pack_weight(sd["c2q_down_projection.2.weight"].to(dev), 32),
-             c2q_b=sd["c2q_down_projection.2.bias"].to(dev),
-             cat_ln_g=sd["concat_fc.0.weight"].to(dev), cat_ln_b=sd["concat_fc.0.bias"].to(dev),
-             cat_w_packed=ops.pack_weight(sd["concat_fc.2.weight"].to(dev), 32), cat_b=sd["concat_fc.2.bias"].to(dev),
-             cat_out_ln_g=sd["concat_fc.4.weight"].to(dev), cat_out_ln_b=sd["concat_fc.4.bias"].to(dev))
+    d = {k: v.to(dev) for k, v in sd.items()}
+    w = dict(wblob=ops.cqa_prepare_weights(d["c2q_down_projection.0.weight"], d["c2q_down_projection.0.bias"],
+                                           d["c2q_down_projection.2.weight"], d["c2q_down_projection.2.bias"],
+                                           d["concat_fc.0.weight"], d["concat_fc.0.bias"], d["concat_fc.2.weight"],
+                                           d["concat_fc.2.bias"]),
+             cat_out_ln_g=d["concat_fc.4.weight"], cat_out_ln_b=d["concat_fc.4.bias"])
     out = ops.cqa_fused_fwd(a.to(dev), am.to(dev), s.to(dev), sm.to(dev), v.to(dev), vm.to(dev), w, scale, want=want)
     torch.cuda.synchronize()
     _lib.check_device_error()

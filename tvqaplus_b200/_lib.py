@@ -35,9 +35,7 @@ class EncoderArgs(C.Structure):
 class CqaArgs(C.Structure):
     _fields_ = [("n", C.c_int), ("t", C.c_int), ("lq", C.c_int), ("ls", C.c_int), ("r", C.c_int), ("scale", C.c_float),
                 ("a_embed", _f), ("a_mask", _f), ("sub_embed", _f), ("sub_mask", _f), ("vid_embed", _f), ("vid_mask", _f),
-                ("c2q_ln_g", _f), ("c2q_ln_b", _f), ("c2q_w_packed", _f), ("c2q_b", _f),
-                ("cat_ln_g", _f), ("cat_ln_b", _f), ("cat_w_packed", _f), ("cat_b", _f),
-                ("cat_out_ln_g", _f), ("cat_out_ln_b", _f),
+                ("wblob", _f), ("cat_out_ln_g", _f), ("cat_out_ln_b", _f), ("workspace", _f),
                 ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
                 ("vid_norm_s", _f), ("sub_norm_s", _f), ("att_vid", _f), ("att_sub", _f),
                 ("mixed_vid", _f), ("mixed_sub", _f)]
@@ -70,6 +68,9 @@ SYMBOLS = {
     "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "stage_encoder_block_fwd": (C.c_int, [C.POINTER(EncoderArgs), C.c_void_p]),
+    "stage_cqa_weight_blob_bytes": (C.c_size_t, []),
+    "stage_cqa_prepare_weights": (C.c_int, [C.c_void_p] * 10),
+    "stage_cqa_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "stage_cqa_fused_fwd": (C.c_int, [C.POINTER(CqaArgs), C.c_void_p]),
     "stage_span_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
     "stage_find_max_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

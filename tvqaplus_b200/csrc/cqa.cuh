@@ -5,14 +5,20 @@
 //   mix = relu(LN384([a, U, a*U]) Wc^T + bc)     (both streams)    qa_ctx_attention / c2q_down_proj (stage.py:381-386)
 //   out = LN128(relu(LN384([ms, mv, ms*mv]) Wf^T + bf))            concat_fc                        (stage.py:107-113)
 //
+// LayerNorm(384) is folded into the GEMM that follows it:
+//        LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * cs) + cb ,  cs = (W*gamma) 1,  cb = W beta + b
+// so the A operand is the RAW [p, q, p*q] row (one pass over TMEM, statistics accumulated on the fly), and the
+// frame-invariant third of c2q, Za = a (Wc*gamma)[:, :128]^T, is computed once per (example, answer) and pre-loaded into
+// the accumulator with tcgen05.st (executed FLOPs of c2q drop by a third; algorithmic FLOPs are still quoted in full).
+//
 // Everything between the fp32 encoder outputs and the statement tile stays on chip:
-//   shared memory: split-fp16 images of the frame's ctx tiles (read K-major for S and MN-major for U), the answer
-//                  tile, P, and the A / W pipelines of the three 384->128 GEMMs (weights streamed by cp.async.bulk)
+//   shared memory: split-fp16 images of the frame's ctx tiles (one cp.async.bulk per frame; read K-major for S and
+//                  MN-major for U), the answer image (one bulk copy per tile), P, and the A / W pipelines of the GEMMs
 //   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator, T1 = S_vid -> c2q(vid), T2 = U_sub -> concat accumulator,
 //                  T3 = U_vid
-// Warp roles (288 threads): warps 0-7 compute (thread = row, warp/4 = column half), warp 8 = MMA issue + weight copies.
+// Warp roles (288 threads): warps 0-7 compute (thread = row, warp/4 = column half), warp 8 = MMA issue + all bulk copies.
 //
-// Algorithmic work per (answer, frame) tile with Lq rows: 4*128*Lq*(Ls+R) + 3*(2*384*128)*Lq FLOP (x3 executed).
+// Algorithmic work per (answer, frame) tile with Lq rows: 4*128*Lq*(Ls+R) + 3*(2*384*128)*Lq FLOP.
 #pragma once
 #include "umma.cuh"
 
@@ -20,137 +26,197 @@ namespace stg {
 
 struct CqaCfg {
   static constexpr int LS_MAX = 112, R_MAX = 48;
-  static constexpr uint32_t LBO_CS = LS_MAX * 16u + 16u;   // 1808
-  static constexpr uint32_t CS_PART = 16u * LBO_CS;        // 28928
-  static constexpr uint32_t LBO_CV = R_MAX * 16u + 16u;    // 784
-  static constexpr uint32_t CV_PART = 16u * LBO_CV;        // 12544
-  static constexpr uint32_t LBO_A = 128u * 16u + 16u;      // 2064: every thread-per-row / warp-per-row A image
-  static constexpr uint32_t AQ_PART = 16u * LBO_A;         // 33024
+  static constexpr uint32_t LBO_CS = LS_MAX * 16u + 16u;     // 1808
+  static constexpr uint32_t CS_PART = 16u * LBO_CS;          // 28928
+  static constexpr uint32_t LBO_CV = R_MAX * 16u + 16u;      // 784
+  static constexpr uint32_t CV_PART = 16u * LBO_CV;          // 12544
+  static constexpr uint32_t LBO_A = 128u * 16u + 16u;        // 2064: every thread-per-row / warp-per-row A image
+  static constexpr uint32_t AQ_PART = 16u * LBO_A;           // 33024
   static constexpr uint32_t PS_PART = (LS_MAX / 8) * LBO_A;  // 28896
   static constexpr uint32_t PV_PART = (R_MAX / 8) * LBO_A;   // 12384
-  static constexpr uint32_t AST_PART = 4u * LBO_A;         // 8256: one 32-column A chunk
-  static constexpr uint32_t AST_BYTES = 2u * AST_PART;     // 16512
-  static constexpr uint32_t W_SLOT = 2u * 4u * 2048u;      // 16384: one kc=32 weight chunk (hi | lo)
+  static constexpr uint32_t AST_PART = 4u * LBO_A;           // 8256: one 32-column A chunk
+  static constexpr uint32_t AST_BYTES = 2u * AST_PART;       // 16512
+  static constexpr uint32_t W_SLOT = 2u * 4u * 2048u;        // 16384: one kc=32 weight chunk (hi | lo)
   static constexpr int W_SLOTS = 4;
-  // regions
-  static constexpr uint32_t OFF_CS = 0;
-  static constexpr uint32_t OFF_CV = OFF_CS + 2u * CS_PART;            // 57856
-  static constexpr uint32_t OFF_AQ = (OFF_CV + 2u * CV_PART + 127u) & ~127u;  // a image; later P_vid + A stages
-  static constexpr uint32_t AQ_BYTES = 2u * AQ_PART;                   // 66048
-  static constexpr uint32_t OFF_PV = OFF_AQ;                           // P_vid (after S is done)
-  static constexpr uint32_t OFF_AST = OFF_AQ + ((2u * PV_PART + 127u) & ~127u);  // 2 A stages behind P_vid
+  // per-frame ctx blob (global and shared layout are identical)
+  static constexpr uint32_t CTX_CS = 0;                                  // sub image hi | lo
+  static constexpr uint32_t CTX_CS_INV = 2u * CS_PART;                   // 57856: inv norms [112]
+  static constexpr uint32_t CTX_CS_MASK = CTX_CS_INV + LS_MAX * 4u;      // masks [112]
+  static constexpr uint32_t CTX_CV = CTX_CS_MASK + LS_MAX * 4u;          // 58752: vid image hi | lo
+  static constexpr uint32_t CTX_CV_INV = CTX_CV + 2u * CV_PART;          // 83840
+  static constexpr uint32_t CTX_CV_MASK = CTX_CV_INV + R_MAX * 4u;
+  static constexpr uint32_t CTX_BYTES = CTX_CV_MASK + R_MAX * 4u;        // 84224
+  // per-(example, answer) blob: image hi | lo, then inv|a|, mask, sum(a), sum(a^2) per row
+  static constexpr uint32_t AQ_BYTES = 2u * AQ_PART;                     // 66048
+  static constexpr uint32_t ABLOB_ROWDATA = AQ_BYTES;
+  static constexpr uint32_t ABLOB_BYTES = AQ_BYTES + 4u * 128u * 4u;     // 68096
+  // shared-memory regions
+  static constexpr uint32_t OFF_CTX = 0;
+  static constexpr uint32_t OFF_AQ = (CTX_BYTES + 127u) & ~127u;         // a image; later P_vid, then the 4 A stages
   static constexpr uint32_t OFF_B = (OFF_AQ + AQ_BYTES + 127u) & ~127u;  // P_sub; later the weight ring
-  static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                // 65536 >= 2*PS_PART (57792)
+  static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                  // 65536 >= 2*PS_PART (57792)
   static constexpr uint32_t SMEM_BYTES = OFF_B + B_BYTES + 1024u;
   static constexpr int THREADS = 288;
-  static_assert(OFF_AST + 2u * AST_BYTES <= OFF_AQ + AQ_BYTES, "A stages must fit behind P_vid");
-  static_assert(2u * PS_PART <= B_BYTES, "P_sub must fit in region B");
+  static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 chunks per tile: c2q(sub), c2q(vid), concat
+  static_assert(4u * AST_BYTES <= AQ_BYTES, "A stages overlay the answer image");
+  static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
+  static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
 };
 
 struct CqaDev {
   int n, t, lq, ls, r, ls_pad, r_pad;
   float scale;
-  const float* a_embed; const float* a_mask;
-  const float* sub_embed; const float* sub_mask;
-  const float* vid_embed; const float* vid_mask;
-  const float* c2q_g; const float* c2q_b; const uint8_t* c2q_w; const float* c2q_bias;
-  const float* cat_g; const float* cat_b; const uint8_t* cat_w; const float* cat_bias;
+  const float* a_embed;       // [n,5,lq,128] fp32 (for the a*U products)
+  const uint8_t* a_blob;      // [n*5] ABLOB_BYTES
+  const uint8_t* ctx_blob;    // [n*t] CTX_BYTES
+  const float* za;            // [n*5, lq, 128]  a (Wc*gamma)[:, :128]^T
+  const uint8_t* c2q_w;       // packed (Wc*gamma)[:, 128:384], kc=32: 8 chunks
+  const float* c2q_cs; const float* c2q_cb;
+  const uint8_t* cat_w;       // packed (Wf*gamma), kc=32: 12 chunks
+  const float* cat_cs; const float* cat_cb;
   const float* out_g; const float* out_b;
   float* statement; float* statement_mask;
   float* vid_raw_s; float* sub_raw_s; float* vid_norm_s; float* sub_norm_s;
   float* att_vid; float* att_sub; float* mixed_vid; float* mixed_sub;
 };
 
-// ---- build a split-fp16 K-major image of `rows` x 128 fp32 rows (warp per row, lane = 4 channels); rows >= n_real are 0.
-// Also records 1/max(||row||, 1e-12) and the row mask.
-__device__ __forceinline__ void build_rows_image(const float* __restrict__ src, const float* __restrict__ msk, int n_real,
-                                                 int n_pad, uint8_t* img, uint32_t lbo, uint32_t part, float* inv_out,
-                                                 float* mask_out, int warp, int lane) {
-  for (int j = warp; j < n_pad; j += 8) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    float m = 0.f;
-    if (j < n_real) {
-      v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(j) * 128) + lane);
-      m = __ldg(msk + j);
-    }
-    const float ss = warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
-    uint2 hi, lo;
-    split2(v.x, v.y, hi.x, lo.x);
-    split2(v.z, v.w, hi.y, lo.y);
-    uint8_t* dst = img + (lane >> 1) * lbo + j * 16 + (lane & 1) * 8;
-    *reinterpret_cast<uint2*>(dst) = hi;
-    *reinterpret_cast<uint2*>(dst + part) = lo;
-    if (lane == 0) {
-      inv_out[j] = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-      mask_out[j] = m;
-    }
+// ------------------------------------------------------------------------------------------------------------------
+// prep: fp32 rows -> split-fp16 operand images + per-row data (one warp per row, lane = 4 channels)
+// ------------------------------------------------------------------------------------------------------------------
+struct CqaPrepDev {
+  int n, t, lq, ls, r, ls_pad, r_pad;
+  const float* a_embed; const float* a_mask;
+  const float* sub_embed; const float* sub_mask;
+  const float* vid_embed; const float* vid_mask;
+  uint8_t* a_blob; uint8_t* ctx_blob;
+};
+
+__global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_a = static_cast<long long>(p.n) * 5 * 128;
+  const long long n_s = static_cast<long long>(p.n) * p.t * p.ls_pad;
+  const long long n_v = static_cast<long long>(p.n) * p.t * p.r_pad;
+  if (warp >= n_a + n_s + n_v) return;
+  const float* src = nullptr;
+  float m = 0.f;
+  uint8_t* img;
+  uint32_t lbo, part;
+  float *inv_out, *mask_out, *sum_out = nullptr, *sq_out = nullptr;
+  int j;
+  if (warp < n_a) {
+    const long long na = warp / 128;
+    j = static_cast<int>(warp % 128);
+    uint8_t* blob = p.a_blob + na * CqaCfg::ABLOB_BYTES;
+    img = blob; lbo = CqaCfg::LBO_A; part = CqaCfg::AQ_PART;
+    float* rd = reinterpret_cast<float*>(blob + CqaCfg::ABLOB_ROWDATA);
+    inv_out = rd; mask_out = rd + 128; sum_out = rd + 256; sq_out = rd + 384;
+    if (j < p.lq) { src = p.a_embed + (na * p.lq + j) * 128; m = __ldg(p.a_mask + na * p.lq + j); }
+  } else if (warp < n_a + n_s) {
+    const long long w = warp - n_a, f = w / p.ls_pad;
+    j = static_cast<int>(w % p.ls_pad);
+    uint8_t* blob = p.ctx_blob + f * CqaCfg::CTX_BYTES;
+    img = blob + CqaCfg::CTX_CS; lbo = CqaCfg::LBO_CS; part = CqaCfg::CS_PART;
+    inv_out = reinterpret_cast<float*>(blob + CqaCfg::CTX_CS_INV);
+    mask_out = reinterpret_cast<float*>(blob + CqaCfg::CTX_CS_MASK);
+    if (j < p.ls) { src = p.sub_embed + (f * p.ls + j) * 128; m = __ldg(p.sub_mask + f * p.ls + j); }
+  } else {
+    const long long w = warp - n_a - n_s, f = w / p.r_pad;
+    j = static_cast<int>(w % p.r_pad);
+    uint8_t* blob = p.ctx_blob + f * CqaCfg::CTX_BYTES;
+    img = blob + CqaCfg::CTX_CV; lbo = CqaCfg::LBO_CV; part = CqaCfg::CV_PART;
+    inv_out = reinterpret_cast<float*>(blob + CqaCfg::CTX_CV_INV);
+    mask_out = reinterpret_cast<float*>(blob + CqaCfg::CTX_CV_MASK);
+    if (j < p.r) { src = p.vid_embed + (f * p.r + j) * 128; m = __ldg(p.vid_mask + f * p.r + j); }
+  }
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (src != nullptr) v = __ldg(reinterpret_cast<const float4*>(src) + lane);
+  const float ss = warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+  const float sm = warp_sum((v.x + v.y) + (v.z + v.w));
+  uint2 hi, lo;
+  split2(v.x, v.y, hi.x, lo.x);
+  split2(v.z, v.w, hi.y, lo.y);
+  uint8_t* dst = img + (lane >> 1) * lbo + j * 16 + (lane & 1) * 8;
+  *reinterpret_cast<uint2*>(dst) = hi;
+  *reinterpret_cast<uint2*>(dst + part) = lo;
+  if (lane == 0) {
+    inv_out[j] = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+    mask_out[j] = m;
+    if (sum_out != nullptr) { sum_out[j] = sm; sq_out[j] = ss; }
   }
 }
 
-// ---- masked, scaled softmax of one S row held in TMEM -> P image (A operand of U = P.ctx).  NCH = 16-column chunks.
+// ------------------------------------------------------------------------------------------------------------------
+// compute-side helpers
+// ------------------------------------------------------------------------------------------------------------------
+struct RowStats { float s1, s2; };  // running sum and sum of squares
+
+// masked + scaled scores of NCH 16-column chunks starting at chunk c0 of one stream; returns the running max
 template <int NCH>
-__device__ __forceinline__ void softmax_row(uint32_t trow, int n_real, int n_pad, float inv_a, float mask_a,
-                                            const float* inv_c, const float* mask_c, float scale, uint8_t* p_img,
-                                            uint32_t p_part, int row, float* raw_out, float* norm_out) {
-  float s[NCH * 16];
+__device__ __forceinline__ float score_chunks(float* s, uint32_t trow, int c0, int n_real, int n_pad, float inv_a,
+                                              float mask_a, const float* inv_c, const float* mask_c, float scale,
+                                              float* raw_out, float mx) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if (c * 16 < n_pad) tmem_ld16(trow + c * 16, s + c * 16);
-  }
+  for (int c = 0; c < NCH; ++c)
+    if ((c0 + c) * 16 < n_pad) tmem_ld16(trow + (c0 + c) * 16, s + c * 16);
   tmem_wait_ld();
-  float mx = -3.0e38f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    if (c * 16 < n_pad) {
+    if ((c0 + c) * 16 < n_pad) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = c * 16 + j;
+        const int col = (c0 + c) * 16 + j;
         if (col < n_real) {
           const float m = mask_a * mask_c[col];
-          float v = s[col] * inv_a * inv_c[col];
+          float v = s[c * 16 + j] * inv_a * inv_c[col];
           v = v - 1e10f * (1.f - m);  // exactly the reference's S - 1e10*(1 - S_mask)
           if (raw_out != nullptr) raw_out[col] = v;
           v *= scale;
-          s[col] = v;
+          s[c * 16 + j] = v;
           mx = fmaxf(mx, v);
         }
       }
     }
   }
+  return mx;
+}
+template <int NCH>
+__device__ __forceinline__ float exp_chunks(float* s, int c0, int n_real, int n_pad, float mx) {
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    if (c * 16 < n_pad) {
+    if ((c0 + c) * 16 < n_pad) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = c * 16 + j;
-        if (col < n_real) {
-          const float e = expf(s[col] - mx);
-          s[col] = e;
-          sum += e;
-        } else {
-          s[col] = 0.f;
-        }
+        const int col = (c0 + c) * 16 + j;
+        float e = 0.f;
+        if (col < n_real) { e = expf(s[c * 16 + j] - mx); sum += e; }
+        s[c * 16 + j] = e;
       }
     }
   }
-  const float inv_sum = 1.f / sum;
+  return sum;
+}
+template <int NCH>
+__device__ __forceinline__ void write_p_chunks(float* s, int c0, int n_real, int n_pad, float inv_sum, float mask_a,
+                                               const float* mask_c, uint8_t* p_img, uint32_t p_part, int row,
+                                               float* norm_out) {
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    if (c * 16 < n_pad) {
+    if ((c0 + c) * 16 < n_pad) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = c * 16 + j;
+        const int col = (c0 + c) * 16 + j;
         if (col < n_real) {
-          const float pj = s[col] * inv_sum * (mask_a * mask_c[col]);
-          s[col] = pj;
+          const float pj = s[c * 16 + j] * inv_sum * (mask_a * mask_c[col]);
+          s[c * 16 + j] = pj;
           if (norm_out != nullptr) norm_out[col] = pj;
         }
       }
 #pragma unroll
       for (int h8 = 0; h8 < 2; ++h8) {
         HL8 hl = split8(s + c * 16 + h8 * 8);
-        uint8_t* dst = p_img + (c * 2 + h8) * CqaCfg::LBO_A + row * 16;
+        uint8_t* dst = p_img + ((c0 + c) * 2 + h8) * CqaCfg::LBO_A + row * 16;
         *reinterpret_cast<uint4*>(dst) = hl.hi;
         *reinterpret_cast<uint4*>(dst + p_part) = hl.lo;
       }
@@ -158,122 +224,44 @@ __device__ __forceinline__ void softmax_row(uint32_t trow, int n_real, int n_pad
   }
 }
 
-// ---- one 16-column slice of the two GEMM-input operands p, q  (concat row = [p, q, p*q])
-template <bool CONCAT>
-__device__ __forceinline__ void load_pq16(int cc, const float (&a_reg)[64], uint32_t tP, uint32_t tQ,
-                                          const float* __restrict__ bias, int col0, float* p, float* q) {
-  if (CONCAT) {
-    tmem_ld16(tP + cc * 16, p);
-    tmem_ld16(tQ + cc * 16, q);
-    tmem_wait_ld();
+// store one K=32 A chunk (32 fp32 values of this thread's row) into an A stage, then publish it
+__device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int row, uint64_t* full) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float b = __ldg(bias + col0 + cc * 16 + j);
-      p[j] = fmaxf(p[j] + b, 0.f);
-      q[j] = fmaxf(q[j] + b, 0.f);
-    }
-  } else {
-    tmem_ld16(tQ + cc * 16, q);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) p[j] = a_reg[cc * 16 + j];
+  for (int s8 = 0; s8 < 4; ++s8) {
+    HL8 hl = split8(v + s8 * 8);
+    uint8_t* dst = stage + s8 * CqaCfg::LBO_A + row * 16;
+    *reinterpret_cast<uint4*>(dst) = hl.hi;
+    *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;
   }
-}
-
-// ---- LayerNorm(384) over [p, q, p*q] + split-fp16 A-chunk production for one 384->128 GEMM.
-// Thread = (row, half): owns columns [64*half, 64*half+64) of each 128-wide segment, i.e. 6 of the 12 K=32 chunks.
-template <bool CONCAT>
-__device__ __forceinline__ void produce_gemm(const float (&a_reg)[64], uint32_t tP, uint32_t tQ, const float* bias,
-                                             const float* __restrict__ ln_g, const float* __restrict__ ln_b, int row,
-                                             int half, float (*xch)[128], uint8_t* a_stage, uint64_t* a_full,
-                                             uint64_t* a_empty, uint32_t& a_use, float* dbg_p, float* dbg_q) {
-  const int col0 = half * 64;
-  float s = 0.f;
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    float p[16], q[16];
-    load_pq16<CONCAT>(cc, a_reg, tP, tQ, bias, col0, p, q);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) s += (p[j] + q[j]) + p[j] * q[j];
-    if (dbg_q != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(dbg_q + col0 + cc * 16 + j) = make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]);
-    }
-    if (CONCAT && dbg_p != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(dbg_p + col0 + cc * 16 + j) = make_float4(p[j], p[j + 1], p[j + 2], p[j + 3]);
-    }
-  }
-  xch[half][row] = s;
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const float mean = (xch[0][row] + xch[1][row]) * (1.f / 384.f);
-  float qq = 0.f;
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    float p[16], q[16];
-    load_pq16<CONCAT>(cc, a_reg, tP, tQ, bias, col0, p, q);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float d0 = p[j] - mean, d1 = q[j] - mean, d2 = p[j] * q[j] - mean;
-      qq += (d0 * d0 + d1 * d1) + d2 * d2;
-    }
-  }
-  xch[2 + half][row] = qq;
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const float rstd = 1.f / sqrtf((xch[2][row] + xch[3][row]) * (1.f / 384.f) + 1e-5f);
-
-#pragma unroll
-  for (int pi = 0; pi < 6; ++pi) {
-    const int seg = pi >> 1, sub = pi & 1;
-    mbar_wait(a_empty, (a_use & 1u) ^ 1u, 30);
-    ++a_use;
-    const int kbase = seg * 128 + col0 + sub * 32;  // first concat column of this chunk
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      float p[16], q[16], v[16];
-      load_pq16<CONCAT>(sub * 2 + c2, a_reg, tP, tQ, bias, col0, p, q);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x = seg == 0 ? p[j] : (seg == 1 ? q[j] : p[j] * q[j]);
-        const int k = kbase + c2 * 16 + j;
-        v[j] = (x - mean) * rstd * __ldg(ln_g + k) + __ldg(ln_b + k);
-      }
-#pragma unroll
-      for (int h8 = 0; h8 < 2; ++h8) {
-        HL8 hl = split8(v + h8 * 8);
-        uint8_t* dst = a_stage + (c2 * 2 + h8) * CqaCfg::LBO_A + row * 16;
-        *reinterpret_cast<uint4*>(dst) = hl.hi;
-        *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;
-      }
-    }
-    fence_async_smem();
-    mbar_arrive(a_full);
-  }
+  fence_async_smem();
+  mbar_arrive(full);
 }
 
 __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t op_ready, mma_done, a_full[2], a_empty[2], w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
+  __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, a_full[4], a_empty[4], w_full[CqaCfg::W_SLOTS],
+      w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float inv_cs[CqaCfg::LS_MAX], mask_cs[CqaCfg::LS_MAX], inv_cv[CqaCfg::R_MAX], mask_cv[CqaCfg::R_MAX];
-  __shared__ float inv_a[128], mask_a[128];
-  __shared__ float xch[4][128];
+  __shared__ float xch[8][128];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sCS = smem + CqaCfg::OFF_CS;
-  uint8_t* sCV = smem + CqaCfg::OFF_CV;
-  uint8_t* sAQ = smem + CqaCfg::OFF_AQ;
-  uint8_t* sPV = smem + CqaCfg::OFF_PV;
-  uint8_t* sAST = smem + CqaCfg::OFF_AST;
-  uint8_t* sB = smem + CqaCfg::OFF_B;
+  uint8_t* sCTX = smem + CqaCfg::OFF_CTX;
+  uint8_t* sCS = sCTX + CqaCfg::CTX_CS;
+  uint8_t* sCV = sCTX + CqaCfg::CTX_CV;
+  const float* inv_cs = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CS_INV);
+  const float* mask_cs = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CS_MASK);
+  const float* inv_cv = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CV_INV);
+  const float* mask_cv = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CV_MASK);
+  uint8_t* sAQ = smem + CqaCfg::OFF_AQ;  // a image -> P_vid -> A stages
+  uint8_t* sB = smem + CqaCfg::OFF_B;    // P_sub -> weight ring
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&op_ready, 256);
     mbar_init(&mma_done, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(&ctx_full, 1);
+    mbar_init(&aq_full, 1);
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&a_full[i], 128);
       mbar_init(&a_empty[i], 1);
     }
@@ -289,111 +277,219 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
   const uint32_t T0 = tbase, T1 = tbase + 128, T2 = tbase + 256, T3 = tbase + 384;
-
   const int n_frames = p.n * p.t;
 
   if (warp < 8) {
     // =================================================================== compute warps
     const int row = (warp & 3) * 32 + lane, half = warp >> 2;
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
-    uint32_t done_cnt = 0, a_use = 0;
-    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+    const uint32_t coff = lane_off + half * 64;
+    const bool live = row < p.lq;
+    uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
+    float any_v = 0.f;  // does this frame have at least one valid region?  (S_mask.sum(-1) != 0, stage.py:386)
+    uint64_t* my_full = &a_full[half * 2];
+    uint64_t* my_empty = &a_empty[half * 2];
+    uint8_t* my_stage = sAQ + half * 2 * CqaCfg::AST_BYTES;
+
+    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
-      // ---- frame setup: ctx images (shared by the 5 answers)
-      build_rows_image(p.sub_embed + static_cast<size_t>(frame) * p.ls * 128, p.sub_mask + static_cast<size_t>(frame) * p.ls,
-                       p.ls, p.ls_pad, sCS, CqaCfg::LBO_CS, CqaCfg::CS_PART, inv_cs, mask_cs, warp, lane);
-      build_rows_image(p.vid_embed + static_cast<size_t>(frame) * p.r * 128, p.vid_mask + static_cast<size_t>(frame) * p.r,
-                       p.r, p.r_pad, sCV, CqaCfg::LBO_CV, CqaCfg::CV_PART, inv_cv, mask_cv, warp, lane);
       for (int a_i = 0; a_i < 5; ++a_i) {
         const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
-        const size_t tile = (na * p.t + t_i);  // index of this (n, a, t) tile
-        // ---- A: answer tile image (rows >= lq are zero)
-        build_rows_image(p.a_embed + na * p.lq * 128, p.a_mask + na * p.lq, p.lq, 128, sAQ, CqaCfg::LBO_A,
-                         CqaCfg::AQ_PART, inv_a, mask_a, warp, lane);
-        fence_async_smem();
-        mbar_arrive(&op_ready);  // E1
-        // ---- B: softmax (warps 0-3: sub stream, warps 4-7: vid stream), thread = row
-        mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
-        ++done_cnt;
-        tc_fence_after();
-        {
-          const float ia = inv_a[row], ma = mask_a[row];
-          const bool live = row < p.lq;
-          if (half == 0) {
-            float* raw = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
-            float* nrm = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
-            softmax_row<7>(T0 + lane_off, p.ls, p.ls_pad, ia, ma, inv_cs, mask_cs, p.scale, sB, CqaCfg::PS_PART, row, raw, nrm);
-          } else {
-            float* raw = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
-            float* nrm = (p.vid_norm_s && live) ? p.vid_norm_s + (tile * p.lq + row) * p.r : nullptr;
-            softmax_row<3>(T1 + lane_off, p.r, p.r_pad, ia, ma, inv_cv, mask_cv, p.scale, sPV, CqaCfg::PV_PART, row, raw, nrm);
-          }
-        }
-        tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(&op_ready);  // E2
-        // ---- my 64 answer values (columns [64*half, +64) of row), kept in registers for both c2q GEMMs
+        const size_t tile = na * p.t + t_i;
+        const size_t orow = (tile * p.lq + row) * 128;
+        // ---- per-row data of the answer tile + my 64 answer values (columns [64*half, +64))
+        const float* rd = reinterpret_cast<const float*>(p.a_blob + na * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
+        const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row), asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);
         float a_reg[64];
         {
           const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + half * 64);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float4 v = (row < p.lq) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
           }
         }
-        // ---- C: c2q for both streams
-        mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
-        ++done_cnt;
-        tc_fence_after();
-        const uint32_t coff = lane_off + half * 64;
-        const bool live = row < p.lq;
-        const size_t orow = (tile * p.lq + row) * 128;
-        produce_gemm<false>(a_reg, 0, T2 + coff, nullptr, p.c2q_g, p.c2q_b, row, half, xch, sAST + half * CqaCfg::AST_BYTES,
-                            &a_full[half], &a_empty[half], a_use, nullptr, (p.att_sub && live) ? p.att_sub + orow : nullptr);
-        produce_gemm<false>(a_reg, 0, T3 + coff, nullptr, p.c2q_g, p.c2q_b, row, half, xch, sAST + half * CqaCfg::AST_BYTES,
-                            &a_full[half], &a_empty[half], a_use, nullptr, (p.att_vid && live) ? p.att_vid + orow : nullptr);
-        // ---- D: concat_fc input from the two c2q accumulators
-        tc_fence_before();
-        mbar_wait(&mma_done, done_cnt & 1u, 33);  // D3: both c2q accumulators complete
-        ++done_cnt;
-        tc_fence_after();
-        produce_gemm<true>(a_reg, T0 + coff, T1 + coff, p.c2q_bias, p.cat_g, p.cat_b, row, half, xch,
-                           sAST + half * CqaCfg::AST_BYTES, &a_full[half], &a_empty[half], a_use,
-                           (p.mixed_sub && live) ? p.mixed_sub + orow : nullptr, (p.mixed_vid && live) ? p.mixed_vid + orow : nullptr);
-        // ---- E: relu(acc + b) -> LN128 -> statement
-        tc_fence_before();
-        mbar_wait(&mma_done, done_cnt & 1u, 34);  // D4: concat accumulator complete
+        if (a_i == 0) {
+          mbar_wait(&ctx_full, frame_cnt & 1u, 30);  // ctx blob (images + inv norms + masks) has landed
+          any_v = 0.f;
+          for (int j = 0; j < p.r; ++j) any_v += mask_cv[j];
+        }
+
+        // ---- softmax of both streams; the 7 sub + 3 vid score chunks are split 5 / 5 between the two column halves
+        mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
         ++done_cnt;
         tc_fence_after();
         {
-          float s = 0.f;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            float v[16];
-            tmem_ld16(T2 + coff + cc * 16, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s += fmaxf(v[j] + __ldg(p.cat_bias + half * 64 + cc * 16 + j), 0.f);
+          float s[80];
+          float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
+          float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
+          float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
+          float* nrm_v = (p.vid_norm_s && live) ? p.vid_norm_s + (tile * p.lq + row) * p.r : nullptr;
+          float mxs = -3.0e38f, mxv = -3.0e38f;
+          if (half == 0) {
+            mxs = score_chunks<4>(s, T0 + lane_off, 0, p.ls, p.ls_pad, ia, ma, inv_cs, mask_cs, p.scale, raw_s, mxs);
+            mxv = score_chunks<1>(s + 64, T1 + lane_off, 0, p.r, p.r_pad, ia, ma, inv_cv, mask_cv, p.scale, raw_v, mxv);
+          } else {
+            mxs = score_chunks<3>(s, T0 + lane_off, 4, p.ls, p.ls_pad, ia, ma, inv_cs, mask_cs, p.scale, raw_s, mxs);
+            mxv = score_chunks<2>(s + 48, T1 + lane_off, 1, p.r, p.r_pad, ia, ma, inv_cv, mask_cv, p.scale, raw_v, mxv);
           }
-          xch[half][row] = s;
+          xch[half][row] = mxs;
+          xch[2 + half][row] = mxv;
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float mean = (xch[0][row] + xch[1][row]) * (1.f / 128.f);
-          float qq = 0.f;
+          mxs = fmaxf(xch[0][row], xch[1][row]);
+          mxv = fmaxf(xch[2][row], xch[3][row]);
+          float sms, smv;
+          if (half == 0) {
+            sms = exp_chunks<4>(s, 0, p.ls, p.ls_pad, mxs);
+            smv = exp_chunks<1>(s + 64, 0, p.r, p.r_pad, mxv);
+          } else {
+            sms = exp_chunks<3>(s, 4, p.ls, p.ls_pad, mxs);
+            smv = exp_chunks<2>(s + 48, 1, p.r, p.r_pad, mxv);
+          }
+          xch[4 + half][row] = sms;
+          xch[6 + half][row] = smv;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float is = 1.f / (xch[4][row] + xch[5][row]), iv = 1.f / (xch[6][row] + xch[7][row]);
+          if (half == 0) {
+            write_p_chunks<4>(s, 0, p.ls, p.ls_pad, is, ma, mask_cs, sB, CqaCfg::PS_PART, row, nrm_s);
+            write_p_chunks<1>(s + 64, 0, p.r, p.r_pad, iv, ma, mask_cv, sAQ, CqaCfg::PV_PART, row, nrm_v);
+          } else {
+            write_p_chunks<3>(s, 4, p.ls, p.ls_pad, is, ma, mask_cs, sB, CqaCfg::PS_PART, row, nrm_s);
+            write_p_chunks<2>(s + 48, 1, p.r, p.r_pad, iv, ma, mask_cv, sAQ, CqaCfg::PV_PART, row, nrm_v);
+          }
+        }
+        // ---- hoisted a.Wa term -> both c2q accumulators (S has been consumed by every thread: second bar.sync above)
+        {
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + half * 64);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            float v[16];
-            tmem_ld16(T2 + coff + cc * 16, v);
-            tmem_wait_ld();
+            float z[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float d = fmaxf(v[j] + __ldg(p.cat_bias + half * 64 + cc * 16 + j), 0.f) - mean;
-              qq += d * d;
+            for (int j = 0; j < 4; ++j) {
+              const float4 v = live ? __ldg(zsrc + cc * 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              z[j * 4] = v.x; z[j * 4 + 1] = v.y; z[j * 4 + 2] = v.z; z[j * 4 + 3] = v.w;
             }
+            tmem_st16(T0 + coff + cc * 16, z);
+            tmem_st16(T1 + coff + cc * 16, z);
           }
-          xch[2 + half][row] = qq;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float rstd = 1.f / sqrtf((xch[2][row] + xch[3][row]) * (1.f / 128.f) + 1e-5f);
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(&op_ready);  // E2: P images + accumulator pre-loads are in place
+
+        // ---- c2q A operands for both streams: raw [U, a*U] chunks, statistics on the fly
+        mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
+        ++done_cnt;
+        tc_fence_after();
+        RowStats st[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t tU = (g == 0 ? T2 : T3) + coff;
+          float* att = g == 0 ? p.att_sub : p.att_vid;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float u[32], pu[32];
+            tmem_ld16(tU + b * 32, u);
+            tmem_ld16(tU + b * 32 + 16, u + 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              pu[j] = a_reg[b * 32 + j] * u[j];
+              s1 += u[j] + pu[j];
+              s2 += u[j] * u[j] + pu[j] * pu[j];
+            }
+            if (att != nullptr && live) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(att + orow + half * 64 + b * 32 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+            }
+            mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 33);
+            put_chunk(u, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
+            ++a_use;
+            mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 34);
+            put_chunk(pu, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
+            ++a_use;
+          }
+          st[g].s1 = s1;
+          st[g].s2 = s2;
+        }
+        xch[half][row] = st[0].s1; xch[2 + half][row] = st[0].s2;
+        xch[4 + half][row] = st[1].s1; xch[6 + half][row] = st[1].s2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float mu_s, r_s, mu_v, r_v;
+        {
+          const float t1 = asum + xch[0][row] + xch[1][row], t2 = asq + xch[2][row] + xch[3][row];
+          mu_s = t1 * (1.f / 384.f);
+          r_s = 1.f / sqrtf(fmaxf(t2 * (1.f / 384.f) - mu_s * mu_s, 0.f) + 1e-5f);
+          const float v1 = asum + xch[4][row] + xch[5][row], v2 = asq + xch[6][row] + xch[7][row];
+          mu_v = v1 * (1.f / 384.f);
+          r_v = 1.f / sqrtf(fmaxf(v2 * (1.f / 384.f) - mu_v * mu_v, 0.f) + 1e-5f);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read xch before it is reused below
+
+        // ---- concat_fc A operands: [ms, mv, ms*mv] with ms/mv = relu(rstd*(acc - mean*cs) + cb)
+        tc_fence_before();
+        mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
+        ++done_cnt;
+        tc_fence_after();
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float ms[32], mv[32];
+          tmem_ld16(T0 + coff + b * 32, ms);
+          tmem_ld16(T0 + coff + b * 32 + 16, ms + 16);
+          tmem_ld16(T1 + coff + b * 32, mv);
+          tmem_ld16(T1 + coff + b * 32 + 16, mv + 16);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = half * 64 + b * 32 + j;
+            const float cs = __ldg(p.c2q_cs + c), cb = __ldg(p.c2q_cb + c);
+            ms[j] = fmaxf(r_s * (ms[j] - mu_s * cs) + cb, 0.f);
+            mv[j] = fmaxf(r_v * (mv[j] - mu_v * cs) + cb, 0.f);
+          }
+          if (live && p.mixed_sub != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.mixed_sub + orow + half * 64 + b * 32 + j) = make_float4(ms[j], ms[j + 1], ms[j + 2], ms[j + 3]);
+          }
+          if (live && p.mixed_vid != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.mixed_vid + orow + half * 64 + b * 32 + j) = make_float4(mv[j], mv[j + 1], mv[j + 2], mv[j + 3]);
+          }
+          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 36);
+          put_chunk(ms, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
+          ++a_use;
+          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 37);
+          put_chunk(mv, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
+          ++a_use;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pr = ms[j] * mv[j];
+            c1 += (ms[j] + mv[j]) + pr;
+            c2 += (ms[j] * ms[j] + mv[j] * mv[j]) + pr * pr;
+            ms[j] = pr;
+          }
+          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 38);
+          put_chunk(ms, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
+          ++a_use;
+        }
+        xch[half][row] = c1;
+        xch[2 + half][row] = c2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mu_c = (xch[0][row] + xch[1][row]) * (1.f / 384.f);
+        const float r_c = 1.f / sqrtf(fmaxf((xch[2][row] + xch[3][row]) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
+
+        // ---- relu(rstd*(acc - mean*cs) + cb) -> LN128 -> statement
+        tc_fence_before();
+        mbar_wait(&mma_done, done_cnt & 1u, 39);  // D4: concat accumulator complete
+        ++done_cnt;
+        tc_fence_after();
+        {
+          float o1 = 0.f, o2 = 0.f;
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             float v[16];
@@ -402,37 +498,60 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int c = half * 64 + cc * 16 + j;
-              v[j] = (fmaxf(v[j] + __ldg(p.cat_bias + c), 0.f) - mean) * rstd * __ldg(p.out_g + c) + __ldg(p.out_b + c);
+              const float o = fmaxf(r_c * (v[j] - mu_c * __ldg(p.cat_cs + c)) + __ldg(p.cat_cb + c), 0.f);
+              o1 += o;
+              o2 += o * o;
+            }
+          }
+          xch[4 + half][row] = o1;
+          xch[6 + half][row] = o2;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float mean = (xch[4][row] + xch[5][row]) * (1.f / 128.f);
+          const float rstd = 1.f / sqrtf(fmaxf((xch[6][row] + xch[7][row]) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            float v[16];
+            tmem_ld16(T2 + coff + cc * 16, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = half * 64 + cc * 16 + j;
+              const float o = fmaxf(r_c * (v[j] - mu_c * __ldg(p.cat_cs + c)) + __ldg(p.cat_cb + c), 0.f);
+              v[j] = (o - mean) * rstd * __ldg(p.out_g + c) + __ldg(p.out_b + c);
             }
             if (live) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(p.statement + orow + half * 64 + cc * 16 + j) =
-                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                *reinterpret_cast<float4*>(p.statement + orow + half * 64 + cc * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           }
-          if (live && half == 0) {
-            float cnt = 0.f;
-            for (int j = 0; j < p.r; ++j) cnt += mask_a[row] * mask_cv[j];  // S_mask.sum(-1) != 0  (stage.py:386)
-            p.statement_mask[tile * p.lq + row] = (cnt != 0.f) ? 1.f : 0.f;
-          }
+          // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
+          if (live && half == 0) p.statement_mask[tile * p.lq + row] = (ma * any_v != 0.f) ? 1.f : 0.f;
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // xch / inv_a / mask_a are rewritten by the next answer
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // xch is rewritten by the next tile
       }
     }
   } else if (lane == 0) {
-    // =================================================================== MMA issue + weight ring (one thread)
-    uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, a_cnt[2] = {0, 0};
+    // =================================================================== MMA issue + every bulk copy (one thread)
+    uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0, ah_cnt0 = 0, ah_cnt1 = 0;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
-    const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sPV);
-    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-      for (int a_i = 0; a_i < 5; ++a_i) {
-        // ---- S = a . ctx^T for both streams
-        mbar_wait(&op_ready, ready_cnt & 1u, 40);  // E1
-        ++ready_cnt;
+    const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
+    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
+      const int n_i = frame / p.t;
+      // ctx region is free: the previous frame's last U has completed (this thread waited on D2 below)
+      mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
+      bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
+      for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
+        const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
+        // ---- answer image: AQ region (A stages of the previous tile) is free once D4 has completed (waited below)
+        mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
+        bulk_g2s(sAQ, p.a_blob + na * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
+        if (a_i == 0) mbar_wait(&ctx_full, frame_cnt & 1u, 40);
+        mbar_wait(&aq_full, tile_cnt & 1u, 41);
         tc_fence_after();
+        // ---- S = a . ctx^T for both streams
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t a_hi = make_smem_desc(aq + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
@@ -447,7 +566,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         umma_commit(&mma_done);  // D1
         ++done_cnt;
         // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
-        mbar_wait(&op_ready, ready_cnt & 1u, 41);  // E2
+        mbar_wait(&op_ready, ready_cnt & 1u, 42);  // E2
         ++ready_cnt;
         tc_fence_after();
         for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
@@ -465,52 +584,66 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
         }
         umma_commit(&mma_done);  // D2
-        mbar_wait(&mma_done, done_cnt & 1u, 42);  // region B (P_sub) is free once U has completed
+        mbar_wait(&mma_done, done_cnt & 1u, 43);  // P_sub (region B) and P_vid (region AQ) are free once U has completed
         ++done_cnt;
-        // ---- three 384->128 GEMMs, 12 K=32 chunks each; chunk order alternates between the two column halves
+        // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk order alternates between the column halves
         auto w_src = [&](int q) -> const uint8_t* {
-          const int g = q / 12, ql = q % 12, pi = ql >> 1, h = ql & 1;
-          const int c = (pi >> 1) * 4 + h * 2 + (pi & 1);  // K chunk of the 384-wide weight
-          return (g < 2 ? p.c2q_w : p.cat_w) + static_cast<size_t>(c) * CqaCfg::W_SLOT;
+          int c;
+          const uint8_t* base;
+          if (q < 16) {
+            const int ql = q & 7, h = ql & 1, j = ql >> 1;
+            c = (j & 1) * 4 + 2 * h + (j >> 1);
+            base = p.c2q_w;
+          } else {
+            const int ql = q - 16, h = ql & 1, j = ql >> 1;
+            c = (j % 3) * 4 + 2 * h + (j / 3);
+            base = p.cat_w;
+          }
+          return base + static_cast<size_t>(c) * CqaCfg::W_SLOT;
         };
         for (int q = 0; q < CqaCfg::W_SLOTS - 1; ++q) {  // prime the ring
           const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, use = (q_cnt + q) / CqaCfg::W_SLOTS;
-          mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 43);
+          mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 44);
           mbar_arrive_expect_tx(&w_full[slot], CqaCfg::W_SLOT);
           bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
         }
-        for (int q = 0; q < 36; ++q) {
-          const int g = q / 12, ql = q % 12, h = ql & 1;
+        for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
+          const int h = q & 1;  // 8, 8 and 12 are even, so the half alternates across GEMM boundaries too
+          const uint32_t cnt = h == 0 ? ah_cnt0 : ah_cnt1;
+          const uint32_t stg = h * 2 + (cnt & 1u);
           const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, wuse = (q_cnt + q) / CqaCfg::W_SLOTS;
-          mbar_wait(&a_full[h], a_cnt[h] & 1u, 45);
-          ++a_cnt[h];
+          mbar_wait(&a_full[stg], (cnt >> 1) & 1u, 45);
+          if (h == 0) ++ah_cnt0; else ++ah_cnt1;
           mbar_wait(&w_full[slot], wuse & 1u, 46);
           tc_fence_after();
-          const uint32_t ast = smem_u32(sAST + h * CqaCfg::AST_BYTES), wsl = smem_u32(sB + slot * CqaCfg::W_SLOT);
-          const uint32_t dcol = g == 0 ? T0 : (g == 1 ? T1 : T2);
+          const uint32_t ast = smem_u32(sAQ + stg * CqaCfg::AST_BYTES), wsl = smem_u32(sB + slot * CqaCfg::W_SLOT);
+          const uint32_t dcol = q < 8 ? T0 : (q < 16 ? T1 : T2);
+          const bool first = (q == 16);  // c2q accumulators start from the pre-loaded a.Wa term; concat starts from zero
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
             const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
             const uint64_t b_hi = make_smem_desc(wsl + ks * 2 * 2048, 2048, 128);
             const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + ks * 2 * 2048, 2048, 128);
-            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (ql > 0 || ks > 0) ? 1u : 0u);
+            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
           }
-          umma_commit(&a_empty[h]);
+          umma_commit(&a_empty[stg]);
           umma_commit(&w_empty[slot]);
-          if (q == 23 || q == 35) {
+          if (q == 15 || q == CqaCfg::CHUNKS - 1) {
             umma_commit(&mma_done);  // D3 / D4
             ++done_cnt;
           }
-          if (q + CqaCfg::W_SLOTS - 1 < 36) {  // refill the slot chunk q-1 used (chunk q keeps the tensor pipe busy meanwhile)
+          if (q + CqaCfg::W_SLOTS - 1 < CqaCfg::CHUNKS) {  // refill the slot chunk q-1 used
             const uint32_t qq = q_cnt + q + CqaCfg::W_SLOTS - 1;
             const uint32_t rslot = qq % CqaCfg::W_SLOTS, ruse = qq / CqaCfg::W_SLOTS;
-            mbar_wait(&w_empty[rslot], (ruse & 1u) ^ 1u, 44);
+            mbar_wait(&w_empty[rslot], (ruse & 1u) ^ 1u, 47);
             mbar_arrive_expect_tx(&w_full[rslot], CqaCfg::W_SLOT);
             bulk_g2s(sB + rslot * CqaCfg::W_SLOT, w_src(q + CqaCfg::W_SLOTS - 1), CqaCfg::W_SLOT, &w_full[rslot]);
           }
         }
-        q_cnt += 36;
+        q_cnt += CqaCfg::CHUNKS;
+        // the AQ region (A stages) and T0/T1 may only be reused after the concat MMAs have completed
+        mbar_wait(&mma_done, (done_cnt - 1u) & 1u, 48);  // D4
       }
     }
   }

@@ -28,20 +28,48 @@ __host__ __device__ inline PackGeom pack_geom(int n, int k, int kc) {
   return g;
 }
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, PackGeom g, uint8_t* __restrict__ out) {
+// w: row-major [n, ld]; packs columns [k0, k0 + g.k) optionally scaled per column by col_scale[k0 + k] (LayerNorm gamma
+// folded into the weight, see cqa.cuh).
+__global__ void pack_weight_kernel(const float* __restrict__ w, int ld, int k0, const float* __restrict__ col_scale,
+                                   PackGeom g, uint8_t* __restrict__ out) {
   // one thread per (k8 slab over the whole padded K, row n)
   const int total = (g.kpad / 8) * g.npad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int n = idx % g.npad, k8 = idx / g.npad;
-    const int k0 = k8 * 8;
+    const int kk = k8 * 8;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (n < g.n && k0 + j < g.k) ? w[static_cast<size_t>(n) * g.k + k0 + j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      float x = (n < g.n && kk + j < g.k) ? w[static_cast<size_t>(n) * ld + k0 + kk + j] : 0.f;
+      if (col_scale != nullptr && kk + j < g.k) x *= col_scale[k0 + kk + j];
+      v[j] = x;
+    }
     HL8 hl = split8(v);
-    const int c = k0 / g.kc, s = (k0 % g.kc) / 8;
+    const int c = kk / g.kc, s = (kk % g.kc) / 8;
     uint8_t* base = out + static_cast<size_t>(c) * g.chunk_bytes + static_cast<size_t>(s) * g.lbo + static_cast<size_t>(n) * 16;
     *reinterpret_cast<uint4*>(base) = hl.hi;
     *reinterpret_cast<uint4*>(base + g.part_bytes) = hl.lo;
+  }
+}
+
+// LayerNorm folded into the Linear that follows it:  LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * cs) + cb  with
+//   cs[n] = sum_k W[n,k] gamma[k],  cb[n] = sum_k W[n,k] beta[k] + b[n].          One warp per output feature n.
+__global__ void fold_layernorm_kernel(const float* __restrict__ w, int n, int k, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                      float* __restrict__ cs, float* __restrict__ cb) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float a = 0.f, b = 0.f;
+  for (int i = lane; i < k; i += 32) {
+    const float x = w[static_cast<size_t>(row) * k + i];
+    a = fmaf(x, gamma[i], a);
+    b = fmaf(x, beta[i], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    cs[row] = a;
+    cb[row] = b + bias[row];
   }
 }
 

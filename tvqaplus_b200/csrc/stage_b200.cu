@@ -88,7 +88,7 @@ int stage_pack_weight(const float* w, int n, int k, int kc, void* packed, void* 
   STG_REQUIRE(aligned16(packed), STAGE_E_BADARG, "pack_weight: packed buffer not 16-byte aligned");
   PackGeom g = pack_geom(n, k, kc);
   const int total = (g.kpad / 8) * g.npad;
-  pack_weight_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, static_cast<uint8_t*>(packed));
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, k, 0, nullptr, g, static_cast<uint8_t*>(packed));
   return check_launch("pack_weight");
 }
 
@@ -142,24 +142,94 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   }
 }
 
+// weight blob layout of the fused CQA kernel
+static constexpr size_t WB_WA = 0;                      // (Wc*gamma)[:, 0:128]   packed kc=64 (Za = a . Wa^T via the linear kernel)
+static constexpr size_t WB_WU = 65536;                  // (Wc*gamma)[:, 128:384] packed kc=32, 8 chunks
+static constexpr size_t WB_WF = WB_WU + 8 * 16384;      // (Wf*gamma)             packed kc=32, 12 chunks
+static constexpr size_t WB_VEC = WB_WF + 12 * 16384;    // c2q cs | c2q cb | cat cs | cat cb | zeros, 128 floats each
+static constexpr size_t WB_BYTES = WB_VEC + 5 * 512;
+
+size_t stage_cqa_weight_blob_bytes(void) { return WB_BYTES; }
+
+int stage_cqa_prepare_weights(const float* c2q_ln_g, const float* c2q_ln_b, const float* c2q_w, const float* c2q_b,
+                              const float* cat_ln_g, const float* cat_ln_b, const float* cat_w, const float* cat_b,
+                              void* wblob, void* stream) {
+  STG_REQUIRE(c2q_ln_g && c2q_ln_b && c2q_w && c2q_b && cat_ln_g && cat_ln_b && cat_w && cat_b && wblob, STAGE_E_BADARG,
+              "cqa_prepare_weights: null pointer");
+  STG_REQUIRE(aligned16(wblob), STAGE_E_BADARG, "cqa_prepare_weights: blob must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* wb = static_cast<uint8_t*>(wblob);
+  float* vec = reinterpret_cast<float*>(wb + WB_VEC);
+  {
+    PackGeom g = pack_geom(128, 128, 64);
+    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 0, c2q_ln_g, g, wb + WB_WA);
+  }
+  {
+    PackGeom g = pack_geom(128, 256, 32);
+    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 128, c2q_ln_g, g, wb + WB_WU);
+  }
+  {
+    PackGeom g = pack_geom(128, 384, 32);
+    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(cat_w, 384, 0, cat_ln_g, g, wb + WB_WF);
+  }
+  fold_layernorm_kernel<<<16, 256, 0, s>>>(c2q_w, 128, 384, c2q_ln_g, c2q_ln_b, c2q_b, vec, vec + 128);
+  fold_layernorm_kernel<<<16, 256, 0, s>>>(cat_w, 128, 384, cat_ln_g, cat_ln_b, cat_b, vec + 256, vec + 384);
+  cudaMemsetAsync(vec + 512, 0, 512, s);
+  return check_launch("cqa_prepare_weights");
+}
+
+static size_t align128(size_t x) { return (x + 127) & ~static_cast<size_t>(127); }
+
+size_t stage_cqa_workspace_bytes(int n, int t, int lq) {
+  if (n <= 0 || t <= 0 || lq <= 0) return 0;
+  return align128(static_cast<size_t>(n) * 5 * CqaCfg::ABLOB_BYTES) + align128(static_cast<size_t>(n) * t * CqaCfg::CTX_BYTES) +
+         align128(static_cast<size_t>(n) * 5 * lq * 128 * sizeof(float));
+}
+
 int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   STG_REQUIRE(a && a->a_embed && a->a_mask && a->sub_embed && a->sub_mask && a->vid_embed && a->vid_mask, STAGE_E_BADARG,
               "cqa: null input (single-stream models are not built yet)");
-  STG_REQUIRE(a->c2q_ln_g && a->c2q_ln_b && a->c2q_w_packed && a->c2q_b && a->cat_ln_g && a->cat_ln_b && a->cat_w_packed &&
-                  a->cat_b && a->cat_out_ln_g && a->cat_out_ln_b, STAGE_E_BADARG, "cqa: null weight");
+  STG_REQUIRE(a->wblob && a->cat_out_ln_g && a->cat_out_ln_b && a->workspace, STAGE_E_BADARG, "cqa: null weight blob / workspace");
   STG_REQUIRE(a->statement && a->statement_mask, STAGE_E_BADARG, "cqa: null output");
   STG_REQUIRE(a->n > 0 && a->t > 0 && a->lq > 0 && a->ls > 0 && a->r > 0, STAGE_E_BADARG, "cqa: non-positive size");
   STG_REQUIRE(a->lq <= 128 && a->ls <= CqaCfg::LS_MAX && a->r <= CqaCfg::R_MAX, STAGE_E_UNSUPPORTED,
               "cqa: lq=%d ls=%d r=%d exceed the tile (128, %d, %d)", a->lq, a->ls, a->r, CqaCfg::LS_MAX, CqaCfg::R_MAX);
   STG_REQUIRE(aligned16(a->a_embed) && aligned16(a->sub_embed) && aligned16(a->vid_embed) && aligned16(a->statement) &&
-                  aligned16(a->c2q_w_packed) && aligned16(a->cat_w_packed), STAGE_E_BADARG, "cqa: pointers must be 16-byte aligned");
+                  aligned16(a->wblob) && (reinterpret_cast<uintptr_t>(a->workspace) & 127u) == 0, STAGE_E_BADARG,
+              "cqa: pointers must be 16-byte (workspace 128-byte) aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint8_t* wb = static_cast<const uint8_t*>(a->wblob);
+  const float* vec = reinterpret_cast<const float*>(wb + WB_VEC);
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  uint8_t* a_blob = ws;
+  uint8_t* ctx_blob = a_blob + align128(static_cast<size_t>(a->n) * 5 * CqaCfg::ABLOB_BYTES);
+  float* za = reinterpret_cast<float*>(ctx_blob + align128(static_cast<size_t>(a->n) * a->t * CqaCfg::CTX_BYTES));
+  const int ls_pad = round_up(a->ls, 16), r_pad = round_up(a->r, 16);
+  // 1. operand images
+  {
+    CqaPrepDev d;
+    d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad;
+    d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
+    d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask; d.a_blob = a_blob; d.ctx_blob = ctx_blob;
+    const long long warps = static_cast<long long>(a->n) * 5 * 128 + static_cast<long long>(a->n) * a->t * (ls_pad + r_pad);
+    cqa_prep_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(d);
+    int rc = check_launch("cqa_prep");
+    if (rc) return rc;
+  }
+  // 2. frame-invariant third of c2q: Za = a . (Wc*gamma)[:, :128]^T
+  {
+    LinearDev d;
+    d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.ln_in_g = nullptr; d.ln_in_b = nullptr;
+    d.ln_out_g = nullptr; d.ln_out_b = nullptr; d.y = za; d.m = static_cast<long long>(a->n) * 5 * a->lq;
+    d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0;
+    int rc = launch_linear<128, 64, 3>(d, s);
+    if (rc) return rc;
+  }
+  // 3. the fused kernel
   CqaDev d;
-  d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r;
-  d.ls_pad = round_up(a->ls, 16); d.r_pad = round_up(a->r, 16); d.scale = a->scale;
-  d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
-  d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask;
-  d.c2q_g = a->c2q_ln_g; d.c2q_b = a->c2q_ln_b; d.c2q_w = static_cast<const uint8_t*>(a->c2q_w_packed); d.c2q_bias = a->c2q_b;
-  d.cat_g = a->cat_ln_g; d.cat_b = a->cat_ln_b; d.cat_w = static_cast<const uint8_t*>(a->cat_w_packed); d.cat_bias = a->cat_b;
+  d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.scale = a->scale;
+  d.a_embed = a->a_embed; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.za = za;
+  d.c2q_w = wb + WB_WU; d.c2q_cs = vec; d.c2q_cb = vec + 128; d.cat_w = wb + WB_WF; d.cat_cs = vec + 256; d.cat_cb = vec + 384;
   d.out_g = a->cat_out_ln_g; d.out_b = a->cat_out_ln_b;
   d.statement = a->statement; d.statement_mask = a->statement_mask;
   d.vid_raw_s = a->vid_raw_s; d.sub_raw_s = a->sub_raw_s; d.vid_norm_s = a->vid_norm_s; d.sub_norm_s = a->sub_norm_s;
@@ -168,7 +238,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   if (rc) return rc;
   const int frames = a->n * a->t;
   const int grid = frames < num_sms() ? frames : num_sms();
-  cqa_kernel<<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(d);
+  cqa_kernel<<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, s>>>(d);
   return check_launch("cqa");
 }
 

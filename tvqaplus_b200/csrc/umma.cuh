@@ -119,6 +119,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "memory");
 }
 
+// 32 lanes x 32-bit, 16 consecutive columns, registers -> TMEM (thread t of the warp writes row lane-base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // descriptors
 // ------------------------------------------------------------------------------------------------
@@ -160,10 +171,12 @@ struct HL8 {  // 8 consecutive k values: 16 B of hi and 16 B of lo
   uint4 hi, lo;
 };
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-  __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-  hi = static_cast<uint32_t>(__half_as_ushort(ha)) | (static_cast<uint32_t>(__half_as_ushort(hb)) << 16);
-  lo = static_cast<uint32_t>(__half_as_ushort(la)) | (static_cast<uint32_t>(__half_as_ushort(lb)) << 16);
+  // packed conversions (F2FP.F16.F32.PACK_AB) instead of two scalar F2F each
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ HL8 split8(const float* v) {
   HL8 o;

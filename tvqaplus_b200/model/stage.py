@@ -183,9 +183,11 @@ class STAGE(nn.Module):
 
     def _cqa_weights(self):
         c2q, cat = self.c2q_down_projection, self.concat_fc
-        return dict(c2q_ln_g=c2q[0].weight, c2q_ln_b=c2q[0].bias, c2q_w_packed=packed(c2q[2].weight, 32), c2q_b=c2q[2].bias,
-                    cat_ln_g=cat[0].weight, cat_ln_b=cat[0].bias, cat_w_packed=packed(cat[2].weight, 32), cat_b=cat[2].bias,
-                    cat_out_ln_g=cat[4].weight, cat_out_ln_b=cat[4].bias)
+        params = (c2q[0].weight, c2q[0].bias, c2q[2].weight, c2q[2].bias, cat[0].weight, cat[0].bias, cat[2].weight, cat[2].bias)
+        tag = tuple((t.data_ptr(), t._version) for t in params)
+        if getattr(self, "_cqa_tag", None) != tag:  # re-fold after an optimizer step / load_state_dict / .to()
+            self._cqa_blob, self._cqa_tag = ops.cqa_prepare_weights(*params), tag
+        return dict(wblob=self._cqa_blob, cat_out_ln_g=cat[4].weight, cat_out_ln_b=cat[4].bias)
 
     def _head_weights(self):
         w = {}

@@ -115,14 +115,25 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
     return y
 
 
+def cqa_prepare_weights(c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, cat_w, cat_b) -> torch.Tensor:
+    """Fold LayerNorm(384) into c2q_down_projection / concat_fc and build their split-fp16 images
+    (stage_cqa_prepare_weights).  Re-run whenever one of the eight parameters changes."""
+    ts = [_f32(t.detach()) for t in (c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, cat_w, cat_b)]
+    blob = torch.empty(lib().stage_cqa_weight_blob_bytes(), dtype=torch.uint8, device=ts[0].device)
+    check(lib().stage_cqa_prepare_weights(*[ptr(t) for t in ts], ptr(blob), current_stream()),
+          "stage_cqa_prepare_weights")
+    _count(6)
+    return blob
+
+
 def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
                   want: Sequence[str] = ()) -> dict:
     """Fused StructuredAttention x2 + c2q_down_projection x2 + concat_fc (stage_cqa_fused_fwd).
 
     a_embed (N,5,Lq,128), a_mask (N,5,Lq), sub_embed (N,T,Ls,128), sub_mask (N,T,Ls), vid_embed (N,T,R,128),
-    vid_mask (N,T,R).  ``w`` holds c2q_ln_g/b, c2q_w_packed (kc=32), c2q_b, cat_ln_g/b, cat_w_packed (kc=32), cat_b,
-    cat_out_ln_g/b.  ``want`` lists optional extra outputs: vid_raw_s, sub_raw_s, vid_norm_s, sub_norm_s, att_vid,
-    att_sub, mixed_vid, mixed_sub.  Returns dict with ``statement`` (N,5,T,Lq,128), ``statement_mask`` (N,5,T,Lq).
+    vid_mask (N,T,R).  ``w`` holds ``wblob`` (cqa_prepare_weights) and cat_out_ln_g/b.  ``want`` lists optional extra
+    outputs: vid_raw_s, sub_raw_s, vid_norm_s, sub_norm_s, att_vid, att_sub, mixed_vid, mixed_sub.
+    Returns dict with ``statement`` (N,5,T,Lq,128), ``statement_mask`` (N,5,T,Lq).
     """
     a_embed, a_mask = _f32(a_embed), _f32(a_mask)
     sub_embed, sub_mask, vid_embed, vid_mask = _f32(sub_embed), _f32(sub_mask), _f32(vid_embed), _f32(vid_mask)
@@ -139,17 +150,17 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
               "mixed_vid": (N, 5, T, Lq, D), "mixed_sub": (N, 5, T, Lq, D)}
     for k in want:
         out[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+    ws_bytes = lib().stage_cqa_workspace_bytes(N, T, Lq)
+    ws = torch.empty(ws_bytes + 128, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 127) // 128 * 128
     a = _lib.CqaArgs(n=N, t=T, lq=Lq, ls=Ls, r=R, scale=float(scale),
                      a_embed=ptr(a_embed), a_mask=ptr(a_mask), sub_embed=ptr(sub_embed), sub_mask=ptr(sub_mask),
-                     vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask),
-                     c2q_ln_g=ptr(w["c2q_ln_g"]), c2q_ln_b=ptr(w["c2q_ln_b"]), c2q_w_packed=ptr(w["c2q_w_packed"]),
-                     c2q_b=ptr(w["c2q_b"]), cat_ln_g=ptr(w["cat_ln_g"]), cat_ln_b=ptr(w["cat_ln_b"]),
-                     cat_w_packed=ptr(w["cat_w_packed"]), cat_b=ptr(w["cat_b"]),
-                     cat_out_ln_g=ptr(w["cat_out_ln_g"]), cat_out_ln_b=ptr(w["cat_out_ln_b"]),
-                     statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
+                     vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask), wblob=ptr(w["wblob"]),
+                     cat_out_ln_g=ptr(_f32(w["cat_out_ln_g"])), cat_out_ln_b=ptr(_f32(w["cat_out_ln_b"])),
+                     workspace=ws_ptr, statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
                      **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
-    _count()
+    _count(3)
     return out
 
 
