@@ -143,6 +143,7 @@ typedef struct {
   float* att_sub;              /* optional */
   float* mixed_vid;            /* optional [n,5,t,lq,128] c2q output */
   float* mixed_sub;            /* optional */
+  long long* timeline;         /* optional debug: [2][64][16] SM clock stamps of CTA 0 (see tools/cqa_timeline.py) */
 } StageCqaArgs;
 int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream);
 

@@ -1,0 +1,37 @@
+"""Phase timeline of the fused CQA kernel (CTA 0, first tiles): SM-clock stamps taken by compute thread 0 and the MMA thread."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from tvqaplus_b200 import ops  # noqa: E402
+
+N, T, Lq, Ls, R = 2, 300, 100, 100, 20
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+a = torch.randn(N, 5, Lq, 128, generator=g).to(dev)
+s = torch.randn(N, T, Ls, 128, generator=g).to(dev)
+v = torch.randn(N, T, R, 128, generator=g).to(dev)
+ones = lambda *sh: torch.ones(*sh, device=dev)
+w = dict(wblob=ops.cqa_prepare_weights(torch.ones(384, device=dev), torch.zeros(384, device=dev), torch.randn(128, 384, device=dev) * 0.05,
+                                       torch.zeros(128, device=dev), torch.ones(384, device=dev), torch.zeros(384, device=dev),
+                                       torch.randn(128, 384, device=dev) * 0.05, torch.zeros(128, device=dev)),
+         cat_out_ln_g=torch.ones(128, device=dev), cat_out_ln_b=torch.zeros(128, device=dev))
+tl = torch.zeros(2, 64, 16, dtype=torch.int64, device=dev)
+for _ in range(2):
+    ops.cqa_fused_fwd(a, ones(N, 5, Lq), s, ones(N, T, Ls), v, ones(N, T, R), w, 10.0, timeline=tl)
+torch.cuda.synchronize()
+tl = tl.cpu()
+c, m = tl[0], tl[1]
+names_c = ["start", "pre-D1", "D1", "softmax done", "E2 sent", "D2", "c2q prod done", "stats done", "D3", "cat prod done", "D4", "end"]
+names_m = ["start", "AQ landed", "S issued", "E2 seen", "U done", "c2q-sub issued", "D3 commit", "D4 commit", "D4 done"]
+t0 = int(c[2][0])
+for tile in range(2, 8):
+    print("tile", tile)
+    print("  compute:", "  ".join("%s %d" % (names_c[i], int(c[tile][i]) - t0) for i in range(12)))
+    print("  mma    :", "  ".join("%s %d" % (names_m[i], int(m[tile][i]) - t0) for i in range(9)))
+d = (c[3:40, 1:12] - c[3:40, 0:11]).float().mean(0)
+print("compute mean phase cycles:", {names_c[i + 1]: int(d[i]) for i in range(11)}, "tile total", int((c[4:40, 0] - c[3:39, 0]).float().mean()))
+dm = (m[3:40, 1:9] - m[3:40, 0:8]).float().mean(0)
+print("mma mean phase cycles:", {names_m[i + 1]: int(dm[i]) for i in range(8)})

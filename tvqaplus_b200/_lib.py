@@ -38,7 +38,7 @@ class CqaArgs(C.Structure):
                 ("wblob", _f), ("cat_out_ln_g", _f), ("cat_out_ln_b", _f), ("workspace", _f),
                 ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
                 ("vid_norm_s", _f), ("sub_norm_s", _f), ("att_vid", _f), ("att_sub", _f),
-                ("mixed_vid", _f), ("mixed_sub", _f)]
+                ("mixed_vid", _f), ("mixed_sub", _f), ("timeline", _f)]
 
 
 class HeadArgs(C.Structure):

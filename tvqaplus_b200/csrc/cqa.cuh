@@ -78,6 +78,7 @@ struct CqaDev {
   float* statement; float* statement_mask;
   float* vid_raw_s; float* sub_raw_s; float* vid_norm_s; float* sub_norm_s;
   float* att_vid; float* att_sub; float* mixed_vid; float* mixed_sub;
+  long long* timeline;  // optional [2][64][16] clock64 stamps of block 0 (compute thread 0 / MMA thread), first 64 tiles
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -149,81 +150,6 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
 // ------------------------------------------------------------------------------------------------------------------
 // compute-side helpers
 // ------------------------------------------------------------------------------------------------------------------
-struct RowStats { float s1, s2; };  // running sum and sum of squares
-
-// masked + scaled scores of NCH 16-column chunks starting at chunk c0 of one stream; returns the running max
-template <int NCH>
-__device__ __forceinline__ float score_chunks(float* s, uint32_t trow, int c0, int n_real, int n_pad, float inv_a,
-                                              float mask_a, const float* inv_c, const float* mask_c, float scale,
-                                              float* raw_out, float mx) {
-#pragma unroll
-  for (int c = 0; c < NCH; ++c)
-    if ((c0 + c) * 16 < n_pad) tmem_ld16(trow + (c0 + c) * 16, s + c * 16);
-  tmem_wait_ld();
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if ((c0 + c) * 16 < n_pad) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = (c0 + c) * 16 + j;
-        if (col < n_real) {
-          const float m = mask_a * mask_c[col];
-          float v = s[c * 16 + j] * inv_a * inv_c[col];
-          v = v - 1e10f * (1.f - m);  // exactly the reference's S - 1e10*(1 - S_mask)
-          if (raw_out != nullptr) raw_out[col] = v;
-          v *= scale;
-          s[c * 16 + j] = v;
-          mx = fmaxf(mx, v);
-        }
-      }
-    }
-  }
-  return mx;
-}
-template <int NCH>
-__device__ __forceinline__ float exp_chunks(float* s, int c0, int n_real, int n_pad, float mx) {
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if ((c0 + c) * 16 < n_pad) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = (c0 + c) * 16 + j;
-        float e = 0.f;
-        if (col < n_real) { e = expf(s[c * 16 + j] - mx); sum += e; }
-        s[c * 16 + j] = e;
-      }
-    }
-  }
-  return sum;
-}
-template <int NCH>
-__device__ __forceinline__ void write_p_chunks(float* s, int c0, int n_real, int n_pad, float inv_sum, float mask_a,
-                                               const float* mask_c, uint8_t* p_img, uint32_t p_part, int row,
-                                               float* norm_out) {
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if ((c0 + c) * 16 < n_pad) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = (c0 + c) * 16 + j;
-        if (col < n_real) {
-          const float pj = s[c * 16 + j] * inv_sum * (mask_a * mask_c[col]);
-          s[c * 16 + j] = pj;
-          if (norm_out != nullptr) norm_out[col] = pj;
-        }
-      }
-#pragma unroll
-      for (int h8 = 0; h8 < 2; ++h8) {
-        HL8 hl = split8(s + c * 16 + h8 * 8);
-        uint8_t* dst = p_img + ((c0 + c) * 2 + h8) * CqaCfg::LBO_A + row * 16;
-        *reinterpret_cast<uint4*>(dst) = hl.hi;
-        *reinterpret_cast<uint4*>(dst + p_part) = hl.lo;
-      }
-    }
-  }
-}
-
 // store one K=32 A chunk (32 fp32 values of this thread's row) into an A stage, then publish it
 __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int row, uint64_t* full) {
 #pragma unroll
@@ -237,12 +163,19 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
   mbar_arrive(full);
 }
 
+#define CQA_STAMP(who, idx)                                                                         \
+  do {                                                                                              \
+    if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64)                                   \
+      p.timeline[((who) * 64 + tl_tile) * 16 + (idx)] = clock64();                                  \
+  } while (0)
+
 __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, a_full[4], a_empty[4], w_full[CqaCfg::W_SLOTS],
       w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
   __shared__ float xch[8][128];
+  __shared__ float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sCTX = smem + CqaCfg::OFF_CTX;
@@ -286,10 +219,16 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
     const uint32_t coff = lane_off + half * 64;
     const bool live = row < p.lq;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
+    int tl_tile = (tid == 0) ? 0 : 64;
     float any_v = 0.f;  // does this frame have at least one valid region?  (S_mask.sum(-1) != 0, stage.py:386)
     uint64_t* my_full = &a_full[half * 2];
     uint64_t* my_empty = &a_empty[half * 2];
     uint8_t* my_stage = sAQ + half * 2 * CqaCfg::AST_BYTES;
+    for (int i = tid; i < 128; i += 256) {  // per-column vectors of the folded GEMM epilogues
+      pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
+      pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
@@ -297,71 +236,124 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
         const size_t tile = na * p.t + t_i;
         const size_t orow = (tile * p.lq + row) * 128;
-        // ---- per-row data of the answer tile + my 64 answer values (columns [64*half, +64))
+        CQA_STAMP(0, 0);
         const float* rd = reinterpret_cast<const float*>(p.a_blob + na * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row), asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);
-        float a_reg[64];
-        {
-          const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + half * 64);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
-          }
-        }
         if (a_i == 0) {
           mbar_wait(&ctx_full, frame_cnt & 1u, 30);  // ctx blob (images + inv norms + masks) has landed
           any_v = 0.f;
           for (int j = 0; j < p.r; ++j) any_v += mask_cv[j];
         }
 
-        // ---- softmax of both streams; the 7 sub + 3 vid score chunks are split 5 / 5 between the two column halves
+        // ---- softmax of both streams: the 7 sub + 3 vid score chunks (16 columns each) are split 5 / 5 between the two
+        //      column halves; slot k of half 0 = sub 0..3, vid 0; of half 1 = sub 4..6, vid 1..2
+        CQA_STAMP(0, 1);
         mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
         ++done_cnt;
         tc_fence_after();
+        CQA_STAMP(0, 2);
         {
           float s[80];
           float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
           float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
           float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
           float* nrm_v = (p.vid_norm_s && live) ? p.vid_norm_s + (tile * p.lq + row) * p.r : nullptr;
+#define CQA_SLOT(k)                                                                      \
+  const bool vid = half ? ((k) >= 3) : ((k) == 4);                                        \
+  const int ch = half ? (vid ? (k) - 2 : (k) + 4) : (vid ? 0 : (k));                      \
+  const int n_real = vid ? p.r : p.ls;                                                    \
+  const bool on = ch * 16 < (vid ? p.r_pad : p.ls_pad);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            CQA_SLOT(k)
+            (void)n_real;
+            if (on) tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, s + k * 16);
+          }
+          tmem_wait_ld();
           float mxs = -3.0e38f, mxv = -3.0e38f;
-          if (half == 0) {
-            mxs = score_chunks<4>(s, T0 + lane_off, 0, p.ls, p.ls_pad, ia, ma, inv_cs, mask_cs, p.scale, raw_s, mxs);
-            mxv = score_chunks<1>(s + 64, T1 + lane_off, 0, p.r, p.r_pad, ia, ma, inv_cv, mask_cv, p.scale, raw_v, mxv);
-          } else {
-            mxs = score_chunks<3>(s, T0 + lane_off, 4, p.ls, p.ls_pad, ia, ma, inv_cs, mask_cs, p.scale, raw_s, mxs);
-            mxv = score_chunks<2>(s + 48, T1 + lane_off, 1, p.r, p.r_pad, ia, ma, inv_cv, mask_cv, p.scale, raw_v, mxv);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            CQA_SLOT(k)
+            if (on) {
+              const float* ic = vid ? inv_cv : inv_cs;
+              const float* mc = vid ? mask_cv : mask_cs;
+              float* raw = vid ? raw_v : raw_s;
+              float mx = -3.0e38f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = ch * 16 + j;
+                if (col < n_real) {
+                  const float m = ma * mc[col];
+                  float v = s[k * 16 + j] * ia * ic[col];
+                  v = v - 1e10f * (1.f - m);  // exactly the reference's S - 1e10*(1 - S_mask)
+                  if (raw != nullptr) raw[col] = v;
+                  v *= p.scale;
+                  s[k * 16 + j] = v;
+                  mx = fmaxf(mx, v);
+                }
+              }
+              if (vid) mxv = fmaxf(mxv, mx); else mxs = fmaxf(mxs, mx);
+            }
           }
           xch[half][row] = mxs;
           xch[2 + half][row] = mxv;
           asm volatile("bar.sync 1, 256;" ::: "memory");
           mxs = fmaxf(xch[0][row], xch[1][row]);
           mxv = fmaxf(xch[2][row], xch[3][row]);
-          float sms, smv;
-          if (half == 0) {
-            sms = exp_chunks<4>(s, 0, p.ls, p.ls_pad, mxs);
-            smv = exp_chunks<1>(s + 64, 0, p.r, p.r_pad, mxv);
-          } else {
-            sms = exp_chunks<3>(s, 4, p.ls, p.ls_pad, mxs);
-            smv = exp_chunks<2>(s + 48, 1, p.r, p.r_pad, mxv);
+          float sms = 0.f, smv = 0.f;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            CQA_SLOT(k)
+            if (on) {
+              const float mx = vid ? mxv : mxs;
+              float sum = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float e = 0.f;
+                if (ch * 16 + j < n_real) { e = expf(s[k * 16 + j] - mx); sum += e; }
+                s[k * 16 + j] = e;
+              }
+              if (vid) smv += sum; else sms += sum;
+            }
           }
           xch[4 + half][row] = sms;
           xch[6 + half][row] = smv;
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const float is = 1.f / (xch[4][row] + xch[5][row]), iv = 1.f / (xch[6][row] + xch[7][row]);
-          if (half == 0) {
-            write_p_chunks<4>(s, 0, p.ls, p.ls_pad, is, ma, mask_cs, sB, CqaCfg::PS_PART, row, nrm_s);
-            write_p_chunks<1>(s + 64, 0, p.r, p.r_pad, iv, ma, mask_cv, sAQ, CqaCfg::PV_PART, row, nrm_v);
-          } else {
-            write_p_chunks<3>(s, 4, p.ls, p.ls_pad, is, ma, mask_cs, sB, CqaCfg::PS_PART, row, nrm_s);
-            write_p_chunks<2>(s + 48, 1, p.r, p.r_pad, iv, ma, mask_cv, sAQ, CqaCfg::PV_PART, row, nrm_v);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            CQA_SLOT(k)
+            if (on) {
+              const float* mc = vid ? mask_cv : mask_cs;
+              float* nrm = vid ? nrm_v : nrm_s;
+              const float isum = vid ? iv : is;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = ch * 16 + j;
+                if (col < n_real) {
+                  const float pj = s[k * 16 + j] * isum * (ma * mc[col]);
+                  s[k * 16 + j] = pj;
+                  if (nrm != nullptr) nrm[col] = pj;
+                }
+              }
+              uint8_t* img = vid ? sAQ : sB;                       // P_vid overlays the answer image, P_sub the weight ring
+              const uint32_t part = vid ? CqaCfg::PV_PART : CqaCfg::PS_PART;
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                HL8 hl = split8(s + k * 16 + h8 * 8);
+                uint8_t* dst = img + (ch * 2 + h8) * CqaCfg::LBO_A + row * 16;
+                *reinterpret_cast<uint4*>(dst) = hl.hi;
+                *reinterpret_cast<uint4*>(dst + part) = hl.lo;
+              }
+            }
           }
+#undef CQA_SLOT
         }
+        CQA_STAMP(0, 3);
         // ---- hoisted a.Wa term -> both c2q accumulators (S has been consumed by every thread: second bar.sync above)
         {
           const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + half * 64);
-#pragma unroll
+#pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
             float z[16];
 #pragma unroll
@@ -377,12 +369,24 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(&op_ready);  // E2: P images + accumulator pre-loads are in place
+        CQA_STAMP(0, 4);
+        // ---- my 64 answer values (columns [64*half, +64) of the row); the loads fly while U = P.ctx runs
+        float a_reg[64];
+        {
+          const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + half * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
+          }
+        }
 
         // ---- c2q A operands for both streams: raw [U, a*U] chunks, statistics on the fly
         mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
         ++done_cnt;
         tc_fence_after();
-        RowStats st[2];
+        CQA_STAMP(0, 5);
+        float st_s1[2], st_s2[2];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint32_t tU = (g == 0 ? T2 : T3) + coff;
@@ -390,33 +394,50 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
-            float u[32], pu[32];
-            tmem_ld16(tU + b * 32, u);
-            tmem_ld16(tU + b * 32 + 16, u + 16);
-            tmem_wait_ld();
+            // the U chunk and the a*U chunk of these 32 columns are filled side by side, 16 columns at a time
+            const uint32_t sU = a_use & 1u, sP = sU ^ 1u;
+            mbar_wait(&my_empty[sU], ((a_use >> 1) & 1u) ^ 1u, 33);
+            mbar_wait(&my_empty[sP], (((a_use + 1) >> 1) & 1u) ^ 1u, 34);
+            uint8_t* stU = my_stage + sU * CqaCfg::AST_BYTES;
+            uint8_t* stP = my_stage + sP * CqaCfg::AST_BYTES;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              pu[j] = a_reg[b * 32 + j] * u[j];
-              s1 += u[j] + pu[j];
-              s2 += u[j] * u[j] + pu[j] * pu[j];
-            }
-            if (att != nullptr && live) {
+            for (int sl = 0; sl < 2; ++sl) {
+              float u[16], pu[16];
+              tmem_ld16(tU + b * 32 + sl * 16, u);
+              tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(att + orow + half * 64 + b * 32 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+              for (int j = 0; j < 16; ++j) {
+                pu[j] = a_reg[b * 32 + sl * 16 + j] * u[j];
+                s1 += u[j] + pu[j];
+                s2 += u[j] * u[j] + pu[j] * pu[j];
+              }
+              if (att != nullptr && live) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(att + orow + half * 64 + b * 32 + sl * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+              }
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                HL8 hu = split8(u + h8 * 8), hp = split8(pu + h8 * 8);
+                uint8_t* du = stU + (sl * 2 + h8) * CqaCfg::LBO_A + row * 16;
+                uint8_t* dp = stP + (sl * 2 + h8) * CqaCfg::LBO_A + row * 16;
+                *reinterpret_cast<uint4*>(du) = hu.hi;
+                *reinterpret_cast<uint4*>(du + CqaCfg::AST_PART) = hu.lo;
+                *reinterpret_cast<uint4*>(dp) = hp.hi;
+                *reinterpret_cast<uint4*>(dp + CqaCfg::AST_PART) = hp.lo;
+              }
             }
-            mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 33);
-            put_chunk(u, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
-            ++a_use;
-            mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 34);
-            put_chunk(pu, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
-            ++a_use;
+            fence_async_smem();
+            mbar_arrive(&my_full[sU]);
+            mbar_arrive(&my_full[sP]);
+            a_use += 2;
           }
-          st[g].s1 = s1;
-          st[g].s2 = s2;
+          st_s1[g] = s1;
+          st_s2[g] = s2;
         }
-        xch[half][row] = st[0].s1; xch[2 + half][row] = st[0].s2;
-        xch[4 + half][row] = st[1].s1; xch[6 + half][row] = st[1].s2;
+        CQA_STAMP(0, 6);
+        xch[half][row] = st_s1[0]; xch[2 + half][row] = st_s2[0];
+        xch[4 + half][row] = st_s1[1]; xch[6 + half][row] = st_s2[1];
         asm volatile("bar.sync 1, 256;" ::: "memory");
         float mu_s, r_s, mu_v, r_v;
         {
@@ -431,11 +452,13 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 
         // ---- concat_fc A operands: [ms, mv, ms*mv] with ms/mv = relu(rstd*(acc - mean*cs) + cb)
         tc_fence_before();
+        CQA_STAMP(0, 7);
         mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
         ++done_cnt;
         tc_fence_after();
+        CQA_STAMP(0, 8);
         float c1 = 0.f, c2 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < 2; ++b) {
           float ms[32], mv[32];
           tmem_ld16(T0 + coff + b * 32, ms);
@@ -446,7 +469,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int c = half * 64 + b * 32 + j;
-            const float cs = __ldg(p.c2q_cs + c), cb = __ldg(p.c2q_cb + c);
+            const float cs = pvec[0][c], cb = pvec[1][c];
             ms[j] = fmaxf(r_s * (ms[j] - mu_s * cs) + cb, 0.f);
             mv[j] = fmaxf(r_v * (mv[j] - mu_v * cs) + cb, 0.f);
           }
@@ -477,6 +500,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           put_chunk(ms, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
           ++a_use;
         }
+        CQA_STAMP(0, 9);
         xch[half][row] = c1;
         xch[2 + half][row] = c2;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -488,9 +512,10 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         mbar_wait(&mma_done, done_cnt & 1u, 39);  // D4: concat accumulator complete
         ++done_cnt;
         tc_fence_after();
+        CQA_STAMP(0, 10);
         {
           float o1 = 0.f, o2 = 0.f;
-#pragma unroll
+#pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
             float v[16];
             tmem_ld16(T2 + coff + cc * 16, v);
@@ -498,7 +523,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int c = half * 64 + cc * 16 + j;
-              const float o = fmaxf(r_c * (v[j] - mu_c * __ldg(p.cat_cs + c)) + __ldg(p.cat_cb + c), 0.f);
+              const float o = fmaxf(r_c * (v[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
               o1 += o;
               o2 += o * o;
             }
@@ -508,7 +533,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const float mean = (xch[4][row] + xch[5][row]) * (1.f / 128.f);
           const float rstd = 1.f / sqrtf(fmaxf((xch[6][row] + xch[7][row]) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
+#pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {
             float v[16];
             tmem_ld16(T2 + coff + cc * 16, v);
@@ -516,8 +541,8 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int c = half * 64 + cc * 16 + j;
-              const float o = fmaxf(r_c * (v[j] - mu_c * __ldg(p.cat_cs + c)) + __ldg(p.cat_cb + c), 0.f);
-              v[j] = (o - mean) * rstd * __ldg(p.out_g + c) + __ldg(p.out_b + c);
+              const float o = fmaxf(r_c * (v[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
+              v[j] = (o - mean) * rstd * pvec[4][c] + pvec[5][c];
             }
             if (live) {
 #pragma unroll
@@ -530,11 +555,14 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 256;" ::: "memory");  // xch is rewritten by the next tile
+        CQA_STAMP(0, 11);
+        ++tl_tile;
       }
     }
   } else if (lane == 0) {
     // =================================================================== MMA issue + every bulk copy (one thread)
     uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0, ah_cnt0 = 0, ah_cnt1 = 0;
+    int tl_tile = 0;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
     const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
@@ -545,12 +573,14 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
       bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
       for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
         const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
+        CQA_STAMP(1, 0);
         // ---- answer image: AQ region (A stages of the previous tile) is free once D4 has completed (waited below)
         mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
         bulk_g2s(sAQ, p.a_blob + na * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
         if (a_i == 0) mbar_wait(&ctx_full, frame_cnt & 1u, 40);
         mbar_wait(&aq_full, tile_cnt & 1u, 41);
         tc_fence_after();
+        CQA_STAMP(1, 1);
         // ---- S = a . ctx^T for both streams
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -565,10 +595,12 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         }
         umma_commit(&mma_done);  // D1
         ++done_cnt;
+        CQA_STAMP(1, 2);
         // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
         mbar_wait(&op_ready, ready_cnt & 1u, 42);  // E2
         ++ready_cnt;
         tc_fence_after();
+        CQA_STAMP(1, 3);
         for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
           const uint64_t a_hi = make_smem_desc(ps + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
           const uint64_t a_lo = make_smem_desc(ps + CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
@@ -586,6 +618,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         umma_commit(&mma_done);  // D2
         mbar_wait(&mma_done, done_cnt & 1u, 43);  // P_sub (region B) and P_vid (region AQ) are free once U has completed
         ++done_cnt;
+        CQA_STAMP(1, 4);
         // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk order alternates between the column halves
         auto w_src = [&](int q) -> const uint8_t* {
           int c;
@@ -632,7 +665,9 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           if (q == 15 || q == CqaCfg::CHUNKS - 1) {
             umma_commit(&mma_done);  // D3 / D4
             ++done_cnt;
+            CQA_STAMP(1, q == 15 ? 6 : 7);
           }
+          if (q == 7) CQA_STAMP(1, 5);
           if (q + CqaCfg::W_SLOTS - 1 < CqaCfg::CHUNKS) {  // refill the slot chunk q-1 used
             const uint32_t qq = q_cnt + q + CqaCfg::W_SLOTS - 1;
             const uint32_t rslot = qq % CqaCfg::W_SLOTS, ruse = qq / CqaCfg::W_SLOTS;
@@ -644,6 +679,8 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         q_cnt += CqaCfg::CHUNKS;
         // the AQ region (A stages) and T0/T1 may only be reused after the concat MMAs have completed
         mbar_wait(&mma_done, (done_cnt - 1u) & 1u, 48);  // D4
+        CQA_STAMP(1, 8);
+        ++tl_tile;
       }
     }
   }

@@ -234,6 +234,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   d.statement = a->statement; d.statement_mask = a->statement_mask;
   d.vid_raw_s = a->vid_raw_s; d.sub_raw_s = a->sub_raw_s; d.vid_norm_s = a->vid_norm_s; d.sub_norm_s = a->sub_norm_s;
   d.att_vid = a->att_vid; d.att_sub = a->att_sub; d.mixed_vid = a->mixed_vid; d.mixed_sub = a->mixed_sub;
+  d.timeline = a->timeline;
   int rc = set_smem(cqa_kernel, CqaCfg::SMEM_BYTES, "cqa");
   if (rc) return rc;
   const int frames = a->n * a->t;

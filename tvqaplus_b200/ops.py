@@ -127,7 +127,7 @@ def cqa_prepare_weights(c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, ca
 
 
 def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
-                  want: Sequence[str] = ()) -> dict:
+                  want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None) -> dict:
     """Fused StructuredAttention x2 + c2q_down_projection x2 + concat_fc (stage_cqa_fused_fwd).
 
     a_embed (N,5,Lq,128), a_mask (N,5,Lq), sub_embed (N,T,Ls,128), sub_mask (N,T,Ls), vid_embed (N,T,R,128),
@@ -158,7 +158,7 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
                      vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask), wblob=ptr(w["wblob"]),
                      cat_out_ln_g=ptr(_f32(w["cat_out_ln_g"])), cat_out_ln_b=ptr(_f32(w["cat_out_ln_b"])),
                      workspace=ws_ptr, statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
-                     **{k: ptr(out.get(k)) for k in shapes})
+                     timeline=ptr(timeline), **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
     _count(3)
     return out
