@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
     const bool live = row < p.lq;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
     int tl_tile = (tid == 0) ? 0 : 64;
-    float any_v = 0.f;  // does this frame have at least one valid region?  (S_mask.sum(-1) != 0, stage.py:386)
+    float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
     uint64_t* my_full = &a_full[half * 2];
     uint64_t* my_empty = &a_empty[half * 2];
     uint8_t* my_stage = sAQ + half * 2 * CqaCfg::AST_BYTES;
@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         if (a_i == 0) {
           mbar_wait(&ctx_full, frame_cnt & 1u, 30);  // ctx blob (images + inv norms + masks) has landed
           any_v = 0.f;
+          any_s = 0.f;
           for (int j = 0; j < p.r; ++j) any_v += mask_cv[j];
+          for (int j = 0; j < p.ls; ++j) any_s += mask_cs[j];
         }
 
         // ---- softmax of both streams: the 7 sub + 3 vid score chunks (16 columns each) are split 5 / 5 between the two
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           }
           tmem_wait_ld();
           float mxs = -3.0e38f, mxv = -3.0e38f;
+          const float sc2 = p.scale * 1.4426950408889634f;
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
             CQA_SLOT(k)
@@ -283,11 +286,10 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
               for (int j = 0; j < 16; ++j) {
                 const int col = ch * 16 + j;
                 if (col < n_real) {
-                  const float m = ma * mc[col];
-                  float v = s[k * 16 + j] * ia * ic[col];
-                  v = v - 1e10f * (1.f - m);  // exactly the reference's S - 1e10*(1 - S_mask)
+                  // S - 1e10*(1 - S_mask) of the reference: |S| <= 1 is absorbed by -1e10 in fp32, so a select is exact
+                  float v = (ma * mc[col] != 0.f) ? s[k * 16 + j] * ia * ic[col] : -1e10f;
                   if (raw != nullptr) raw[col] = v;
-                  v *= p.scale;
+                  v *= sc2;  // scale * log2(e): the softmax below runs in base 2
                   s[k * 16 + j] = v;
                   mx = fmaxf(mx, v);
                 }
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float e = 0.f;
-                if (ch * 16 + j < n_real) { e = expf(s[k * 16 + j] - mx); sum += e; }
+                if (ch * 16 + j < n_real) { e = fast_exp2(s[k * 16 + j] - mx); sum += e; }
                 s[k * 16 + j] = e;
               }
               if (vid) smv += sum; else sms += sum;
@@ -319,19 +321,21 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           xch[4 + half][row] = sms;
           xch[6 + half][row] = smv;
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float is = 1.f / (xch[4][row] + xch[5][row]), iv = 1.f / (xch[6][row] + xch[7][row]);
+          // masked entries of a live row are exactly 0 (exp2(-1.4e11 - max) underflows); a fully masked row is uniform
+          // and must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
+          const float is = (ma != 0.f && any_s != 0.f) ? 1.f / (xch[4][row] + xch[5][row]) : 0.f;
+          const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / (xch[6][row] + xch[7][row]) : 0.f;
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
             CQA_SLOT(k)
             if (on) {
-              const float* mc = vid ? mask_cv : mask_cs;
               float* nrm = vid ? nrm_v : nrm_s;
               const float isum = vid ? iv : is;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int col = ch * 16 + j;
                 if (col < n_real) {
-                  const float pj = s[k * 16 + j] * isum * (ma * mc[col]);
+                  const float pj = s[k * 16 + j] * isum;
                   s[k * 16 + j] = pj;
                   if (nrm != nullptr) nrm[col] = pj;
                 }
