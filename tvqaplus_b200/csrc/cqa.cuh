@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   __shared__ float xch[8][128];
   __shared__ float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   uint8_t* sCTX = smem + CqaCfg::OFF_CTX;
   uint8_t* sCS = sCTX + CqaCfg::CTX_CS;
   uint8_t* sCV = sCTX + CqaCfg::CTX_CV;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float row_mean[128], row_rstd[128], row_mask[128];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   float* X = reinterpret_cast<float*>(smem);
   uint8_t* sA = smem + EncCfg::OFF_A;
   uint8_t* sW = smem + EncCfg::OFF_W;

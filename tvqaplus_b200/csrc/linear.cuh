@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float row_inv[128], row_mean[128], row_rstd[128];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
