@@ -16,7 +16,8 @@
 //                  MN-major for U), the answer image (one bulk copy per tile), P, and the A / W pipelines of the GEMMs
 //   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator, T1 = S_vid -> c2q(vid), T2 = U_sub -> concat accumulator,
 //                  T3 = U_vid
-// Warp roles (288 threads): warps 0-7 compute (thread = row, warp/4 = column half), warp 8 = MMA issue + all bulk copies.
+// Warp roles (544 threads): warps 0-15 compute (thread = row x column quarter; 4 warps per scheduler hide the FP and
+// TMEM latencies of the epilogue math), warp 16 = MMA issue + all bulk copies.
 //
 // Algorithmic work per (answer, frame) tile with Lq rows: 4*128*Lq*(Ls+R) + 3*(2*384*128)*Lq FLOP.
 #pragma once
@@ -56,9 +57,9 @@ struct CqaCfg {
   static constexpr uint32_t OFF_B = (OFF_AQ + AQ_BYTES + 127u) & ~127u;  // P_sub; later the weight ring
   static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                  // 65536 >= 2*PS_PART (57792)
   static constexpr uint32_t SMEM_BYTES = OFF_B + B_BYTES + 1024u;
-  static constexpr int THREADS = 288;
+  static constexpr int THREADS = 544;
   static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 chunks per tile: c2q(sub), c2q(vid), concat
-  static_assert(4u * AST_BYTES <= AQ_BYTES, "A stages overlay the answer image");
+  static_assert(4u * AST_BYTES <= AQ_BYTES, "the 4 A stages (one per column quarter) overlay the answer image");
   static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
   static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
 };
@@ -169,12 +170,12 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
       p.timeline[((who) * 64 + tl_tile) * 16 + (idx)] = clock64();                                  \
   } while (0)
 
-__global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
+__global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, a_full[4], a_empty[4], w_full[CqaCfg::W_SLOTS],
       w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float xch[8][128];
+  __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
   __shared__ float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&op_ready, 256);
+    mbar_init(&op_ready, 512);
     mbar_init(&mma_done, 1);
     mbar_init(&ctx_full, 1);
     mbar_init(&aq_full, 1);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
     }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<512>(&tmem_slot);
+  if (warp == 16) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -212,30 +213,47 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
   const uint32_t T0 = tbase, T1 = tbase + 128, T2 = tbase + 256, T3 = tbase + 384;
   const int n_frames = p.n * p.t;
 
-  if (warp < 8) {
+  if (warp < 16) {
     // =================================================================== compute warps
-    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    // thread = (row, quarter): row = 32*(warp & 3) + lane (the TMEM lane quadrant a warp may touch is warp % 4),
+    // quarter = warp / 4 owns columns [32*quarter, +32) of every 128-wide segment = exactly one K=32 chunk per segment
+    const int row = (warp & 3) * 32 + lane, qd = warp >> 2;
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
-    const uint32_t coff = lane_off + half * 64;
+    const uint32_t coff = lane_off + qd * 32;
     const bool live = row < p.lq;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
     int tl_tile = (tid == 0) ? 0 : 64;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
-    uint64_t* my_full = &a_full[half * 2];
-    uint64_t* my_empty = &a_empty[half * 2];
-    uint8_t* my_stage = sAQ + half * 2 * CqaCfg::AST_BYTES;
-    for (int i = tid; i < 128; i += 256) {  // per-column vectors of the folded GEMM epilogues
+    uint64_t* my_full = &a_full[qd];
+    uint64_t* my_empty = &a_empty[qd];
+    uint8_t* my_stage = sAQ + qd * CqaCfg::AST_BYTES;
+    for (int i = tid; i < 128; i += 512) {  // per-column vectors of the folded GEMM epilogues
       pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
       pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+
+    // publish one K=32 chunk: wait for the stage, let `fill(sl, v)` produce 16 columns at a time, split, store, arrive
+#define CQA_CHUNK_BEGIN(code)                                              \
+  mbar_wait(my_empty, (a_use & 1u) ^ 1u, code);                            \
+  ++a_use;
+#define CQA_CHUNK_PUT16(sl, v)                                             \
+  _Pragma("unroll") for (int h8 = 0; h8 < 2; ++h8) {                       \
+    HL8 hl = split8((v) + h8 * 8);                                         \
+    uint8_t* dst = my_stage + ((sl) * 2 + h8) * CqaCfg::LBO_A + row * 16;  \
+    *reinterpret_cast<uint4*>(dst) = hl.hi;                                \
+    *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;             \
+  }
+#define CQA_CHUNK_END()  \
+  fence_async_smem();    \
+  mbar_arrive(my_full);
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
       for (int a_i = 0; a_i < 5; ++a_i) {
         const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
         const size_t tile = na * p.t + t_i;
-        const size_t orow = (tile * p.lq + row) * 128;
+        const size_t orow = (tile * p.lq + row) * 128 + qd * 32;  // my 32 columns of this tile's output row
         CQA_STAMP(0, 0);
         const float* rd = reinterpret_cast<const float*>(p.a_blob + na * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row), asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);
@@ -247,26 +265,26 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           for (int j = 0; j < p.ls; ++j) any_s += mask_cs[j];
         }
 
-        // ---- softmax of both streams: the 7 sub + 3 vid score chunks (16 columns each) are split 5 / 5 between the two
-        //      column halves; slot k of half 0 = sub 0..3, vid 0; of half 1 = sub 4..6, vid 1..2
+        // ---- softmax of both streams: the 7 sub + 3 vid score chunks (16 columns each) are dealt to the quarters as
+        //      q0: sub 0,1,2   q1: sub 3,4,5   q2: sub 6, vid 0   q3: vid 1, 2
         CQA_STAMP(0, 1);
         mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
         ++done_cnt;
         tc_fence_after();
         CQA_STAMP(0, 2);
         {
-          float s[80];
+          float s[48];
           float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
           float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
           float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
           float* nrm_v = (p.vid_norm_s && live) ? p.vid_norm_s + (tile * p.lq + row) * p.r : nullptr;
-#define CQA_SLOT(k)                                                                      \
-  const bool vid = half ? ((k) >= 3) : ((k) == 4);                                        \
-  const int ch = half ? (vid ? (k) - 2 : (k) + 4) : (vid ? 0 : (k));                      \
-  const int n_real = vid ? p.r : p.ls;                                                    \
-  const bool on = ch * 16 < (vid ? p.r_pad : p.ls_pad);
+#define CQA_SLOT(k)                                                                   \
+  const bool vid = (qd == 3) || (qd == 2 && (k) == 1);                                 \
+  const int ch = qd < 2 ? 3 * qd + (k) : (qd == 2 ? ((k) == 0 ? 6 : 0) : (k) + 1);      \
+  const int n_real = vid ? p.r : p.ls;                                                 \
+  const bool on = (qd < 2 || (k) < 2) && ch * 16 < (vid ? p.r_pad : p.ls_pad);
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
+          for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             (void)n_real;
             if (on) tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, s + k * 16);
@@ -275,7 +293,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           float mxs = -3.0e38f, mxv = -3.0e38f;
           const float sc2 = p.scale * 1.4426950408889634f;
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
+          for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             if (on) {
               const float* ic = vid ? inv_cv : inv_cs;
@@ -297,14 +315,14 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
               if (vid) mxv = fmaxf(mxv, mx); else mxs = fmaxf(mxs, mx);
             }
           }
-          xch[half][row] = mxs;
-          xch[2 + half][row] = mxv;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          mxs = fmaxf(xch[0][row], xch[1][row]);
-          mxv = fmaxf(xch[2][row], xch[3][row]);
+          xq[0][qd][row] = mxs;
+          xq[1][qd][row] = mxv;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          mxs = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row]));
+          mxv = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row]));
           float sms = 0.f, smv = 0.f;
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
+          for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             if (on) {
               const float mx = vid ? mxv : mxs;
@@ -318,15 +336,15 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
               if (vid) smv += sum; else sms += sum;
             }
           }
-          xch[4 + half][row] = sms;
-          xch[6 + half][row] = smv;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          xq[2][qd][row] = sms;
+          xq[3][qd][row] = smv;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
           // masked entries of a live row are exactly 0 (exp2(-1.4e11 - max) underflows); a fully masked row is uniform
           // and must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
-          const float is = (ma != 0.f && any_s != 0.f) ? 1.f / (xch[4][row] + xch[5][row]) : 0.f;
-          const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / (xch[6][row] + xch[7][row]) : 0.f;
+          const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) : 0.f;
+          const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) : 0.f;
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
+          for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             if (on) {
               float* nrm = vid ? nrm_v : nrm_s;
@@ -356,9 +374,9 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         CQA_STAMP(0, 3);
         // ---- hoisted a.Wa term -> both c2q accumulators (S has been consumed by every thread: second bar.sync above)
         {
-          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + half * 64);
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
             float z[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -374,18 +392,18 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         fence_async_smem();
         mbar_arrive(&op_ready);  // E2: P images + accumulator pre-loads are in place
         CQA_STAMP(0, 4);
-        // ---- my 64 answer values (columns [64*half, +64) of the row); the loads fly while U = P.ctx runs
-        float a_reg[64];
+        // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
+        float a_reg[32];
         {
-          const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + half * 64);
+          const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + qd * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
           }
         }
 
-        // ---- c2q A operands for both streams: raw [U, a*U] chunks, statistics on the fly
+        // ---- c2q A operands for both streams: the raw U chunk, then the raw a*U chunk; statistics on the fly
         mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
         ++done_cnt;
         tc_fence_after();
@@ -396,65 +414,58 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           const uint32_t tU = (g == 0 ? T2 : T3) + coff;
           float* att = g == 0 ? p.att_sub : p.att_vid;
           float s1 = 0.f, s2 = 0.f;
+          CQA_CHUNK_BEGIN(33)
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            // the U chunk and the a*U chunk of these 32 columns are filled side by side, 16 columns at a time
-            const uint32_t sU = a_use & 1u, sP = sU ^ 1u;
-            mbar_wait(&my_empty[sU], ((a_use >> 1) & 1u) ^ 1u, 33);
-            mbar_wait(&my_empty[sP], (((a_use + 1) >> 1) & 1u) ^ 1u, 34);
-            uint8_t* stU = my_stage + sU * CqaCfg::AST_BYTES;
-            uint8_t* stP = my_stage + sP * CqaCfg::AST_BYTES;
+          for (int sl = 0; sl < 2; ++sl) {
+            float u[16];
+            tmem_ld16(tU + sl * 16, u);
+            tmem_wait_ld();
 #pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-              float u[16], pu[16];
-              tmem_ld16(tU + b * 32 + sl * 16, u);
-              tmem_wait_ld();
+            for (int j = 0; j < 16; ++j) { s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
+            if (att != nullptr && live) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                pu[j] = a_reg[b * 32 + sl * 16 + j] * u[j];
-                s1 += u[j] + pu[j];
-                s2 += u[j] * u[j] + pu[j] * pu[j];
-              }
-              if (att != nullptr && live) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(att + orow + half * 64 + b * 32 + sl * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
-              }
-#pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {
-                HL8 hu = split8(u + h8 * 8), hp = split8(pu + h8 * 8);
-                uint8_t* du = stU + (sl * 2 + h8) * CqaCfg::LBO_A + row * 16;
-                uint8_t* dp = stP + (sl * 2 + h8) * CqaCfg::LBO_A + row * 16;
-                *reinterpret_cast<uint4*>(du) = hu.hi;
-                *reinterpret_cast<uint4*>(du + CqaCfg::AST_PART) = hu.lo;
-                *reinterpret_cast<uint4*>(dp) = hp.hi;
-                *reinterpret_cast<uint4*>(dp + CqaCfg::AST_PART) = hp.lo;
-              }
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(att + orow + sl * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
             }
-            fence_async_smem();
-            mbar_arrive(&my_full[sU]);
-            mbar_arrive(&my_full[sP]);
-            a_use += 2;
+            CQA_CHUNK_PUT16(sl, u)
           }
+          CQA_CHUNK_END()
+          CQA_CHUNK_BEGIN(34)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            float u[16];
+            tmem_ld16(tU + sl * 16, u);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              u[j] *= a_reg[sl * 16 + j];
+              s1 += u[j];
+              s2 = fmaf(u[j], u[j], s2);
+            }
+            CQA_CHUNK_PUT16(sl, u)
+          }
+          CQA_CHUNK_END()
           st_s1[g] = s1;
           st_s2[g] = s2;
         }
         CQA_STAMP(0, 6);
-        xch[half][row] = st_s1[0]; xch[2 + half][row] = st_s2[0];
-        xch[4 + half][row] = st_s1[1]; xch[6 + half][row] = st_s2[1];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        xq[0][qd][row] = st_s1[0]; xq[1][qd][row] = st_s2[0];
+        xq[2][qd][row] = st_s1[1]; xq[3][qd][row] = st_s2[1];
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         float mu_s, r_s, mu_v, r_v;
         {
-          const float t1 = asum + xch[0][row] + xch[1][row], t2 = asq + xch[2][row] + xch[3][row];
+          const float t1 = asum + ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row]));
+          const float t2 = asq + ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row]));
           mu_s = t1 * (1.f / 384.f);
           r_s = 1.f / sqrtf(fmaxf(t2 * (1.f / 384.f) - mu_s * mu_s, 0.f) + 1e-5f);
-          const float v1 = asum + xch[4][row] + xch[5][row], v2 = asq + xch[6][row] + xch[7][row];
+          const float v1 = asum + ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row]));
+          const float v2 = asq + ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row]));
           mu_v = v1 * (1.f / 384.f);
           r_v = 1.f / sqrtf(fmaxf(v2 * (1.f / 384.f) - mu_v * mu_v, 0.f) + 1e-5f);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read xch before it is reused below
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // everyone has read xq before it is reused below
 
-        // ---- concat_fc A operands: [ms, mv, ms*mv] with ms/mv = relu(rstd*(acc - mean*cs) + cb)
+        // ---- concat_fc A operands: ms chunk, mv chunk, ms*mv chunk with ms/mv = relu(rstd*(acc - mean*cs) + cb)
         tc_fence_before();
         CQA_STAMP(0, 7);
         mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
@@ -462,54 +473,55 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 8);
         float c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-          float ms[32], mv[32];
-          tmem_ld16(T0 + coff + b * 32, ms);
-          tmem_ld16(T0 + coff + b * 32 + 16, ms + 16);
-          tmem_ld16(T1 + coff + b * 32, mv);
-          tmem_ld16(T1 + coff + b * 32 + 16, mv + 16);
-          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = half * 64 + b * 32 + j;
-            const float cs = pvec[0][c], cb = pvec[1][c];
-            ms[j] = fmaxf(r_s * (ms[j] - mu_s * cs) + cb, 0.f);
-            mv[j] = fmaxf(r_v * (mv[j] - mu_v * cs) + cb, 0.f);
-          }
-          if (live && p.mixed_sub != nullptr) {
+        for (int seg = 0; seg < 3; ++seg) {
+          CQA_CHUNK_BEGIN(36)
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.mixed_sub + orow + half * 64 + b * 32 + j) = make_float4(ms[j], ms[j + 1], ms[j + 2], ms[j + 3]);
-          }
-          if (live && p.mixed_vid != nullptr) {
+          for (int sl = 0; sl < 2; ++sl) {
+            float v[16];
+            if (seg != 1) {
+              tmem_ld16(T0 + coff + sl * 16, v);
+              tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.mixed_vid + orow + half * 64 + b * 32 + j) = make_float4(mv[j], mv[j + 1], mv[j + 2], mv[j + 3]);
-          }
-          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 36);
-          put_chunk(ms, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
-          ++a_use;
-          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 37);
-          put_chunk(mv, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
-          ++a_use;
+              for (int j = 0; j < 16; ++j) {
+                const int c = qd * 32 + sl * 16 + j;
+                v[j] = fmaxf(r_s * (v[j] - mu_s * pvec[0][c]) + pvec[1][c], 0.f);
+              }
+              if (seg == 0 && live && p.mixed_sub != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pr = ms[j] * mv[j];
-            c1 += (ms[j] + mv[j]) + pr;
-            c2 += (ms[j] * ms[j] + mv[j] * mv[j]) + pr * pr;
-            ms[j] = pr;
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(p.mixed_sub + orow + sl * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            }
+            if (seg != 0) {
+              float w[16];
+              tmem_ld16(T1 + coff + sl * 16, w);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int c = qd * 32 + sl * 16 + j;
+                w[j] = fmaxf(r_v * (w[j] - mu_v * pvec[0][c]) + pvec[1][c], 0.f);
+              }
+              if (seg == 1 && live && p.mixed_vid != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(p.mixed_vid + orow + sl * 16 + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (seg == 1) ? w[j] : v[j] * w[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { c1 += v[j]; c2 = fmaf(v[j], v[j], c2); }
+            CQA_CHUNK_PUT16(sl, v)
           }
-          mbar_wait(&my_empty[a_use & 1u], ((a_use >> 1) & 1u) ^ 1u, 38);
-          put_chunk(ms, my_stage + (a_use & 1u) * CqaCfg::AST_BYTES, row, &my_full[a_use & 1u]);
-          ++a_use;
+          CQA_CHUNK_END()
         }
         CQA_STAMP(0, 9);
-        xch[half][row] = c1;
-        xch[2 + half][row] = c2;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mu_c = (xch[0][row] + xch[1][row]) * (1.f / 384.f);
-        const float r_c = 1.f / sqrtf(fmaxf((xch[2][row] + xch[3][row]) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
+        xq[0][qd][row] = c1;
+        xq[1][qd][row] = c2;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float mu_c = ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) * (1.f / 384.f);
+        const float r_c = 1.f / sqrtf(fmaxf(((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
 
         // ---- relu(rstd*(acc - mean*cs) + cb) -> LN128 -> statement
         tc_fence_before();
@@ -518,54 +530,47 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 10);
         {
+          float o[32];
+          tmem_ld16(T2 + coff, o);
+          tmem_ld16(T2 + coff + 16, o + 16);
+          tmem_wait_ld();
           float o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            float v[16];
-            tmem_ld16(T2 + coff + cc * 16, v);
-            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = half * 64 + cc * 16 + j;
-              const float o = fmaxf(r_c * (v[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
-              o1 += o;
-              o2 += o * o;
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int c = qd * 32 + j;
+            o[j] = fmaxf(r_c * (o[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
+            o1 += o[j];
+            o2 = fmaf(o[j], o[j], o2);
           }
-          xch[4 + half][row] = o1;
-          xch[6 + half][row] = o2;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float mean = (xch[4][row] + xch[5][row]) * (1.f / 128.f);
-          const float rstd = 1.f / sqrtf(fmaxf((xch[6][row] + xch[7][row]) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            float v[16];
-            tmem_ld16(T2 + coff + cc * 16, v);
-            tmem_wait_ld();
+          xq[2][qd][row] = o1;
+          xq[3][qd][row] = o2;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
+          const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+          if (live) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = half * 64 + cc * 16 + j;
-              const float o = fmaxf(r_c * (v[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
-              v[j] = (o - mean) * rstd * pvec[4][c] + pvec[5][c];
-            }
-            if (live) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(p.statement + orow + half * 64 + cc * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) {
+              const int c = qd * 32 + j;
+              *reinterpret_cast<float4*>(p.statement + orow + j) =
+                  make_float4((o[j] - mean) * rstd * pvec[4][c] + pvec[5][c], (o[j + 1] - mean) * rstd * pvec[4][c + 1] + pvec[5][c + 1],
+                              (o[j + 2] - mean) * rstd * pvec[4][c + 2] + pvec[5][c + 2], (o[j + 3] - mean) * rstd * pvec[4][c + 3] + pvec[5][c + 3]);
             }
           }
           // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
-          if (live && half == 0) p.statement_mask[tile * p.lq + row] = (ma * any_v != 0.f) ? 1.f : 0.f;
+          if (live && qd == 0) p.statement_mask[tile * p.lq + row] = (ma * any_v != 0.f) ? 1.f : 0.f;
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // xch is rewritten by the next tile
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // xq is rewritten by the next tile
         CQA_STAMP(0, 11);
         ++tl_tile;
       }
     }
-  } else if (lane == 0) {
+#undef CQA_CHUNK_BEGIN
+#undef CQA_CHUNK_PUT16
+#undef CQA_CHUNK_END
+  } else if (warp == 16 && lane == 0) {
     // =================================================================== MMA issue + every bulk copy (one thread)
-    uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0, ah_cnt0 = 0, ah_cnt1 = 0;
+    uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
     int tl_tile = 0;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
@@ -624,19 +629,10 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
         ++done_cnt;
         CQA_STAMP(1, 4);
         // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk order alternates between the column halves
+        // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk q comes from quarter q % 4 and, because every
+        //      quarter owns one K=32 chunk per segment, the weight chunks are consumed in their natural order
         auto w_src = [&](int q) -> const uint8_t* {
-          int c;
-          const uint8_t* base;
-          if (q < 16) {
-            const int ql = q & 7, h = ql & 1, j = ql >> 1;
-            c = (j & 1) * 4 + 2 * h + (j >> 1);
-            base = p.c2q_w;
-          } else {
-            const int ql = q - 16, h = ql & 1, j = ql >> 1;
-            c = (j % 3) * 4 + 2 * h + (j / 3);
-            base = p.cat_w;
-          }
-          return base + static_cast<size_t>(c) * CqaCfg::W_SLOT;
+          return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
         };
         for (int q = 0; q < CqaCfg::W_SLOTS - 1; ++q) {  // prime the ring
           const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, use = (q_cnt + q) / CqaCfg::W_SLOTS;
@@ -645,12 +641,9 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
           bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
         }
         for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
-          const int h = q & 1;  // 8, 8 and 12 are even, so the half alternates across GEMM boundaries too
-          const uint32_t cnt = h == 0 ? ah_cnt0 : ah_cnt1;
-          const uint32_t stg = h * 2 + (cnt & 1u);
+          const uint32_t stg = q & 3;  // A stage = producing quarter; every quarter delivers 7 chunks per tile, in step
           const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, wuse = (q_cnt + q) / CqaCfg::W_SLOTS;
-          mbar_wait(&a_full[stg], (cnt >> 1) & 1u, 45);
-          if (h == 0) ++ah_cnt0; else ++ah_cnt1;
+          mbar_wait(&a_full[stg], ((q_cnt + q) >> 2) & 1u, 45);
           mbar_wait(&w_full[slot], wuse & 1u, 46);
           tc_fence_after();
           const uint32_t ast = smem_u32(sAQ + stg * CqaCfg::AST_BYTES), wsl = smem_u32(sB + slot * CqaCfg::W_SLOT);
@@ -691,7 +684,7 @@ __global__ void __launch_bounds__(288, 1) cqa_kernel(CqaDev p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tbase);
+  if (warp == 16) tmem_dealloc<512>(tbase);
 }
 
 }  // namespace stg
