@@ -69,10 +69,10 @@ typedef struct {
 } StageLinearArgs;
 int stage_linear_fwd(const StageLinearArgs* a, void* stream);
 
-/* ---- EncoderBlock (model/encoder.py:9-52, model/cnn.py:6-47, model/position_encoding.py:33-43,
- *      model/self_attention.py:19-71) ---------------------------------------------------------------------------
- * x + pe -> n_conv x [LN -> depthwise conv(k, zero pad k/2) -> pointwise 128x128 -> ReLU -> + residual]
- *        -> (heads>0: LN -> MHA -> + residual) -> LN.
+/* ---- EncoderBlock, conv part (model/encoder.py:9-44,52, model/cnn.py:6-47, model/position_encoding.py:33-43) -------
+ * x + pe -> n_conv x [LN -> depthwise conv(k, zero pad k/2) -> pointwise 128x128 -> ReLU -> + residual] -> LN.
+ * With self-attention (n_heads > 0) the caller passes STAGE_ENC_NO_FINAL_LN here and finishes the block with
+ * stage_mha_fwd (LN -> MHA -> + residual -> LN).
  * out_mode 0: y[n_seq,L,128].  out_mode 1: masked max-pool over L (mask_logits + max, model/stage.py:503):
  * y[n_seq,128].  L <= 128. */
 #define STAGE_ENC_NO_PE 1        /* skip the position-encoding add */
@@ -84,11 +84,11 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream);
 typedef struct {
   int64_t n_seq;
   int L;
-  int n_conv, ksize, n_heads;
+  int n_conv, ksize;
   int out_mode;
-  int flags;           /* STAGE_ENC_* bits; 0 = the full EncoderBlock */
+  int flags;           /* STAGE_ENC_* bits; 0 = the full (attention-free) EncoderBlock */
   const float* x;      /* [n_seq,L,128] */
-  const float* mask;   /* [n_seq,L] (needed for out_mode 1 and n_heads > 0) */
+  const float* mask;   /* [n_seq,L] (needed for out_mode 1) */
   const float* pe;     /* [>=L,128] position-encoding buffer (NULL with STAGE_ENC_NO_PE) */
   const float* ln_g[STAGE_MAX_CONV];
   const float* ln_b[STAGE_MAX_CONV];
@@ -96,16 +96,34 @@ typedef struct {
   const float* dw_b[STAGE_MAX_CONV];
   const void* pw_packed[STAGE_MAX_CONV]; /* stage_pack_weight(pointwise [128,128], kc=64) */
   const float* pw_b[STAGE_MAX_CONV];
-  const float* attn_ln_g;   /* heads > 0 only */
-  const float* attn_ln_b;
-  const void* attn_w_packed[4]; /* linears.0..3 */
-  const float* attn_b[4];
   const float* final_ln_g;
   const float* final_ln_b;
   float* y;
-  float* workspace;    /* heads > 0: n_seq*L*128*4 floats; else may be NULL */
 } StageEncoderArgs;
 int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream);
+
+/* ---- multi-head self-attention (model/self_attention.py:19-71) with the EncoderBlock glue around it
+ *      (model/encoder.py:46-52) -------------------------------------------------------------------------------------
+ * y = LN_fin?( (x +)? Wo . concat_h softmax(Q_h K_h^T / sqrt(d_k)) V_h ),  Q,K,V = LN_in?(x) W^T + b.
+ * Query-row mask exactly like the reference (self_attention.py:43,66-67): rows with mask == 0 attend uniformly,
+ * valid rows also see padded keys.  n_heads in {1, 2, 4}; L <= 128.  out_mode as for the encoder. */
+typedef struct {
+  int64_t n_seq;
+  int L;
+  int n_heads;
+  int residual;            /* 1: y = x + attention(LN_in(x)) */
+  int out_mode;
+  const float* x;          /* [n_seq,L,128] */
+  const float* mask;       /* [n_seq,L] or NULL (no masking) */
+  const float* ln_in_g;    /* attn_layer_norm or NULL */
+  const float* ln_in_b;
+  const void* w_packed[4]; /* stage_pack_weight(linears.0..3 weight [128,128], kc=64) */
+  const float* b[4];
+  const float* final_ln_g; /* closing LayerNorm or NULL */
+  const float* final_ln_b;
+  float* y;
+} StageMhaArgs;
+int stage_mha_fwd(const StageMhaArgs* a, void* stream);
 
 /* ---- fused QA<->context attention + fusion MLPs ------------------------------------------------------------------
  * StructuredAttention (model/context_query_attention.py:35-101) for both streams, qa_ctx_attention +

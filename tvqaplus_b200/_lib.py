@@ -24,12 +24,17 @@ class LinearArgs(C.Structure):
 
 
 class EncoderArgs(C.Structure):
-    _fields_ = [("n_seq", C.c_int64), ("L", C.c_int), ("n_conv", C.c_int), ("ksize", C.c_int), ("n_heads", C.c_int),
+    _fields_ = [("n_seq", C.c_int64), ("L", C.c_int), ("n_conv", C.c_int), ("ksize", C.c_int),
                 ("out_mode", C.c_int), ("flags", C.c_int), ("x", _f), ("mask", _f), ("pe", _f),
                 ("ln_g", _f * MAX_CONV), ("ln_b", _f * MAX_CONV), ("dw_w", _f * MAX_CONV), ("dw_b", _f * MAX_CONV),
                 ("pw_packed", _f * MAX_CONV), ("pw_b", _f * MAX_CONV),
-                ("attn_ln_g", _f), ("attn_ln_b", _f), ("attn_w_packed", _f * 4), ("attn_b", _f * 4),
-                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f), ("workspace", _f)]
+                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f)]
+
+
+class MhaArgs(C.Structure):
+    _fields_ = [("n_seq", C.c_int64), ("L", C.c_int), ("n_heads", C.c_int), ("residual", C.c_int), ("out_mode", C.c_int),
+                ("x", _f), ("mask", _f), ("ln_in_g", _f), ("ln_in_b", _f), ("w_packed", _f * 4), ("b", _f * 4),
+                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f)]
 
 
 class CqaArgs(C.Structure):
@@ -68,6 +73,7 @@ SYMBOLS = {
     "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "stage_encoder_block_fwd": (C.c_int, [C.POINTER(EncoderArgs), C.c_void_p]),
+    "stage_mha_fwd": (C.c_int, [C.POINTER(MhaArgs), C.c_void_p]),
     "stage_cqa_weight_blob_bytes": (C.c_size_t, []),
     "stage_cqa_prepare_weights": (C.c_int, [C.c_void_p] * 10),
     "stage_cqa_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -7,6 +7,7 @@
 #include "linear.cuh"
 #include "encoder.cuh"
 #include "cqa.cuh"
+#include "mha.cuh"
 #include "head.cuh"
 #define STG_HAVE_PACK 1
 #define STG_HAVE_HEAD 1
@@ -119,7 +120,6 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(a->n_seq > 0 && a->L > 0, STAGE_E_BADARG, "encoder: n_seq=%lld L=%d", (long long)a->n_seq, a->L);
   STG_REQUIRE(a->L <= STAGE_MAX_SEQ, STAGE_E_UNSUPPORTED, "encoder: L=%d > %d", a->L, STAGE_MAX_SEQ);
   STG_REQUIRE(a->n_conv >= 1 && a->n_conv <= STAGE_MAX_CONV, STAGE_E_UNSUPPORTED, "encoder: n_conv=%d", a->n_conv);
-  STG_REQUIRE(a->n_heads == 0, STAGE_E_UNSUPPORTED, "encoder: self-attention (n_heads=%d) is not built yet", a->n_heads);
   STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
   EncDev d;
@@ -140,6 +140,33 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
     case 7: return launch_encoder<7>(d, s);
     default: return fail(STAGE_E_UNSUPPORTED, "encoder: kernel_size=%d (built: 3, 5, 7)", a->ksize);
   }
+}
+
+int stage_mha_fwd(const StageMhaArgs* a, void* stream) {
+  STG_REQUIRE(a && a->x && a->y, STAGE_E_BADARG, "mha: null pointer");
+  STG_REQUIRE(a->n_seq > 0 && a->L > 0, STAGE_E_BADARG, "mha: n_seq=%lld L=%d", (long long)a->n_seq, a->L);
+  STG_REQUIRE(a->L <= STAGE_MAX_SEQ, STAGE_E_UNSUPPORTED, "mha: L=%d > %d", a->L, STAGE_MAX_SEQ);
+  STG_REQUIRE(a->n_heads == 1 || a->n_heads == 2 || a->n_heads == 4, STAGE_E_UNSUPPORTED, "mha: n_heads=%d (built: 1, 2, 4)", a->n_heads);
+  STG_REQUIRE((a->ln_in_g == nullptr) == (a->ln_in_b == nullptr) && (a->final_ln_g == nullptr) == (a->final_ln_b == nullptr),
+              STAGE_E_BADARG, "mha: LayerNorm gamma/beta must come in pairs");
+  STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "mha: out_mode=%d needs a mask", a->out_mode);
+  STG_REQUIRE(aligned16(a->x) && aligned16(a->y), STAGE_E_BADARG, "mha: pointers must be 16-byte aligned");
+  MhaDev d;
+  d.x = a->x; d.mask = a->mask; d.ln_g = a->ln_in_g; d.ln_b = a->ln_in_b; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b;
+  d.y = a->y; d.n_seq = a->n_seq; d.L = a->L; d.n_heads = a->n_heads; d.residual = a->residual; d.out_mode = a->out_mode;
+  for (int i = 0; i < 4; ++i) {
+    STG_REQUIRE(a->w_packed[i] && a->b[i] && aligned16(a->w_packed[i]) && aligned16(a->b[i]), STAGE_E_BADARG,
+                "mha: linears.%d weight/bias null or misaligned", i);
+    d.w[i] = static_cast<const uint8_t*>(a->w_packed[i]);
+    d.b[i] = a->b[i];
+  }
+  int rc = set_smem(mha_kernel, MhaCfg::SMEM_BYTES, "mha");
+  if (rc) return rc;
+  const int G = 128 / a->L;
+  const long long tiles = (a->n_seq + G - 1) / G;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  mha_kernel<<<grid, MhaCfg::THREADS, MhaCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(d);
+  return check_launch("mha");
 }
 
 // weight blob layout of the fused CQA kernel

@@ -48,8 +48,8 @@ class EncoderBlock(nn.Module):
             return ops.encoder_block_fwd(x, mask, pe, convs, fin, self.kernel_size, out_mode=1 if pool else 0)
         # convs (no closing LN) -> LN + MHA + residual -> closing LN (+ pool)
         y = ops.encoder_block_fwd(x, mask, pe, convs, None, self.kernel_size, skip_final_ln=True)
-        y = ops.mha_fwd(y, mask, self.multi_head_attn.attn_args(self.attn_layer_norm), self.num_heads, residual=True)
-        return ops.layernorm_pool_fwd(y, mask, fin, pool=pool)
+        return ops.mha_fwd(y, mask, self.multi_head_attn.attn_args(self.attn_layer_norm), self.num_heads, residual=True,
+                           final_ln=fin, pool=pool)
 
 
 class StackedEncoder(nn.Module):

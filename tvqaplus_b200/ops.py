@@ -75,7 +75,7 @@ def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
 
 
 def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optional[torch.Tensor], convs: Sequence[dict],
-                      final_ln, ksize: int, *, n_heads: int = 0, attn: Optional[dict] = None, out_mode: int = 0,
+                      final_ln, ksize: int, *, out_mode: int = 0,
                       conv_only: bool = False, pre_ln_only: bool = False, relu: bool = True,
                       skip_final_ln: bool = False) -> torch.Tensor:
     """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
@@ -103,13 +103,11 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
     mask_c = _f32(mask) if mask is not None else None
     pe_c = _f32(pe) if pe is not None else None
     fin = (_f32(final_ln[0]), _f32(final_ln[1])) if final_ln is not None else (None, None)
-    a = _lib.EncoderArgs(n_seq=n_seq, L=L, n_conv=len(convs), ksize=ksize, n_heads=n_heads, out_mode=out_mode,
+    a = _lib.EncoderArgs(n_seq=n_seq, L=L, n_conv=len(convs), ksize=ksize, out_mode=out_mode,
                          flags=flags, x=ptr(x), mask=ptr(mask_c), pe=ptr(pe_c),
                          ln_g=_arr(cols["ln_g"]), ln_b=_arr(cols["ln_b"]), dw_w=_arr(cols["dw_w"]),
                          dw_b=_arr(cols["dw_b"]), pw_packed=_arr([ptr(c["pw_packed"]) for c in convs]),
-                         pw_b=_arr(cols["pw_b"]),
-                         attn_ln_g=None, attn_ln_b=None, attn_w_packed=_arr([], 4), attn_b=_arr([], 4),
-                         final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y), workspace=None)
+                         pw_b=_arr(cols["pw_b"]), final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y))
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
     _count()
     return y
@@ -220,16 +218,47 @@ def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     return y
 
 
+_zero_cqa_blobs: dict = {}
+
+
 def attention_only_fwd(c_embed, c_mask, q_embed, q_mask, scale: float) -> dict:
     """StructuredAttention alone for one stream: C (N,5,Lq,128), Q (N,T,Lr,128) -> att (N,5,T,Lq,128),
-    raw_s / norm_s (N,5,T,Lq,Lr).  Runs the fused kernel with the query tensor in the `sub` slot and stops after
-    U = P.Q (no projection weights needed)."""
-    raise NotImplementedError("tvqaplus_b200: attention-only mode of the CQA kernel is not built yet")
+    raw_s / norm_s (N,5,T,Lq,Lr).  Runs the fused kernel with the query tensor in its subtitle slot (Lr <= 112), a
+    one-item fully-masked dummy in the region slot and all-zero projection weights, and keeps only U = P.Q and the
+    score tensors.  Not a hot path (STAGE.forward uses ``cqa_fused_fwd``)."""
+    c_embed, q_embed = _f32(c_embed), _f32(q_embed)
+    dev = c_embed.device
+    N, T = q_embed.shape[0], q_embed.shape[1]
+    key = str(dev)
+    if key not in _zero_cqa_blobs:
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        _zero_cqa_blobs[key] = dict(wblob=cqa_prepare_weights(z(384), z(384), z(128, 384), z(128), z(384), z(384), z(128, 384), z(128)),
+                                    cat_out_ln_g=z(128), cat_out_ln_b=z(128))
+    dummy = torch.zeros(N, T, 1, HSZ, dtype=torch.float32, device=dev)
+    dmask = torch.zeros(N, T, 1, dtype=torch.float32, device=dev)
+    out = cqa_fused_fwd(c_embed, c_mask, q_embed, q_mask, dummy, dmask, _zero_cqa_blobs[key], scale,
+                        want=("att_sub", "sub_raw_s", "sub_norm_s"))
+    return dict(att=out["att_sub"], raw_s=out["sub_raw_s"], norm_s=out["sub_norm_s"])
 
 
-def mha_fwd(x, mask, attn: dict, n_heads: int, residual: bool = False):
-    raise NotImplementedError("tvqaplus_b200: the multi-head self-attention kernel (n_heads > 0) is not built yet")
-
-
-def layernorm_pool_fwd(x, mask, ln, pool: bool = False):
-    raise NotImplementedError("tvqaplus_b200: the multi-head self-attention kernel (n_heads > 0) is not built yet")
+def mha_fwd(x, mask, attn: dict, n_heads: int, *, residual: bool = False, final_ln=None, pool: bool = False):
+    """Multi-head self-attention (stage_mha_fwd): y = LN_fin?((x +)? MHA(LN_in?(x))); ``attn`` = dict(ln_g, ln_b,
+    w_packed[4], b[4]) as ``MultiHeadedAttention.attn_args`` builds it.  ``pool=True`` returns the masked max over L."""
+    x = _f32(x)
+    n_seq, L, D = x.shape
+    if D != HSZ:
+        raise RuntimeError("tvqaplus_b200: hidden size %d != %d" % (D, HSZ))
+    if pool and mask is None:
+        raise RuntimeError("tvqaplus_b200: the masked max-pool needs a mask")
+    y = torch.empty((n_seq, D) if pool else (n_seq, L, D), dtype=torch.float32, device=x.device)
+    mask_c = _f32(mask) if mask is not None else None
+    ln = (_f32(attn["ln_g"]), _f32(attn["ln_b"])) if attn.get("ln_g") is not None else (None, None)
+    fin = (_f32(final_ln[0]), _f32(final_ln[1])) if final_ln is not None else (None, None)
+    bs = [_f32(b) for b in attn["b"]]
+    a = _lib.MhaArgs(n_seq=n_seq, L=L, n_heads=n_heads, residual=int(residual), out_mode=int(pool), x=ptr(x),
+                     mask=ptr(mask_c), ln_in_g=ptr(ln[0]), ln_in_b=ptr(ln[1]),
+                     w_packed=_arr([ptr(w) for w in attn["w_packed"]], 4), b=_arr([ptr(b) for b in bs], 4),
+                     final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y))
+    check(lib().stage_mha_fwd(C.byref(a), current_stream()), "stage_mha_fwd")
+    _count()
+    return y
