@@ -101,33 +101,16 @@ class ClockSampler:
 
 def make_host_batch(N, pin):
     """Dense synthetic batch of configs[1] on the host (pinned for the e2e leg)."""
-    from oracle import stage_oracle as O
-    T, R, Lq, Ls = SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"]
-    g = torch.Generator().manual_seed(2018)
-
-    def rnd(*shape):
-        t = torch.empty(*shape, pin_memory=pin)
-        t.normal_(generator=g)
-        return t
-
-    b = O.Batch(qid=list(range(N)), vid_name=["syn"] * N, qas_bert=rnd(N, 5, Lq, 768), sub_bert=rnd(N, T, Ls, 768),
-                vid=rnd(N, T, R, 300), qas_mask=torch.ones(N, 5, Lq), sub_mask=torch.ones(N, T, Ls),
-                vid_mask=torch.ones(N, T, R), ts_label_mask=torch.ones(N, T), target=torch.randint(0, 5, (N,), generator=g),
-                ts_label={"st": torch.randint(0, T // 2, (N,), generator=g), "ed": torch.randint(T // 2, T, (N,), generator=g)},
-                qas=torch.ones(N, 5, Lq, dtype=torch.long), att_labels=None, anno_st_idx=[0] * N, q_l=[Lq // 2] * N,
-                image_indices=None, boxes=None, use_hard_negatives=False, eval_object_word_ids=None)
-    if pin:
-        for k in ("qas_mask", "sub_mask", "vid_mask", "ts_label_mask"):
-            b[k] = b[k].pin_memory()
-    return b
+    from tvqaplus_b200 import host
+    return host.synthetic_batch(N, SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"], seed=2018, pin=pin)
 
 
 TENSOR_KEYS = ("qas_bert", "sub_bert", "vid", "qas_mask", "sub_mask", "vid_mask", "ts_label_mask", "target")
 
 
 def to_device(b, dev, non_blocking=False, into=None):
-    from oracle import stage_oracle as O
-    out = O.Batch(b)
+    from tvqaplus_b200 import host
+    out = host.Batch(b)
     for k in TENSOR_KEYS:
         if into is not None:
             into[k].copy_(b[k], non_blocking=non_blocking)
@@ -191,8 +174,7 @@ def main():
         return
 
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
-    from oracle import stage_oracle as O
-    from tvqaplus_b200 import _lib, ops
+    from tvqaplus_b200 import _lib, host, ops
     from tvqaplus_b200.model import STAGE
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the STAGE kernels)")
@@ -202,12 +184,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.lib()
-    opt = O.default_opt()
+    opt = host.default_opt()
     torch.manual_seed(2018)
     model = STAGE(opt).to(dev).eval()
     N = args.batch
-    host = make_host_batch(N, pin=not args.no_e2e)
-    dbatch = to_device(host, dev)
+    hbatch = make_host_batch(N, pin=not args.no_e2e)
+    dbatch = to_device(hbatch, dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -251,14 +233,14 @@ def main():
         res_host = [dict(a=torch.empty(N, 5).pin_memory(), p=torch.empty(N, 5, SHAPE["T"], 2).pin_memory()) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
-        h2d = sum(host[k].numel() * host[k].element_size() for k in TENSOR_KEYS)
+        h2d = sum(hbatch[k].numel() * hbatch[k].element_size() for k in TENSOR_KEYS)
         d2h = res_host[0]["a"].numel() * 4 + res_host[0]["p"].numel() * 4
 
         def run_e2e(steps):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(copy_stream):
                 s0.record()
-                to_device(host, dev, non_blocking=True, into=bufs[0])
+                to_device(hbatch, dev, non_blocking=True, into=bufs[0])
                 ready[0].record()
             for i in range(steps):
                 cur = i % 2
@@ -266,10 +248,10 @@ def main():
                     with torch.cuda.stream(copy_stream):
                         if i >= 1:
                             copy_stream.wait_event(freed[1 - cur])
-                        to_device(host, dev, non_blocking=True, into=bufs[1 - cur])
+                        to_device(hbatch, dev, non_blocking=True, into=bufs[1 - cur])
                         ready[1 - cur].record()
                 main_stream.wait_event(ready[cur])
-                b = O.Batch(host)
+                b = host.Batch(hbatch)
                 b.update(bufs[cur])
                 ans, _, _, _, probs = model(b)
                 res_host[cur]["a"].copy_(ans, non_blocking=True)

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from oracle import stage_oracle as O  # noqa: E402
+from tvqaplus_b200 import host  # noqa: E402
 from tvqaplus_b200.model import STAGE  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -16,7 +16,7 @@ ap.add_argument("--iters", type=int, default=2)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(2018)
-model = STAGE(O.default_opt()).to(dev).eval()
+model = STAGE(host.default_opt()).to(dev).eval()
 batch = bench.to_device(bench.make_host_batch(a.batch, pin=False), dev)
 for _ in range(a.iters):
     model(batch)

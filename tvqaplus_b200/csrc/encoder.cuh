@@ -1,12 +1,22 @@
 // EncoderBlock on one SM-resident tile:  x + pe -> n_conv x [LN -> depthwise conv -> pointwise GEMM -> ReLU -> +res] -> LN
 // (model/encoder.py:29-52).  A tile is 128 rows = floor(128/L) whole sequences; the fp32 residual stream never leaves
-// shared memory, the pointwise 128x128 GEMM runs on tcgen05 (split-fp16, accumulator in TMEM), the weights arrive by
-// one cp.async.bulk per conv and the next conv's weights are prefetched while the epilogue runs.
+// shared memory, the pointwise 128x128 GEMM runs on tcgen05 (split-fp16, accumulator in TMEM).
+//
+// 512 threads, one CTA per SM, persistent over tiles:
+//   phase 0   the tile's raw rows were prefetched by ONE cp.async.bulk (they are contiguous in HBM) into the region
+//             that later holds the A image; warp-per-row: + position encoding -> X (fp32, smem) and the row's LayerNorm
+//             statistics from the same registers
+//   conv      warp = 8 consecutive rows, lane = 4 channels: a register sliding window of LayerNorm-ed rows feeds the
+//             k-tap depthwise FIR (each row is normalised once, 2 FMA per element); result split to fp16 (hi, lo) and
+//             stored as the tcgen05 A operand image
+//   GEMM      thread 0: 8 K-steps x 3 MMAs (split product), weights of the conv arrive by one bulk copy that was
+//             launched under the previous epilogue
+//   epilogue  thread = (row, column quarter): X += relu(D + b); the NEXT LayerNorm's statistics are accumulated from the
+//             values being written (no extra pass over X)
+//   tail      closing LayerNorm -> store, or mask_logits + max over the sequence (model/stage.py:503)
 //
 // Padded tokens are processed like real ones (the reference never masks before the convs, SURVEY.md §7 quirk i); the
 // depthwise conv sees zeros outside [0, L) of its own sequence only.
-//
-// out_mode 0: y[n_seq, L, 128];  out_mode 1: y[n_seq, 128] = max_l mask_logits(LN(x), mask)  (model/stage.py:503).
 //
 // Algorithmic work per token: n_conv*(2*k*128 + 2*128*128) FLOP; reads 512 B, writes 512 B (mode 0) or 512/L B.
 #pragma once
@@ -19,14 +29,15 @@ struct EncCfg {
   static constexpr uint32_t X_BYTES = 128u * XS * 4u;  // 67584
   static constexpr uint32_t LBO_A = 128u * 16u + 16u;
   static constexpr uint32_t A_PART = 16u * LBO_A;      // 33024
-  static constexpr uint32_t A_BYTES = 2u * A_PART;
+  static constexpr uint32_t A_BYTES = 2u * A_PART;     // 66048 >= 128 raw rows (65536)
   static constexpr uint32_t LBO_B = 128u * 16u;
   static constexpr uint32_t W_CHUNK = 2u * 8u * LBO_B;  // one kc=64 chunk: hi | lo
   static constexpr uint32_t W_BYTES = 2u * W_CHUNK;     // 65536
   static constexpr uint32_t OFF_A = (X_BYTES + 127u) & ~127u;
   static constexpr uint32_t OFF_W = OFF_A + ((A_BYTES + 127u) & ~127u);
   static constexpr uint32_t SMEM_BYTES = OFF_W + W_BYTES + 1024u;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 512;
+  static constexpr int ROWS_PER_WARP = 8;
 };
 
 struct EncDev {
@@ -49,11 +60,14 @@ struct EncDev {
 #define STG_NEG (-1e10f)
 
 template <int KS>
-__global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
+__global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t w_bar, mma_bar;
+  __shared__ uint64_t w_bar, mma_bar, x_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float row_mean[128], row_rstd[128], row_mask[128];
+  __shared__ float2 row_stat[128];   // (mean * rstd, rstd) of the LayerNorm that reads X next
+  __shared__ float row_mask[128];
+  __shared__ int row_sid[128];       // sequence index of a tile row (r / L)
+  __shared__ float xq[2][4][128];    // cross-quarter exchange of the epilogue: [sum | sum of squares][quarter][row]
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   float* X = reinterpret_cast<float*>(smem);
@@ -61,69 +75,80 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
   uint8_t* sW = smem + EncCfg::OFF_W;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int P = KS / 2;
+  constexpr int RW = EncCfg::ROWS_PER_WARP;
+  constexpr int WIN = RW + 2 * P;
+
+  const int L = p.L;
+  const int G = 128 / L;  // sequences per tile
+  const long long n_tiles = (p.n_seq + G - 1) / G;
 
   if (tid == 0) {
     mbar_init(&w_bar, 1);
     mbar_init(&mma_bar, 1);
+    mbar_init(&x_bar, 1);
     mbar_fence_init();
   }
+  if (tid < 128) row_sid[tid] = static_cast<int>(tid) / L;
   if (warp == 0) tmem_alloc<128>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
   const uint32_t idesc = make_idesc_f16(128);
+  uint32_t w_count = 0, mma_count = 0, x_count = 0;
 
-  const int L = p.L;
-  const int G = 128 / L;  // sequences per tile
-  const long long n_tiles = (p.n_seq + G - 1) / G;
-  uint32_t w_count = 0, mma_count = 0;
-
+  auto rows_of = [&](long long tile) -> int {
+    const long long seq0 = tile * G;
+    const long long n_here = (p.n_seq - seq0) < G ? (p.n_seq - seq0) : G;
+    return static_cast<int>(n_here) * L;
+  };
   if (tid == 0 && static_cast<long long>(blockIdx.x) < n_tiles) {
+    const uint32_t bytes = static_cast<uint32_t>(rows_of(blockIdx.x)) * 512u;
+    mbar_arrive_expect_tx(&x_bar, bytes);
+    bulk_g2s(sA, p.x + static_cast<long long>(blockIdx.x) * G * L * 128, bytes, &x_bar);
     mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
     bulk_g2s(sW, p.pw[0], EncCfg::W_BYTES, &w_bar);
   }
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long seq0 = tile * G;
-    const int n_here = static_cast<int>((p.n_seq - seq0) < G ? (p.n_seq - seq0) : G);
-    const int n_valid = n_here * L;
+    const int n_valid = rows_of(tile);
+    const int n_here = n_valid / L;
 
-    // ---- phase 0: x + pe -> X (warp per row, 128-bit coalesced)
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = warp * 16 + rr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      float m = 0.f;
-      if (r < n_valid) {
-        const int g = r / L, pos = r - g * L;
-        const long long grow = (seq0 + g) * L + pos;
-        float4 a = __ldg(reinterpret_cast<const float4*>(p.x + grow * 128) + lane);
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!(p.flags & STAGE_ENC_NO_PE)) e = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
-        v = make_float4(a.x + e.x, a.y + e.y, a.z + e.z, a.w + e.w);
-        if (p.mask != nullptr) m = __ldg(p.mask + grow);
-      }
-      *reinterpret_cast<float4*>(X + r * EncCfg::XS + lane * 4) = v;
-      if (lane == 0) row_mask[r] = m;
-    }
-    __syncthreads();
-
-    for (int ci = 0; ci < p.n_conv; ++ci) {
-      // ---- phase 1: LayerNorm statistics, exact two-pass, warp per row
-      for (int rr = 0; rr < 16; ++rr) {
-        const int r = warp * 16 + rr;
-        float4 v = *reinterpret_cast<const float4*>(X + r * EncCfg::XS + lane * 4);
+    // ---- phase 0: raw rows (smem, prefetched) + pe -> X, first LayerNorm statistics.  warp per row, lane = 4 channels
+    mbar_wait(&x_bar, x_count & 1u, 22);
+    ++x_count;
+    {
+      const float4* raw = reinterpret_cast<const float4*>(sA);
+#pragma unroll
+      for (int rr = 0; rr < RW; ++rr) {
+        const int r = warp * RW + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float m = 0.f;
+        if (r < n_valid) {
+          v = raw[r * 32 + lane];
+          const int pos = r - row_sid[r] * L;
+          if (!(p.flags & STAGE_ENC_NO_PE)) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
+            v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+          }
+          if (p.mask != nullptr) m = __ldg(p.mask + seq0 * L + r);
+        }
+        *reinterpret_cast<float4*>(X + r * EncCfg::XS + lane * 4) = v;
         const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
         const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
         const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
         if (lane == 0) {
-          row_mean[r] = mean;
-          row_rstd[r] = 1.f / sqrtf(var + 1e-5f);
+          const float rs = 1.f / sqrtf(var + 1e-5f);
+          row_stat[r] = make_float2(mean * rs, rs);
+          row_mask[r] = m;
         }
       }
-      __syncthreads();
+    }
+    __syncthreads();
 
-      // ---- phase 2: depthwise conv over LN(x) (LN applied on the fly) -> split-fp16 A image.  lane = 4 channels
+    for (int ci = 0; ci < p.n_conv; ++ci) {
+      // ---- conv: LayerNorm applied once per row into a register window, k-tap FIR, split -> A image
       {
         const bool idn = (p.ln_g[ci] == nullptr);  // no LayerNorm in front of this conv
         const float4 g4 = idn ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(reinterpret_cast<const float4*>(p.ln_g[ci]) + lane);
@@ -134,20 +159,34 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int j = 0; j < KS; ++j) wt[c][j] = __ldg(p.dw_w[ci] + (lane * 4 + c) * KS + j);
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = warp * 16 + rr;
-          const int s0 = (r / L) * L;
+        const int r0 = warp * RW;
+        float4 win[WIN];
+        int sid[WIN];
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+          const int q = r0 - P + i;
+          win[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sid[i] = -1;
+          if (q >= 0 && q < 128) {
+            const float4 v = *reinterpret_cast<const float4*>(X + q * EncCfg::XS + lane * 4);
+            const float2 st = idn ? make_float2(0.f, 1.f) : row_stat[q];
+            win[i] = make_float4(fmaf(fmaf(v.x, st.y, -st.x), g4.x, b4.x), fmaf(fmaf(v.y, st.y, -st.x), g4.y, b4.y),
+                                 fmaf(fmaf(v.z, st.y, -st.x), g4.z, b4.z), fmaf(fmaf(v.w, st.y, -st.x), g4.w, b4.w));
+            sid[i] = row_sid[q];
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < RW; ++o) {
+          const int r = r0 + o;
+          const int me = sid[o + P];
           float o0 = db.x, o1 = db.y, o2 = db.z, o3 = db.w;
 #pragma unroll
           for (int j = 0; j < KS; ++j) {
-            const int q = r + j - P;
-            if (q >= s0 && q < s0 + L && q < 128) {
-              const float4 v = *reinterpret_cast<const float4*>(X + q * EncCfg::XS + lane * 4);
-              const float mu = idn ? 0.f : row_mean[q], rs = idn ? 1.f : row_rstd[q];
-              o0 = fmaf(wt[0][j], (v.x - mu) * rs * g4.x + b4.x, o0);
-              o1 = fmaf(wt[1][j], (v.y - mu) * rs * g4.y + b4.y, o1);
-              o2 = fmaf(wt[2][j], (v.z - mu) * rs * g4.z + b4.z, o2);
-              o3 = fmaf(wt[3][j], (v.w - mu) * rs * g4.w + b4.w, o3);
+            if (sid[o + j] == me) {  // warp-uniform: the tap lies inside this row's own sequence
+              o0 = fmaf(wt[0][j], win[o + j].x, o0);
+              o1 = fmaf(wt[1][j], win[o + j].y, o1);
+              o2 = fmaf(wt[2][j], win[o + j].z, o2);
+              o3 = fmaf(wt[3][j], win[o + j].w, o3);
             }
           }
           uint2 hi, lo;
@@ -161,10 +200,9 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
       fence_async_smem();
       __syncthreads();
 
-      // ---- phase 3: pointwise GEMM  D[128 x 128] = A[128 x 128] . W^T   (8 K-steps x 3 MMAs)
+      // ---- pointwise GEMM  D[128 x 128] = A[128 x 128] . W^T   (8 K-steps x 3 MMAs)
       if (tid == 0) {
         mbar_wait(&w_bar, w_count & 1u, 20);
-        ++w_count;
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
 #pragma unroll
@@ -178,63 +216,78 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
         }
         umma_commit(&mma_bar);
       }
+      ++w_count;
       mbar_wait(&mma_bar, mma_count & 1u, 21);
       ++mma_count;
       tc_fence_after();
-      if (tid == 0) {  // weights for the next conv (or conv 0 of this CTA's next tile) stream in under the epilogue
+      if (tid == 0) {
+        // weights of the next conv (or conv 0 of this CTA's next tile) stream in under the epilogue; after the last conv
+        // the A region is free as well and receives the next tile's raw rows
         const int nxt = ci + 1;
-        if (nxt < p.n_conv || tile + gridDim.x < n_tiles) {
+        const bool more = tile + gridDim.x < n_tiles;
+        if (nxt < p.n_conv || more) {
           mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
           bulk_g2s(sW, p.pw[nxt < p.n_conv ? nxt : 0], EncCfg::W_BYTES, &w_bar);
         }
+        if (nxt == p.n_conv && more) {
+          const long long nt = tile + gridDim.x;
+          const uint32_t bytes = static_cast<uint32_t>(rows_of(nt)) * 512u;
+          mbar_arrive_expect_tx(&x_bar, bytes);
+          bulk_g2s(sA, p.x + nt * G * L * 128, bytes, &x_bar);
+        }
       }
 
-      // ---- phase 4: epilogue  X += relu(D + b)   (thread = row, warp/4 picks the column half)
+      // ---- epilogue  X += relu(D + b)   (thread = row x column quarter) + statistics of the new row
       {
-        const int r = (warp & 3) * 32 + lane;
-        const int cb = (warp >> 2) * 64;
+        const int r = (warp & 3) * 32 + lane, qd = warp >> 2;
+        const int cb = qd * 32;
         const uint32_t trow = tbase + (((warp & 3) * 32u) << 16) + cb;
         float* xr = X + r * EncCfg::XS + cb;
+        float v[32];
+        tmem_ld16(trow, v);
+        tmem_ld16(trow + 16, v + 16);
+        tmem_wait_ld();
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + c0, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.pw_b[ci] + cb + c0 + j));
-            float4 xv = *reinterpret_cast<float4*>(xr + c0 + j);
-            float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
-            if (!(p.flags & STAGE_ENC_NO_RELU)) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
-            if (p.flags & STAGE_ENC_NO_RESIDUAL) xv = dv;
-            else xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
-            *reinterpret_cast<float4*>(xr + c0 + j) = xv;
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.pw_b[ci] + cb + j));
+          float4 xv = *reinterpret_cast<float4*>(xr + j);
+          float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+          if (!(p.flags & STAGE_ENC_NO_RELU)) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
+          if (p.flags & STAGE_ENC_NO_RESIDUAL) xv = dv;
+          else xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
+          *reinterpret_cast<float4*>(xr + j) = xv;
+          s1 += (xv.x + xv.y) + (xv.z + xv.w);
+          s2 = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, s2))));
         }
+        xq[0][qd][r] = s1;
+        xq[1][qd][r] = s2;
       }
       tc_fence_before();
       __syncthreads();
+      if (tid < 128) {
+        const float mean = ((xq[0][0][tid] + xq[0][1][tid]) + (xq[0][2][tid] + xq[0][3][tid])) * (1.f / 128.f);
+        const float ex2 = ((xq[1][0][tid] + xq[1][1][tid]) + (xq[1][2][tid] + xq[1][3][tid])) * (1.f / 128.f);
+        const float rs = 1.f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+        row_stat[tid] = make_float2(mean * rs, rs);
+      }
+      __syncthreads();
     }
 
-    // ---- final LayerNorm (+ store or masked max-pool)
+    // ---- closing LayerNorm (+ store, or mask_logits written back to X for the max-pool).  warp per row
     {
       const bool fin = !(p.flags & STAGE_ENC_NO_FINAL_LN);
       const float4 g4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_g) + lane) : make_float4(1.f, 1.f, 1.f, 1.f);
       const float4 b4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_b) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int rr = 0; rr < 16; ++rr) {
-        const int r = warp * 16 + rr;
-        float4 v = *reinterpret_cast<const float4*>(X + r * EncCfg::XS + lane * 4);
-        const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-        const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
-        const float rs = 1.f / sqrtf(var + 1e-5f);
-        float4 o = make_float4(a * rs * g4.x + b4.x, b * rs * g4.y + b4.y, c * rs * g4.z + b4.z, d * rs * g4.w + b4.w);
-        if (!fin) o = v;
+#pragma unroll
+      for (int rr = 0; rr < RW; ++rr) {
+        const int r = warp * RW + rr;
+        const float4 v = *reinterpret_cast<const float4*>(X + r * EncCfg::XS + lane * 4);
+        const float2 st = fin ? row_stat[r] : make_float2(0.f, 1.f);
+        float4 o = make_float4(fmaf(fmaf(v.x, st.y, -st.x), g4.x, b4.x), fmaf(fmaf(v.y, st.y, -st.x), g4.y, b4.y),
+                               fmaf(fmaf(v.z, st.y, -st.x), g4.z, b4.z), fmaf(fmaf(v.w, st.y, -st.x), g4.w, b4.w));
         if (p.out_mode == 0) {
-          if (r < n_valid) {
-            const int g = r / L, pos = r - g * L;
-            *reinterpret_cast<float4*>(p.y + ((seq0 + g) * L + pos) * 128 + lane * 4) = o;
-          }
+          if (r < n_valid) *reinterpret_cast<float4*>(p.y + (seq0 * L + r) * 128 + lane * 4) = o;
         } else {
           const float m = row_mask[r], off = (1.f - m) * STG_NEG;  // mask_logits: x*m + (1-m)*(-1e10)
           o = make_float4(o.x * m + off, o.y * m + off, o.z * m + off, o.w * m + off);
@@ -244,11 +297,19 @@ __global__ void __launch_bounds__(256, 1) encoder_kernel(EncDev p) {
     }
     if (p.out_mode != 0) {
       __syncthreads();
-      const int c = tid & 127;
-      for (int g = tid >> 7; g < n_here; g += 2) {
-        float mx = X[(g * L) * EncCfg::XS + c];
-        for (int pos = 1; pos < L; ++pos) mx = fmaxf(mx, X[(g * L + pos) * EncCfg::XS + c]);
-        p.y[(seq0 + g) * 128 + c] = mx;
+      // column-wise max over each sequence: thread = (channel, quarter of the sequence's rows), quarters merged through xq
+      const int c = tid & 127, part = tid >> 7;
+      const int span = (L + 3) / 4;
+      for (int g = 0; g < n_here; ++g) {
+        const int lo = g * L + part * span;
+        const int hi = min(g * L + L, lo + span);
+        float mx = -3.0e38f;
+        for (int r = lo; r < hi; ++r) mx = fmaxf(mx, X[r * EncCfg::XS + c]);
+        xq[g & 1][part][c] = mx;
+        __syncthreads();
+        if (part == 0) {
+          p.y[(seq0 + g) * 128 + c] = fmaxf(fmaxf(xq[g & 1][0][c], xq[g & 1][1][c]), fmaxf(xq[g & 1][2][c], xq[g & 1][3][c]));
+        }
       }
     }
     __syncthreads();
