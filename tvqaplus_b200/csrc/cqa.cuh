@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   *reinterpret_cast<uint2*>(dst) = hi;
   *reinterpret_cast<uint2*>(dst + part) = lo;
   if (lane == 0) {
-    inv_out[j] = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+    // F.normalize: x / max(||x||, eps); a masked row / column stores 0 so the kernel needs one load, not two
+    inv_out[j] = (m != 0.f) ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 0.f;
     mask_out[j] = m;
     if (sum_out != nullptr) { sum_out[j] = sm; sq_out[j] = ss; }
   }
@@ -164,19 +165,23 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
   mbar_arrive(full);
 }
 
+// phase stamps exist only in the TIMELINE instantiation (tools/cqa_timeline.py); the production kernel carries none
 #define CQA_STAMP(who, idx)                                                                         \
   do {                                                                                              \
-    if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64)                                   \
-      p.timeline[((who) * 64 + tl_tile) * 16 + (idx)] = clock64();                                  \
+    if constexpr (TIMELINE) {                                                                       \
+      if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64)                                 \
+        p.timeline[((who) * 64 + tl_tile) * 16 + (idx)] = clock64();                                \
+    }                                                                                               \
   } while (0)
 
+template <bool TIMELINE>
 __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, a_full[4], a_empty[4], w_full[CqaCfg::W_SLOTS],
       w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
   __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
-  __shared__ float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
+  __shared__ __align__(16) float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   uint8_t* sCTX = smem + CqaCfg::OFF_CTX;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
     const uint32_t coff = lane_off + qd * 32;
     const bool live = row < p.lq;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
-    int tl_tile = (tid == 0) ? 0 : 64;
+    [[maybe_unused]] int tl_tile = (tid == 0) ? 0 : 64;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
     uint64_t* my_full = &a_full[qd];
     uint64_t* my_empty = &a_empty[qd];
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         const size_t orow = (tile * p.lq + row) * 128 + qd * 32;  // my 32 columns of this tile's output row
         CQA_STAMP(0, 0);
         const float* rd = reinterpret_cast<const float*>(p.a_blob + na * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
-        const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row), asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);
+        const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row);
         if (a_i == 0) {
           mbar_wait(&ctx_full, frame_cnt & 1u, 30);  // ctx blob (images + inv norms + masks) has landed
           any_v = 0.f;
@@ -290,23 +295,30 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
             if (on) tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, s + k * 16);
           }
           tmem_wait_ld();
-          float mxs = -3.0e38f, mxv = -3.0e38f;
+          // |cos| <= 1, so scale*log2(e) bounds every live score: with that as the (fixed) softmax shift no row maximum has
+          // to be exchanged between the quarters.  Very large scales (exp2 underflow) take the exact-maximum path.
           const float sc2 = p.scale * 1.4426950408889634f;
+          const bool fixed_shift = sc2 <= 60.f;
+          float mxs = -3.0e38f, mxv = -3.0e38f;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             if (on) {
-              const float* ic = vid ? inv_cv : inv_cs;
-              const float* mc = vid ? mask_cv : mask_cs;
+              const float4* ic4 = reinterpret_cast<const float4*>((vid ? inv_cv : inv_cs) + ch * 16);
               float* raw = vid ? raw_v : raw_s;
               float mx = -3.0e38f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int col = ch * 16 + j;
-                if (col < n_real) {
-                  // S - 1e10*(1 - S_mask) of the reference: |S| <= 1 is absorbed by -1e10 in fp32, so a select is exact
-                  float v = (ma * mc[col] != 0.f) ? s[k * 16 + j] * ia * ic[col] : -1e10f;
-                  if (raw != nullptr) raw[col] = v;
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 c4 = ic4[j4];
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = j4 * 4 + e;
+                  // S - 1e10*(1 - S_mask) of the reference: |S| <= 1 is absorbed by -1e10 in fp32, so a select is exact.
+                  // Padded columns (>= n_real) carry inverse norm 0 and behave like masked ones (weight exactly 0).
+                  const float w = ia * cc[e];
+                  float v = (w != 0.f) ? s[k * 16 + j] * w : -1e10f;
+                  if (raw != nullptr && ch * 16 + j < n_real) raw[ch * 16 + j] = v;
                   v *= sc2;  // scale * log2(e): the softmax below runs in base 2
                   s[k * 16 + j] = v;
                   mx = fmaxf(mx, v);
@@ -315,22 +327,28 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
               if (vid) mxv = fmaxf(mxv, mx); else mxs = fmaxf(mxs, mx);
             }
           }
-          xq[0][qd][row] = mxs;
-          xq[1][qd][row] = mxv;
-          asm volatile("bar.sync 1, 512;" ::: "memory");
-          mxs = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row]));
-          mxv = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row]));
+          if (fixed_shift) {
+            mxs = sc2;
+            mxv = sc2;
+          } else {
+            xq[0][qd][row] = mxs;
+            xq[1][qd][row] = mxv;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            mxs = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row]));
+            mxv = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row]));
+          }
           float sms = 0.f, smv = 0.f;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
+            (void)n_real;
             if (on) {
               const float mx = vid ? mxv : mxs;
               float sum = 0.f;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float e = 0.f;
-                if (ch * 16 + j < n_real) { e = fast_exp2(s[k * 16 + j] - mx); sum += e; }
+                const float e = fast_exp2(s[k * 16 + j] - mx);  // masked / padded: exp2(-1.4e11) = 0
+                sum += e;
                 s[k * 16 + j] = e;
               }
               if (vid) smv += sum; else sms += sum;
@@ -339,8 +357,8 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           xq[2][qd][row] = sms;
           xq[3][qd][row] = smv;
           asm volatile("bar.sync 1, 512;" ::: "memory");
-          // masked entries of a live row are exactly 0 (exp2(-1.4e11 - max) underflows); a fully masked row is uniform
-          // and must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
+          // masked entries of a live row are exactly 0; a fully masked row must become 0 after the "* S_mask" of the
+          // reference -> its 1/sum is replaced by 0
           const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) : 0.f;
           const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) : 0.f;
 #pragma unroll
@@ -350,13 +368,11 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
               float* nrm = vid ? nrm_v : nrm_s;
               const float isum = vid ? iv : is;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int col = ch * 16 + j;
-                if (col < n_real) {
-                  const float pj = s[k * 16 + j] * isum;
-                  s[k * 16 + j] = pj;
-                  if (nrm != nullptr) nrm[col] = pj;
-                }
+              for (int j = 0; j < 16; ++j) s[k * 16 + j] *= isum;
+              if (nrm != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (ch * 16 + j < n_real) nrm[ch * 16 + j] = s[k * 16 + j];
               }
               uint8_t* img = vid ? sAQ : sB;                       // P_vid overlays the answer image, P_sub the weight ring
               const uint32_t part = vid ? CqaCfg::PV_PART : CqaCfg::PS_PART;
@@ -372,25 +388,9 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
 #undef CQA_SLOT
         }
         CQA_STAMP(0, 3);
-        // ---- hoisted a.Wa term -> both c2q accumulators (S has been consumed by every thread: second bar.sync above)
-        {
-          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            float z[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 v = live ? __ldg(zsrc + cc * 4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              z[j * 4] = v.x; z[j * 4 + 1] = v.y; z[j * 4 + 2] = v.z; z[j * 4 + 3] = v.w;
-            }
-            tmem_st16(T0 + coff + cc * 16, z);
-            tmem_st16(T1 + coff + cc * 16, z);
-          }
-          tmem_wait_st();
-        }
         tc_fence_before();
         fence_async_smem();
-        mbar_arrive(&op_ready);  // E2: P images + accumulator pre-loads are in place
+        mbar_arrive(&op_ready);  // E2: P images are in place, S has been consumed
         CQA_STAMP(0, 4);
         // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
         float a_reg[32];
@@ -414,58 +414,70 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           const uint32_t tU = (g == 0 ? T2 : T3) + coff;
           float* att = g == 0 ? p.att_sub : p.att_vid;
           float s1 = 0.f, s2 = 0.f;
+          float u[32];
+          tmem_ld16(tU, u);
+          tmem_ld16(tU + 16, u + 16);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
+          if (att != nullptr && live) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(att + orow + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+          }
           CQA_CHUNK_BEGIN(33)
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            float u[16];
-            tmem_ld16(tU + sl * 16, u);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
-            if (att != nullptr && live) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(att + orow + sl * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
-            }
-            CQA_CHUNK_PUT16(sl, u)
-          }
+          CQA_CHUNK_PUT16(0, u)
+          CQA_CHUNK_PUT16(1, u + 16)
           CQA_CHUNK_END()
-          CQA_CHUNK_BEGIN(34)
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            float u[16];
-            tmem_ld16(tU + sl * 16, u);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              u[j] *= a_reg[sl * 16 + j];
-              s1 += u[j];
-              s2 = fmaf(u[j], u[j], s2);
-            }
-            CQA_CHUNK_PUT16(sl, u)
+          for (int j = 0; j < 32; ++j) {
+            u[j] *= a_reg[j];
+            s1 += u[j];
+            s2 = fmaf(u[j], u[j], s2);
           }
+          CQA_CHUNK_BEGIN(34)
+          CQA_CHUNK_PUT16(0, u)
+          CQA_CHUNK_PUT16(1, u + 16)
           CQA_CHUNK_END()
           st_s1[g] = s1;
           st_s2[g] = s2;
         }
         CQA_STAMP(0, 6);
+        // the frame-invariant a.Wa term of c2q (same for both streams) joins the accumulators in the concat production.
+        // Its loads fly under the statistics exchange; it is then parked in my own cells of T3 (U_vid, which I have just
+        // consumed) so that it costs no registers while the c2q MMAs drain.
+        float za[32];
+        {
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
+          }
+        }
+        const float asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);  // sum(a), sum(a^2) of my row
         xq[0][qd][row] = st_s1[0]; xq[1][qd][row] = st_s2[0];
         xq[2][qd][row] = st_s1[1]; xq[3][qd][row] = st_s2[1];
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        float mu_s, r_s, mu_v, r_v;
+        tmem_st16(T3 + coff, za);
+        tmem_st16(T3 + coff + 16, za + 16);
+        float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
         {
           const float t1 = asum + ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row]));
           const float t2 = asq + ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row]));
-          mu_s = t1 * (1.f / 384.f);
+          const float mu_s = t1 * (1.f / 384.f);
           r_s = 1.f / sqrtf(fmaxf(t2 * (1.f / 384.f) - mu_s * mu_s, 0.f) + 1e-5f);
+          nm_s = -r_s * mu_s;
           const float v1 = asum + ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row]));
           const float v2 = asq + ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row]));
-          mu_v = v1 * (1.f / 384.f);
+          const float mu_v = v1 * (1.f / 384.f);
           r_v = 1.f / sqrtf(fmaxf(v2 * (1.f / 384.f) - mu_v * mu_v, 0.f) + 1e-5f);
+          nm_v = -r_v * mu_v;
         }
+        tmem_wait_st();
         asm volatile("bar.sync 1, 512;" ::: "memory");  // everyone has read xq before it is reused below
 
-        // ---- concat_fc A operands: ms chunk, mv chunk, ms*mv chunk with ms/mv = relu(rstd*(acc - mean*cs) + cb)
+        // ---- concat_fc A operands: ms chunk, mv chunk, ms*mv chunk with ms/mv = relu(rstd*(acc + za - mean*cs) + cb)
         tc_fence_before();
         CQA_STAMP(0, 7);
         mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
@@ -473,47 +485,57 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 8);
         float c1 = 0.f, c2 = 0.f;
+        {
+          float ms[32], mv[32];
+          const float4* cs4 = reinterpret_cast<const float4*>(&pvec[0][qd * 32]);
+          const float4* cb4 = reinterpret_cast<const float4*>(&pvec[1][qd * 32]);
 #pragma unroll
-        for (int seg = 0; seg < 3; ++seg) {
-          CQA_CHUNK_BEGIN(36)
+          for (int sl = 0; sl < 2; ++sl) {  // 16 columns at a time keeps (ms, mv, za) within the register budget
+            float zz[16];
+            tmem_ld16(T0 + coff + sl * 16, ms + sl * 16);
+            tmem_ld16(T1 + coff + sl * 16, mv + sl * 16);
+            tmem_ld16(T3 + coff + sl * 16, zz);
+            tmem_wait_ld();
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            float v[16];
-            if (seg != 1) {
-              tmem_ld16(T0 + coff + sl * 16, v);
-              tmem_wait_ld();
+            for (int j4 = sl * 4; j4 < sl * 4 + 4; ++j4) {
+              const float4 cs = cs4[j4], cb = cb4[j4];
+              const float csv[4] = {cs.x, cs.y, cs.z, cs.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = qd * 32 + sl * 16 + j;
-                v[j] = fmaxf(r_s * (v[j] - mu_s * pvec[0][c]) + pvec[1][c], 0.f);
-              }
-              if (seg == 0 && live && p.mixed_sub != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(p.mixed_sub + orow + sl * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float z = zz[j - sl * 16];
+                ms[j] = fmaxf(fmaf(r_s, ms[j] + z, fmaf(nm_s, csv[e], cbv[e])), 0.f);
+                mv[j] = fmaxf(fmaf(r_v, mv[j] + z, fmaf(nm_v, csv[e], cbv[e])), 0.f);
               }
             }
-            if (seg != 0) {
-              float w[16];
-              tmem_ld16(T1 + coff + sl * 16, w);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = qd * 32 + sl * 16 + j;
-                w[j] = fmaxf(r_v * (w[j] - mu_v * pvec[0][c]) + pvec[1][c], 0.f);
-              }
-              if (seg == 1 && live && p.mixed_vid != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(p.mixed_vid + orow + sl * 16 + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = (seg == 1) ? w[j] : v[j] * w[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { c1 += v[j]; c2 = fmaf(v[j], v[j], c2); }
-            CQA_CHUNK_PUT16(sl, v)
           }
+          if (live && p.mixed_sub != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.mixed_sub + orow + j) = make_float4(ms[j], ms[j + 1], ms[j + 2], ms[j + 3]);
+          }
+          if (live && p.mixed_vid != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.mixed_vid + orow + j) = make_float4(mv[j], mv[j + 1], mv[j + 2], mv[j + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
+          CQA_CHUNK_BEGIN(36)
+          CQA_CHUNK_PUT16(0, ms)
+          CQA_CHUNK_PUT16(1, ms + 16)
+          CQA_CHUNK_END()
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { c1 += mv[j]; c2 = fmaf(mv[j], mv[j], c2); }
+          CQA_CHUNK_BEGIN(37)
+          CQA_CHUNK_PUT16(0, mv)
+          CQA_CHUNK_PUT16(1, mv + 16)
+          CQA_CHUNK_END()
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { ms[j] *= mv[j]; c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
+          CQA_CHUNK_BEGIN(38)
+          CQA_CHUNK_PUT16(0, ms)
+          CQA_CHUNK_PUT16(1, ms + 16)
           CQA_CHUNK_END()
         }
         CQA_STAMP(0, 9);
@@ -522,6 +544,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const float mu_c = ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) * (1.f / 384.f);
         const float r_c = 1.f / sqrtf(fmaxf(((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
+        const float nm_c = -r_c * mu_c;
 
         // ---- relu(rstd*(acc - mean*cs) + cb) -> LN128 -> statement
         tc_fence_before();
@@ -535,25 +558,35 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           tmem_ld16(T2 + coff + 16, o + 16);
           tmem_wait_ld();
           float o1 = 0.f, o2 = 0.f;
+          const float4* cs4 = reinterpret_cast<const float4*>(&pvec[2][qd * 32]);
+          const float4* cb4 = reinterpret_cast<const float4*>(&pvec[3][qd * 32]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = qd * 32 + j;
-            o[j] = fmaxf(r_c * (o[j] - mu_c * pvec[2][c]) + pvec[3][c], 0.f);
-            o1 += o[j];
-            o2 = fmaf(o[j], o[j], o2);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cs = cs4[j4], cb = cb4[j4];
+            const float csv[4] = {cs.x, cs.y, cs.z, cs.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              o[j] = fmaxf(fmaf(r_c, o[j], fmaf(nm_c, csv[e], cbv[e])), 0.f);
+              o1 += o[j];
+              o2 = fmaf(o[j], o[j], o2);
+            }
           }
           xq[2][qd][row] = o1;
           xq[3][qd][row] = o2;
           asm volatile("bar.sync 1, 512;" ::: "memory");
           const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
           const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+          const float nmr = -mean * rstd;
           if (live) {
+            const float4* g4p = reinterpret_cast<const float4*>(&pvec[4][qd * 32]);
+            const float4* b4p = reinterpret_cast<const float4*>(&pvec[5][qd * 32]);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const int c = qd * 32 + j;
+              const float4 g = g4p[j >> 2], b = b4p[j >> 2];
               *reinterpret_cast<float4*>(p.statement + orow + j) =
-                  make_float4((o[j] - mean) * rstd * pvec[4][c] + pvec[5][c], (o[j + 1] - mean) * rstd * pvec[4][c + 1] + pvec[5][c + 1],
-                              (o[j + 2] - mean) * rstd * pvec[4][c + 2] + pvec[5][c + 2], (o[j + 3] - mean) * rstd * pvec[4][c + 3] + pvec[5][c + 3]);
+                  make_float4(fmaf(fmaf(o[j], rstd, nmr), g.x, b.x), fmaf(fmaf(o[j + 1], rstd, nmr), g.y, b.y),
+                              fmaf(fmaf(o[j + 2], rstd, nmr), g.z, b.z), fmaf(fmaf(o[j + 3], rstd, nmr), g.w, b.w));
             }
           }
           // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
@@ -562,7 +595,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         tc_fence_before();
         asm volatile("bar.sync 1, 512;" ::: "memory");  // xq is rewritten by the next tile
         CQA_STAMP(0, 11);
-        ++tl_tile;
+        if constexpr (TIMELINE) ++tl_tile;
       }
     }
 #undef CQA_CHUNK_BEGIN
@@ -571,7 +604,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
   } else if (warp == 16 && lane == 0) {
     // =================================================================== MMA issue + every bulk copy (one thread)
     uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
-    int tl_tile = 0;
+    [[maybe_unused]] int tl_tile = 0;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
     const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
@@ -648,7 +681,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           tc_fence_after();
           const uint32_t ast = smem_u32(sAQ + stg * CqaCfg::AST_BYTES), wsl = smem_u32(sB + slot * CqaCfg::W_SLOT);
           const uint32_t dcol = q < 8 ? T0 : (q < 16 ? T1 : T2);
-          const bool first = (q == 16);  // c2q accumulators start from the pre-loaded a.Wa term; concat starts from zero
+          const bool first = (q == 0 || q == 8 || q == 16);  // every accumulator starts from zero (a.Wa joins in the epilogue math)
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
@@ -677,7 +710,7 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         // the AQ region (A stages) and T0/T1 may only be reused after the concat MMAs have completed
         mbar_wait(&mma_done, (done_cnt - 1u) & 1u, 48);  // D4
         CQA_STAMP(1, 8);
-        ++tl_tile;
+        if constexpr (TIMELINE) ++tl_tile;
       }
     }
   }

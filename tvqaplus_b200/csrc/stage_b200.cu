@@ -262,11 +262,17 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   d.vid_raw_s = a->vid_raw_s; d.sub_raw_s = a->sub_raw_s; d.vid_norm_s = a->vid_norm_s; d.sub_norm_s = a->sub_norm_s;
   d.att_vid = a->att_vid; d.att_sub = a->att_sub; d.mixed_vid = a->mixed_vid; d.mixed_sub = a->mixed_sub;
   d.timeline = a->timeline;
-  int rc = set_smem(cqa_kernel, CqaCfg::SMEM_BYTES, "cqa");
-  if (rc) return rc;
   const int frames = a->n * a->t;
   const int grid = frames < num_sms() ? frames : num_sms();
-  cqa_kernel<<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, s>>>(d);
+  if (a->timeline != nullptr) {  // instrumented build of the same kernel (tools/cqa_timeline.py)
+    int rc = set_smem(cqa_kernel<true>, CqaCfg::SMEM_BYTES, "cqa");
+    if (rc) return rc;
+    cqa_kernel<true><<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, s>>>(d);
+  } else {
+    int rc = set_smem(cqa_kernel<false>, CqaCfg::SMEM_BYTES, "cqa");
+    if (rc) return rc;
+    cqa_kernel<false><<<grid, CqaCfg::THREADS, CqaCfg::SMEM_BYTES, s>>>(d);
+  }
   return check_launch("cqa");
 }
 
