@@ -35,8 +35,8 @@ struct CqaCfg {
   static constexpr uint32_t AQ_PART = 16u * LBO_A;           // 33024
   static constexpr uint32_t PS_PART = (LS_MAX / 8) * LBO_A;  // 28896
   static constexpr uint32_t PV_PART = (R_MAX / 8) * LBO_A;   // 12384
-  static constexpr uint32_t AST_PART = 4u * LBO_A;           // 8256: one 32-column A chunk
-  static constexpr uint32_t AST_BYTES = 2u * AST_PART;       // 16512
+  static constexpr uint32_t AST_PART = 8u * LBO_A;           // 16512: one K=64 A stage (16 columns from each column quarter)
+  static constexpr uint32_t AST_BYTES = 2u * AST_PART;       // 33024: hi | lo
   static constexpr uint32_t W_SLOT = 2u * 4u * 2048u;        // 16384: one kc=32 weight chunk (hi | lo)
   static constexpr int W_SLOTS = 4;
   // per-frame ctx blob (global and shared layout are identical)
@@ -57,9 +57,10 @@ struct CqaCfg {
   static constexpr uint32_t OFF_B = (OFF_AQ + AQ_BYTES + 127u) & ~127u;  // P_sub; later the weight ring
   static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                  // 65536 >= 2*PS_PART (57792)
   static constexpr uint32_t SMEM_BYTES = OFF_B + B_BYTES + 1024u;
-  static constexpr int THREADS = 544;
-  static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 chunks per tile: c2q(sub), c2q(vid), concat
-  static_assert(4u * AST_BYTES <= AQ_BYTES, "the 4 A stages (one per column quarter) overlay the answer image");
+  static constexpr int THREADS = 576;        // 16 compute warps + MMA warp + copy warp
+  static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 weight chunks per tile: c2q(sub), c2q(vid), concat
+  static constexpr int HALF_SEGS = CHUNKS / 2;  // K=64 A stages per tile
+  static_assert(2u * AST_BYTES <= AQ_BYTES, "the two A stages overlay the answer image");
   static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
   static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
 };
@@ -175,10 +176,10 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
   } while (0)
 
 template <bool TIMELINE>
-__global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
+__global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, a_full[4], a_empty[4], w_full[CqaCfg::W_SLOTS],
-      w_empty[CqaCfg::W_SLOTS];
+  __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
+      w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
   __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
   __shared__ __align__(16) float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
@@ -200,8 +201,11 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
     mbar_init(&mma_done, 1);
     mbar_init(&ctx_full, 1);
     mbar_init(&aq_full, 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&a_full[i], 128);
+    mbar_init(&ctx_free, 1);
+    mbar_init(&aq_free, 1);
+    mbar_init(&b_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 512);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < CqaCfg::W_SLOTS; ++i) {
@@ -229,29 +233,28 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
     [[maybe_unused]] int tl_tile = (tid == 0) ? 0 : 64;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
-    uint64_t* my_full = &a_full[qd];
-    uint64_t* my_empty = &a_empty[qd];
-    uint8_t* my_stage = sAQ + qd * CqaCfg::AST_BYTES;
     for (int i = tid; i < 128; i += 512) {  // per-column vectors of the folded GEMM epilogues
       pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
       pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
     }
     asm volatile("bar.sync 1, 512;" ::: "memory");
 
-    // publish one K=32 chunk: wait for the stage, let `fill(sl, v)` produce 16 columns at a time, split, store, arrive
-#define CQA_CHUNK_BEGIN(code)                                              \
-  mbar_wait(my_empty, (a_use & 1u) ^ 1u, code);                            \
-  ++a_use;
-#define CQA_CHUNK_PUT16(sl, v)                                             \
-  _Pragma("unroll") for (int h8 = 0; h8 < 2; ++h8) {                       \
-    HL8 hl = split8((v) + h8 * 8);                                         \
-    uint8_t* dst = my_stage + ((sl) * 2 + h8) * CqaCfg::LBO_A + row * 16;  \
-    *reinterpret_cast<uint4*>(dst) = hl.hi;                                \
-    *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;             \
+    // One 128-column segment of a GEMM's A operand = two K=64 stages; stage h holds columns [32*quarter + 16*h, +16) of
+    // every quarter (the weight columns are packed in the same order).  CQA_SEG_PUT publishes my 16 columns of stage h:
+    // wait until the MMAs of the previous segment have drained the stage, split, store, fence, arrive.
+#define CQA_SEG_PUT(h, v, code)                                                              \
+  {                                                                                          \
+    mbar_wait(&a_empty[h], (a_use & 1u) ^ 1u, code);                                         \
+    _Pragma("unroll") for (int h8 = 0; h8 < 2; ++h8) {                                       \
+      HL8 hl = split8((v) + h8 * 8);                                                         \
+      uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2 + h8) * CqaCfg::LBO_A + row * 16; \
+      *reinterpret_cast<uint4*>(dst) = hl.hi;                                                \
+      *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;                             \
+    }                                                                                        \
+    fence_async_smem();                                                                      \
+    mbar_arrive(&a_full[h]);                                                                 \
   }
-#define CQA_CHUNK_END()  \
-  fence_async_smem();    \
-  mbar_arrive(my_full);
+#define CQA_SEG_DONE() ++a_use;
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
@@ -425,20 +428,18 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(att + orow + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
           }
-          CQA_CHUNK_BEGIN(33)
-          CQA_CHUNK_PUT16(0, u)
-          CQA_CHUNK_PUT16(1, u + 16)
-          CQA_CHUNK_END()
+          CQA_SEG_PUT(0, u, 33)
+          CQA_SEG_PUT(1, u + 16, 33)
+          CQA_SEG_DONE()
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             u[j] *= a_reg[j];
             s1 += u[j];
             s2 = fmaf(u[j], u[j], s2);
           }
-          CQA_CHUNK_BEGIN(34)
-          CQA_CHUNK_PUT16(0, u)
-          CQA_CHUNK_PUT16(1, u + 16)
-          CQA_CHUNK_END()
+          CQA_SEG_PUT(0, u, 34)
+          CQA_SEG_PUT(1, u + 16, 34)
+          CQA_SEG_DONE()
           st_s1[g] = s1;
           st_s2[g] = s2;
         }
@@ -521,22 +522,19 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) { c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
-          CQA_CHUNK_BEGIN(36)
-          CQA_CHUNK_PUT16(0, ms)
-          CQA_CHUNK_PUT16(1, ms + 16)
-          CQA_CHUNK_END()
+          CQA_SEG_PUT(0, ms, 36)
+          CQA_SEG_PUT(1, ms + 16, 36)
+          CQA_SEG_DONE()
 #pragma unroll
           for (int j = 0; j < 32; ++j) { c1 += mv[j]; c2 = fmaf(mv[j], mv[j], c2); }
-          CQA_CHUNK_BEGIN(37)
-          CQA_CHUNK_PUT16(0, mv)
-          CQA_CHUNK_PUT16(1, mv + 16)
-          CQA_CHUNK_END()
+          CQA_SEG_PUT(0, mv, 37)
+          CQA_SEG_PUT(1, mv + 16, 37)
+          CQA_SEG_DONE()
 #pragma unroll
           for (int j = 0; j < 32; ++j) { ms[j] *= mv[j]; c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
-          CQA_CHUNK_BEGIN(38)
-          CQA_CHUNK_PUT16(0, ms)
-          CQA_CHUNK_PUT16(1, ms + 16)
-          CQA_CHUNK_END()
+          CQA_SEG_PUT(0, ms, 38)
+          CQA_SEG_PUT(1, ms + 16, 38)
+          CQA_SEG_DONE()
         }
         CQA_STAMP(0, 9);
         xq[0][qd][row] = c1;
@@ -598,27 +596,18 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
         if constexpr (TIMELINE) ++tl_tile;
       }
     }
-#undef CQA_CHUNK_BEGIN
-#undef CQA_CHUNK_PUT16
-#undef CQA_CHUNK_END
+#undef CQA_SEG_PUT
+#undef CQA_SEG_DONE
   } else if (warp == 16 && lane == 0) {
-    // =================================================================== MMA issue + every bulk copy (one thread)
-    uint32_t ready_cnt = 0, done_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
+    // =================================================================== MMA issue (one thread; never waits for a completion)
+    uint32_t ready_cnt = 0, seg_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
     [[maybe_unused]] int tl_tile = 0;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
     const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
-      const int n_i = frame / p.t;
-      // ctx region is free: the previous frame's last U has completed (this thread waited on D2 below)
-      mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
-      bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
       for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
-        const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
         CQA_STAMP(1, 0);
-        // ---- answer image: AQ region (A stages of the previous tile) is free once D4 has completed (waited below)
-        mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
-        bulk_g2s(sAQ, p.a_blob + na * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
         if (a_i == 0) mbar_wait(&ctx_full, frame_cnt & 1u, 40);
         mbar_wait(&aq_full, tile_cnt & 1u, 41);
         tc_fence_after();
@@ -636,7 +625,6 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           umma_split3(T1, a_hi, a_lo, v_hi, v_lo, id_svid, ks > 0 ? 1u : 0u);
         }
         umma_commit(&mma_done);  // D1
-        ++done_cnt;
         CQA_STAMP(1, 2);
         // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
         mbar_wait(&op_ready, ready_cnt & 1u, 42);  // E2
@@ -658,59 +646,71 @@ __global__ void __launch_bounds__(544, 1) cqa_kernel(CqaDev p) {
           umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
         }
         umma_commit(&mma_done);  // D2
-        mbar_wait(&mma_done, done_cnt & 1u, 43);  // P_sub (region B) and P_vid (region AQ) are free once U has completed
-        ++done_cnt;
+        umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
+        if (a_i == 4) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         CQA_STAMP(1, 4);
-        // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk order alternates between the column halves
-        // ---- GEMM chunks: 8 (c2q sub) + 8 (c2q vid) + 12 (concat); chunk q comes from quarter q % 4 and, because every
-        //      quarter owns one K=32 chunk per segment, the weight chunks are consumed in their natural order
-        auto w_src = [&](int q) -> const uint8_t* {
-          return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
-        };
-        for (int q = 0; q < CqaCfg::W_SLOTS - 1; ++q) {  // prime the ring
-          const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, use = (q_cnt + q) / CqaCfg::W_SLOTS;
-          mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 44);
+        // ---- GEMMs: 14 K=64 A stages (4 c2q sub, 4 c2q vid, 6 concat), each against two K=32 weight slots
+        for (int hs = 0; hs < CqaCfg::HALF_SEGS; ++hs) {
+          const uint32_t h = hs & 1u;
+          mbar_wait(&a_full[h], seg_cnt & 1u, 45);
+          const uint32_t i0 = q_cnt + 2u * hs;
+          mbar_wait(&w_full[i0 % CqaCfg::W_SLOTS], (i0 / CqaCfg::W_SLOTS) & 1u, 46);
+          mbar_wait(&w_full[(i0 + 1u) % CqaCfg::W_SLOTS], ((i0 + 1u) / CqaCfg::W_SLOTS) & 1u, 46);
+          tc_fence_after();
+          const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
+          const uint32_t dcol = hs < 4 ? T0 : (hs < 8 ? T1 : T2);
+          const bool first = (hs == 0 || hs == 4 || hs == 8);  // every accumulator starts from zero (a.Wa joins in the epilogue math)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t wsl = smem_u32(sB + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT);
+            const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
+            const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
+            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
+          }
+          umma_commit(&a_empty[h]);
+          umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
+          umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
+          if (h == 1u) ++seg_cnt;
+          if (hs == 7) {
+            umma_commit(&mma_done);  // D3
+            CQA_STAMP(1, 6);
+          }
+          if (hs == 3) CQA_STAMP(1, 5);
+        }
+        umma_commit(&mma_done);  // D4
+        umma_commit(&aq_free);   // the A stages (AQ region) may receive the next answer image
+        CQA_STAMP(1, 7);
+        q_cnt += CqaCfg::CHUNKS;
+        CQA_STAMP(1, 8);
+        if constexpr (TIMELINE) ++tl_tile;
+      }
+    }
+  } else if (warp == 17 && lane == 0) {
+    // =================================================================== every bulk copy (one thread)
+    uint32_t q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
+    auto w_src = [&](int q) -> const uint8_t* {
+      return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
+    };
+    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
+      const int n_i = frame / p.t;
+      if (frame_cnt > 0) mbar_wait(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
+      mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
+      bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
+      for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
+        const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
+        if (tile_cnt > 0) mbar_wait(&aq_free, (tile_cnt - 1u) & 1u, 51);  // previous tile's concat MMAs have drained the A stages
+        mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
+        bulk_g2s(sAQ, p.a_blob + na * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
+        mbar_wait(&b_free, tile_cnt & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
+        for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
+          const uint32_t i = q_cnt + q, slot = i % CqaCfg::W_SLOTS, use = i / CqaCfg::W_SLOTS;
+          mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 53);
           mbar_arrive_expect_tx(&w_full[slot], CqaCfg::W_SLOT);
           bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
         }
-        for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
-          const uint32_t stg = q & 3;  // A stage = producing quarter; every quarter delivers 7 chunks per tile, in step
-          const uint32_t slot = (q_cnt + q) % CqaCfg::W_SLOTS, wuse = (q_cnt + q) / CqaCfg::W_SLOTS;
-          mbar_wait(&a_full[stg], ((q_cnt + q) >> 2) & 1u, 45);
-          mbar_wait(&w_full[slot], wuse & 1u, 46);
-          tc_fence_after();
-          const uint32_t ast = smem_u32(sAQ + stg * CqaCfg::AST_BYTES), wsl = smem_u32(sB + slot * CqaCfg::W_SLOT);
-          const uint32_t dcol = q < 8 ? T0 : (q < 16 ? T1 : T2);
-          const bool first = (q == 0 || q == 8 || q == 16);  // every accumulator starts from zero (a.Wa joins in the epilogue math)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t b_hi = make_smem_desc(wsl + ks * 2 * 2048, 2048, 128);
-            const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + ks * 2 * 2048, 2048, 128);
-            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
-          }
-          umma_commit(&a_empty[stg]);
-          umma_commit(&w_empty[slot]);
-          if (q == 15 || q == CqaCfg::CHUNKS - 1) {
-            umma_commit(&mma_done);  // D3 / D4
-            ++done_cnt;
-            CQA_STAMP(1, q == 15 ? 6 : 7);
-          }
-          if (q == 7) CQA_STAMP(1, 5);
-          if (q + CqaCfg::W_SLOTS - 1 < CqaCfg::CHUNKS) {  // refill the slot chunk q-1 used
-            const uint32_t qq = q_cnt + q + CqaCfg::W_SLOTS - 1;
-            const uint32_t rslot = qq % CqaCfg::W_SLOTS, ruse = qq / CqaCfg::W_SLOTS;
-            mbar_wait(&w_empty[rslot], (ruse & 1u) ^ 1u, 47);
-            mbar_arrive_expect_tx(&w_full[rslot], CqaCfg::W_SLOT);
-            bulk_g2s(sB + rslot * CqaCfg::W_SLOT, w_src(q + CqaCfg::W_SLOTS - 1), CqaCfg::W_SLOT, &w_full[rslot]);
-          }
-        }
         q_cnt += CqaCfg::CHUNKS;
-        // the AQ region (A stages) and T0/T1 may only be reused after the concat MMAs have completed
-        mbar_wait(&mma_done, (done_cnt - 1u) & 1u, 48);  // D4
-        CQA_STAMP(1, 8);
-        if constexpr (TIMELINE) ++tl_tile;
       }
     }
   }

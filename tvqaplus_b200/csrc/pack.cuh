@@ -29,9 +29,10 @@ __host__ __device__ inline PackGeom pack_geom(int n, int k, int kc) {
 }
 
 // w: row-major [n, ld]; packs columns [k0, k0 + g.k) optionally scaled per column by col_scale[k0 + k] (LayerNorm gamma
-// folded into the weight, see cqa.cuh).
+// folded into the weight, see cqa.cuh).  perm128 = 1 reorders the columns inside every 128-column segment to the order
+// in which the fused CQA kernel stages its A operand: packed position h*64 + q*16 + j  <-  source column q*32 + h*16 + j.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int ld, int k0, const float* __restrict__ col_scale,
-                                   PackGeom g, uint8_t* __restrict__ out) {
+                                   PackGeom g, uint8_t* __restrict__ out, int perm128 = 0) {
   // one thread per (k8 slab over the whole padded K, row n)
   const int total = (g.kpad / 8) * g.npad;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -40,8 +41,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int ld, int k0, 
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float x = (n < g.n && kk + j < g.k) ? w[static_cast<size_t>(n) * ld + k0 + kk + j] : 0.f;
-      if (col_scale != nullptr && kk + j < g.k) x *= col_scale[k0 + kk + j];
+      int src = kk + j;
+      if (perm128) {
+        const int pos = src & 127;
+        src = (src & ~127) + ((pos & 63) >> 4) * 32 + (pos >> 6) * 16 + (pos & 15);
+      }
+      float x = (n < g.n && src < g.k) ? w[static_cast<size_t>(n) * ld + k0 + src] : 0.f;
+      if (col_scale != nullptr && src < g.k) x *= col_scale[k0 + src];
       v[j] = x;
     }
     HL8 hl = split8(v);

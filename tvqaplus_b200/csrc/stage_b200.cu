@@ -193,11 +193,11 @@ int stage_cqa_prepare_weights(const float* c2q_ln_g, const float* c2q_ln_b, cons
   }
   {
     PackGeom g = pack_geom(128, 256, 32);
-    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 128, c2q_ln_g, g, wb + WB_WU);
+    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 128, c2q_ln_g, g, wb + WB_WU, 1);
   }
   {
     PackGeom g = pack_geom(128, 384, 32);
-    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(cat_w, 384, 0, cat_ln_g, g, wb + WB_WF);
+    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(cat_w, 384, 0, cat_ln_g, g, wb + WB_WF, 1);
   }
   fold_layernorm_kernel<<<16, 256, 0, s>>>(c2q_w, 128, 384, c2q_ln_g, c2q_ln_b, c2q_b, vec, vec + 128);
   fold_layernorm_kernel<<<16, 256, 0, s>>>(cat_w, 128, 384, cat_ln_g, cat_ln_b, cat_b, vec + 256, vec + 384);
