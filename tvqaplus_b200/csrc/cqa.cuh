@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           for (int j = 0; j < p.ls; ++j) any_s += mask_cs[j];
         }
 
-        // ---- softmax of both streams: the 7 sub + 3 vid score chunks (16 columns each) are dealt to the quarters as
+        // ---- softmax of both streams, normalisation deferred: P' = exp2(scale*log2e*S - shift) goes to the tensor cores
+        //      un-normalised and U = P'.ctx is divided by the row sum when it is read back (the partial sums of the four
+        //      quarters meet in shared memory under the U MMAs, so this phase has no block barrier at all).
+        //      The 7 sub + 3 vid score chunks (16 columns each) are dealt to the quarters as
         //      q0: sub 0,1,2   q1: sub 3,4,5   q2: sub 6, vid 0   q3: vid 1, 2
         CQA_STAMP(0, 1);
         mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
@@ -281,7 +284,6 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 2);
         {
-          float s[48];
           float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
           float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
           float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
@@ -291,25 +293,50 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   const int ch = qd < 2 ? 3 * qd + (k) : (qd == 2 ? ((k) == 0 ? 6 : 0) : (k) + 1);      \
   const int n_real = vid ? p.r : p.ls;                                                 \
   const bool on = (qd < 2 || (k) < 2) && ch * 16 < (vid ? p.r_pad : p.ls_pad);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            CQA_SLOT(k)
-            (void)n_real;
-            if (on) tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, s + k * 16);
-          }
-          tmem_wait_ld();
-          // |cos| <= 1, so scale*log2(e) bounds every live score: with that as the (fixed) softmax shift no row maximum has
-          // to be exchanged between the quarters.  Very large scales (exp2 underflow) take the exact-maximum path.
+          // |cos| <= 1, so sc2 = scale*log2(e) bounds every live score: shifting by sc2 - 15 keeps P' inside fp16 range
+          // ((0, 2^15]) without knowing the row maximum.  Very large scales take the exact-maximum path instead.
           const float sc2 = p.scale * 1.4426950408889634f;
-          const bool fixed_shift = sc2 <= 60.f;
-          float mxs = -3.0e38f, mxv = -3.0e38f;
+          float shift_s = sc2 - 15.f, shift_v = sc2 - 15.f;
+          if (sc2 > 50.f) {
+            float mxs = -3.0e38f, mxv = -3.0e38f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              CQA_SLOT(k)
+              (void)n_real;
+              if (on) {
+                float sv[16];
+                tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, sv);
+                tmem_wait_ld();
+                const float* ic = (vid ? inv_cv : inv_cs) + ch * 16;
+                float mx = -3.0e38f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float w = ia * ic[j];
+                  if (w != 0.f) mx = fmaxf(mx, sv[j] * w * sc2);
+                }
+                if (vid) mxv = fmaxf(mxv, mx); else mxs = fmaxf(mxs, mx);
+              }
+            }
+            xq[0][qd][row] = mxs;
+            xq[1][qd][row] = mxv;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            shift_s = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row])) - 15.f;
+            shift_v = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row])) - 15.f;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+          }
+          float sms = 0.f, smv = 0.f;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             CQA_SLOT(k)
             if (on) {
+              float sv[16];
+              tmem_ld16((vid ? T1 : T0) + lane_off + ch * 16, sv);
+              tmem_wait_ld();
               const float4* ic4 = reinterpret_cast<const float4*>((vid ? inv_cv : inv_cs) + ch * 16);
               float* raw = vid ? raw_v : raw_s;
-              float mx = -3.0e38f;
+              float* nrm = vid ? nrm_v : nrm_s;
+              const float shift = vid ? shift_v : shift_s;
+              float sum = 0.f;
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 c4 = ic4[j4];
@@ -320,80 +347,37 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
                   // S - 1e10*(1 - S_mask) of the reference: |S| <= 1 is absorbed by -1e10 in fp32, so a select is exact.
                   // Padded columns (>= n_real) carry inverse norm 0 and behave like masked ones (weight exactly 0).
                   const float w = ia * cc[e];
-                  float v = (w != 0.f) ? s[k * 16 + j] * w : -1e10f;
+                  const float v = (w != 0.f) ? sv[j] * w : -1e10f;
                   if (raw != nullptr && ch * 16 + j < n_real) raw[ch * 16 + j] = v;
-                  v *= sc2;  // scale * log2(e): the softmax below runs in base 2
-                  s[k * 16 + j] = v;
-                  mx = fmaxf(mx, v);
+                  const float ex = fast_exp2(fmaf(v, sc2, -shift));  // masked / padded: exp2(-1.4e11) = 0
+                  sum += ex;
+                  sv[j] = ex;
                 }
               }
-              if (vid) mxv = fmaxf(mxv, mx); else mxs = fmaxf(mxs, mx);
-            }
-          }
-          if (fixed_shift) {
-            mxs = sc2;
-            mxv = sc2;
-          } else {
-            xq[0][qd][row] = mxs;
-            xq[1][qd][row] = mxv;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            mxs = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row]));
-            mxv = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row]));
-          }
-          float sms = 0.f, smv = 0.f;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            CQA_SLOT(k)
-            (void)n_real;
-            if (on) {
-              const float mx = vid ? mxv : mxs;
-              float sum = 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float e = fast_exp2(s[k * 16 + j] - mx);  // masked / padded: exp2(-1.4e11) = 0
-                sum += e;
-                s[k * 16 + j] = e;
-              }
-              if (vid) smv += sum; else sms += sum;
-            }
-          }
-          xq[2][qd][row] = sms;
-          xq[3][qd][row] = smv;
-          asm volatile("bar.sync 1, 512;" ::: "memory");
-          // masked entries of a live row are exactly 0; a fully masked row must become 0 after the "* S_mask" of the
-          // reference -> its 1/sum is replaced by 0
-          const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) : 0.f;
-          const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) : 0.f;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            CQA_SLOT(k)
-            if (on) {
-              float* nrm = vid ? nrm_v : nrm_s;
-              const float isum = vid ? iv : is;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) s[k * 16 + j] *= isum;
-              if (nrm != nullptr) {
+              if (nrm != nullptr) {  // optional output: normalised after the row sums are known (see below)
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                  if (ch * 16 + j < n_real) nrm[ch * 16 + j] = s[k * 16 + j];
+                  if (ch * 16 + j < n_real) nrm[ch * 16 + j] = sv[j];
               }
+              if (vid) smv += sum; else sms += sum;
               uint8_t* img = vid ? sAQ : sB;                       // P_vid overlays the answer image, P_sub the weight ring
               const uint32_t part = vid ? CqaCfg::PV_PART : CqaCfg::PS_PART;
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8) {
-                HL8 hl = split8(s + k * 16 + h8 * 8);
+                HL8 hl = split8(sv + h8 * 8);
                 uint8_t* dst = img + (ch * 2 + h8) * CqaCfg::LBO_A + row * 16;
                 *reinterpret_cast<uint4*>(dst) = hl.hi;
                 *reinterpret_cast<uint4*>(dst + part) = hl.lo;
               }
             }
           }
-#undef CQA_SLOT
+          xq[2][qd][row] = sms;
+          xq[3][qd][row] = smv;
         }
         CQA_STAMP(0, 3);
         tc_fence_before();
         fence_async_smem();
-        mbar_arrive(&op_ready);  // E2: P images are in place, S has been consumed
+        mbar_arrive(&op_ready);  // E2: P' images and the partial row sums are in place, S has been consumed
         CQA_STAMP(0, 4);
         // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
         float a_reg[32];
@@ -406,39 +390,65 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           }
         }
 
-        // ---- c2q A operands for both streams: the raw U chunk, then the raw a*U chunk; statistics on the fly
+        // ---- c2q A operands for both streams: the raw U segment, then the raw a*U segment; statistics on the fly.
+        //      Everything is produced 16 columns (one stage contribution) at a time to stay inside the register budget
+        //      (shared memory takes the whole L1 carve-out here, so a spill would cost an L2 round trip).
         mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
         ++done_cnt;
         tc_fence_after();
         CQA_STAMP(0, 5);
+        // U completed => every thread has passed E2 => all partial row sums are in xq[2..3].  Masked entries of a live row
+        // are exactly 0; a fully masked row must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
+        const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) : 0.f;
+        const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) : 0.f;
+        if (p.sub_norm_s != nullptr || p.vid_norm_s != nullptr) {  // optional output: normalise what this thread stored above
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            CQA_SLOT(k)
+            float* nrm = vid ? p.vid_norm_s : p.sub_norm_s;
+            if (on && live && nrm != nullptr) {
+              nrm += (tile * p.lq + row) * n_real;
+              for (int j = 0; j < 16; ++j)
+                if (ch * 16 + j < n_real) nrm[ch * 16 + j] *= (vid ? iv : is);
+            }
+          }
+        }
+#undef CQA_SLOT
         float st_s1[2], st_s2[2];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint32_t tU = (g == 0 ? T2 : T3) + coff;
+          const float isum = g == 0 ? is : iv;
           float* att = g == 0 ? p.att_sub : p.att_vid;
           float s1 = 0.f, s2 = 0.f;
-          float u[32];
-          tmem_ld16(tU, u);
-          tmem_ld16(tU + 16, u + 16);
-          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
-          if (att != nullptr && live) {
+          for (int h = 0; h < 2; ++h) {
+            float u[16];
+            tmem_ld16(tU + h * 16, u);
+            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(att + orow + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+            for (int j = 0; j < 16; ++j) { u[j] *= isum; s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
+            if (att != nullptr && live) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(att + orow + h * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
+            }
+            CQA_SEG_PUT(h, u, 33)
           }
-          CQA_SEG_PUT(0, u, 33)
-          CQA_SEG_PUT(1, u + 16, 33)
           CQA_SEG_DONE()
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            u[j] *= a_reg[j];
-            s1 += u[j];
-            s2 = fmaf(u[j], u[j], s2);
+          for (int h = 0; h < 2; ++h) {
+            float u[16];
+            tmem_ld16(tU + h * 16, u);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              u[j] *= isum * a_reg[h * 16 + j];
+              s1 += u[j];
+              s2 = fmaf(u[j], u[j], s2);
+            }
+            CQA_SEG_PUT(h, u, 34)
           }
-          CQA_SEG_PUT(0, u, 34)
-          CQA_SEG_PUT(1, u + 16, 34)
           CQA_SEG_DONE()
           st_s1[g] = s1;
           st_s2[g] = s2;
@@ -447,23 +457,21 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         // the frame-invariant a.Wa term of c2q (same for both streams) joins the accumulators in the concat production.
         // Its loads fly under the statistics exchange; it is then parked in my own cells of T3 (U_vid, which I have just
         // consumed) so that it costs no registers while the c2q MMAs drain.
-        float za[32];
+        float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
         {
+          float za[32];
           const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
           }
-        }
-        const float asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);  // sum(a), sum(a^2) of my row
-        xq[0][qd][row] = st_s1[0]; xq[1][qd][row] = st_s2[0];
-        xq[2][qd][row] = st_s1[1]; xq[3][qd][row] = st_s2[1];
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        tmem_st16(T3 + coff, za);
-        tmem_st16(T3 + coff + 16, za + 16);
-        float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
-        {
+          const float asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);  // sum(a), sum(a^2) of my row
+          xq[0][qd][row] = st_s1[0]; xq[1][qd][row] = st_s2[0];
+          xq[2][qd][row] = st_s1[1]; xq[3][qd][row] = st_s2[1];
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          tmem_st16(T3 + coff, za);
+          tmem_st16(T3 + coff + 16, za + 16);
           const float t1 = asum + ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row]));
           const float t2 = asq + ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row]));
           const float mu_s = t1 * (1.f / 384.f);
@@ -474,11 +482,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           const float mu_v = v1 * (1.f / 384.f);
           r_v = 1.f / sqrtf(fmaxf(v2 * (1.f / 384.f) - mu_v * mu_v, 0.f) + 1e-5f);
           nm_v = -r_v * mu_v;
+          tmem_wait_st();
         }
-        tmem_wait_st();
         asm volatile("bar.sync 1, 512;" ::: "memory");  // everyone has read xq before it is reused below
 
-        // ---- concat_fc A operands: ms chunk, mv chunk, ms*mv chunk with ms/mv = relu(rstd*(acc + za - mean*cs) + cb)
+        // ---- concat_fc A operands: ms, mv, ms*mv segments with ms/mv = relu(rstd*(acc + za - mean*cs) + cb).  The
+        //      activated values are written back over their accumulators (my own TMEM cells), so the product segment
+        //      re-reads them instead of holding 64 registers.
         tc_fence_before();
         CQA_STAMP(0, 7);
         mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
@@ -486,56 +496,57 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 8);
         float c1 = 0.f, c2 = 0.f;
-        {
-          float ms[32], mv[32];
-          const float4* cs4 = reinterpret_cast<const float4*>(&pvec[0][qd * 32]);
-          const float4* cb4 = reinterpret_cast<const float4*>(&pvec[1][qd * 32]);
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {  // 16 columns at a time keeps (ms, mv, za) within the register budget
-            float zz[16];
-            tmem_ld16(T0 + coff + sl * 16, ms + sl * 16);
-            tmem_ld16(T1 + coff + sl * 16, mv + sl * 16);
-            tmem_ld16(T3 + coff + sl * 16, zz);
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t tC = (g == 0 ? T0 : T1) + coff;
+          const float rr = g == 0 ? r_s : r_v, nm = g == 0 ? nm_s : nm_v;
+          float* mixed = g == 0 ? p.mixed_sub : p.mixed_vid;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float m[16], zz[16];
+            tmem_ld16(tC + h * 16, m);
+            tmem_ld16(T3 + coff + h * 16, zz);
             tmem_wait_ld();
+            const float4* cs4 = reinterpret_cast<const float4*>(&pvec[0][qd * 32 + h * 16]);
+            const float4* cb4 = reinterpret_cast<const float4*>(&pvec[1][qd * 32 + h * 16]);
 #pragma unroll
-            for (int j4 = sl * 4; j4 < sl * 4 + 4; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
               const float4 cs = cs4[j4], cb = cb4[j4];
               const float csv[4] = {cs.x, cs.y, cs.z, cs.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const float z = zz[j - sl * 16];
-                ms[j] = fmaxf(fmaf(r_s, ms[j] + z, fmaf(nm_s, csv[e], cbv[e])), 0.f);
-                mv[j] = fmaxf(fmaf(r_v, mv[j] + z, fmaf(nm_v, csv[e], cbv[e])), 0.f);
+                m[j] = fmaxf(fmaf(rr, m[j] + zz[j], fmaf(nm, csv[e], cbv[e])), 0.f);
+                c1 += m[j];
+                c2 = fmaf(m[j], m[j], c2);
               }
             }
+            tmem_st16(tC + h * 16, m);
+            if (live && mixed != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(mixed + orow + h * 16 + j) = make_float4(m[j], m[j + 1], m[j + 2], m[j + 3]);
+            }
+            CQA_SEG_PUT(h, m, 36)
           }
-          if (live && p.mixed_sub != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.mixed_sub + orow + j) = make_float4(ms[j], ms[j + 1], ms[j + 2], ms[j + 3]);
-          }
-          if (live && p.mixed_vid != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.mixed_vid + orow + j) = make_float4(mv[j], mv[j + 1], mv[j + 2], mv[j + 3]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
-          CQA_SEG_PUT(0, ms, 36)
-          CQA_SEG_PUT(1, ms + 16, 36)
-          CQA_SEG_DONE()
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { c1 += mv[j]; c2 = fmaf(mv[j], mv[j], c2); }
-          CQA_SEG_PUT(0, mv, 37)
-          CQA_SEG_PUT(1, mv + 16, 37)
-          CQA_SEG_DONE()
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { ms[j] *= mv[j]; c1 += ms[j]; c2 = fmaf(ms[j], ms[j], c2); }
-          CQA_SEG_PUT(0, ms, 38)
-          CQA_SEG_PUT(1, ms + 16, 38)
           CQA_SEG_DONE()
         }
+        tmem_wait_st();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float m[16], w[16];
+          tmem_ld16(T0 + coff + h * 16, m);
+          tmem_ld16(T1 + coff + h * 16, w);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            m[j] *= w[j];
+            c1 += m[j];
+            c2 = fmaf(m[j], m[j], c2);
+          }
+          CQA_SEG_PUT(h, m, 38)
+        }
+        CQA_SEG_DONE()
         CQA_STAMP(0, 9);
         xq[0][qd][row] = c1;
         xq[1][qd][row] = c2;
