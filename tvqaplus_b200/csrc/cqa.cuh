@@ -244,13 +244,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     // wait until the MMAs of the previous segment have drained the stage, split, store, fence, arrive.
 #define CQA_SEG_PUT(h, v, code)                                                              \
   {                                                                                          \
+    const HL8 hl0 = split8((v)), hl1 = split8((v) + 8);                                      \
+    uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2) * CqaCfg::LBO_A + row * 16;      \
     mbar_wait(&a_empty[h], (a_use & 1u) ^ 1u, code);                                         \
-    _Pragma("unroll") for (int h8 = 0; h8 < 2; ++h8) {                                       \
-      HL8 hl = split8((v) + h8 * 8);                                                         \
-      uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2 + h8) * CqaCfg::LBO_A + row * 16; \
-      *reinterpret_cast<uint4*>(dst) = hl.hi;                                                \
-      *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;                             \
-    }                                                                                        \
+    *reinterpret_cast<uint4*>(dst) = hl0.hi;                                                 \
+    *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl0.lo;                              \
+    *reinterpret_cast<uint4*>(dst + CqaCfg::LBO_A) = hl1.hi;                                 \
+    *reinterpret_cast<uint4*>(dst + CqaCfg::LBO_A + CqaCfg::AST_PART) = hl1.lo;              \
     fence_async_smem();                                                                      \
     mbar_arrive(&a_full[h]);                                                                 \
   }
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
               }
             }
           }
-          xq[2][qd][row] = sms;
-          xq[3][qd][row] = smv;
+          xq[0][qd][row] = sms;  // (xq[0..1] were last read before this tile's predecessor passed its final barrier)
+          xq[1][qd][row] = smv;
         }
         CQA_STAMP(0, 3);
         tc_fence_before();
@@ -390,6 +390,18 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           }
         }
 
+        // ---- the frame-invariant a.Wa term of c2q (same for both streams): its loads fly under the U MMAs, then it is
+        //      written into both c2q accumulators (my own cells of T0 / T1; S there is dead once U has completed) and the
+        //      c2q MMAs accumulate on top of it
+        float za[32];
+        {
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
+          }
+        }
         // ---- c2q A operands for both streams: the raw U segment, then the raw a*U segment; statistics on the fly.
         //      Everything is produced 16 columns (one stage contribution) at a time to stay inside the register budget
         //      (shared memory takes the whole L1 carve-out here, so a spill would cost an L2 round trip).
@@ -397,10 +409,16 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         ++done_cnt;
         tc_fence_after();
         CQA_STAMP(0, 5);
+        tmem_st16(T0 + coff, za);
+        tmem_st16(T0 + coff + 16, za + 16);
+        tmem_st16(T1 + coff, za);
+        tmem_st16(T1 + coff + 16, za + 16);
+        tmem_wait_st();
+        tc_fence_before();  // orders the stores before my a_full arrivals, i.e. before the first c2q MMA
         // U completed => every thread has passed E2 => all partial row sums are in xq[2..3].  Masked entries of a live row
         // are exactly 0; a fully masked row must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
-        const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) : 0.f;
-        const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) : 0.f;
+        const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) : 0.f;
+        const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) : 0.f;
         if (p.sub_norm_s != nullptr || p.vid_norm_s != nullptr) {  // optional output: normalise what this thread stored above
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
@@ -454,24 +472,12 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           st_s2[g] = s2;
         }
         CQA_STAMP(0, 6);
-        // the frame-invariant a.Wa term of c2q (same for both streams) joins the accumulators in the concat production.
-        // Its loads fly under the statistics exchange; it is then parked in my own cells of T3 (U_vid, which I have just
-        // consumed) so that it costs no registers while the c2q MMAs drain.
         float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
         {
-          float za[32];
-          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
-          }
           const float asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);  // sum(a), sum(a^2) of my row
           xq[0][qd][row] = st_s1[0]; xq[1][qd][row] = st_s2[0];
           xq[2][qd][row] = st_s1[1]; xq[3][qd][row] = st_s2[1];
           asm volatile("bar.sync 1, 512;" ::: "memory");
-          tmem_st16(T3 + coff, za);
-          tmem_st16(T3 + coff + 16, za + 16);
           const float t1 = asum + ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row]));
           const float t2 = asq + ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row]));
           const float mu_s = t1 * (1.f / 384.f);
@@ -482,7 +488,6 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           const float mu_v = v1 * (1.f / 384.f);
           r_v = 1.f / sqrtf(fmaxf(v2 * (1.f / 384.f) - mu_v * mu_v, 0.f) + 1e-5f);
           nm_v = -r_v * mu_v;
-          tmem_wait_st();
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");  // everyone has read xq before it is reused below
 
@@ -503,9 +508,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           float* mixed = g == 0 ? p.mixed_sub : p.mixed_vid;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            float m[16], zz[16];
+            float m[16];
             tmem_ld16(tC + h * 16, m);
-            tmem_ld16(T3 + coff + h * 16, zz);
             tmem_wait_ld();
             const float4* cs4 = reinterpret_cast<const float4*>(&pvec[0][qd * 32 + h * 16]);
             const float4* cb4 = reinterpret_cast<const float4*>(&pvec[1][qd * 32 + h * 16]);
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                m[j] = fmaxf(fmaf(rr, m[j] + zz[j], fmaf(nm, csv[e], cbv[e])), 0.f);
+                m[j] = fmaxf(fmaf(rr, m[j], fmaf(nm, csv[e], cbv[e])), 0.f);
                 c1 += m[j];
                 c2 = fmaf(m[j], m[j], c2);
               }
@@ -602,7 +606,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           if (live && qd == 0) p.statement_mask[tile * p.lq + row] = (ma * any_v != 0.f) ? 1.f : 0.f;
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // xq is rewritten by the next tile
+        // no barrier here: the next tile first writes xq[0..1] (softmax sums), which every thread finished reading before the
+        // barrier above; xq[2..3] are rewritten only after the next tile's c2q production, which needs all 512 threads
         CQA_STAMP(0, 11);
         if constexpr (TIMELINE) ++tl_tile;
       }
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           tc_fence_after();
           const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
           const uint32_t dcol = hs < 4 ? T0 : (hs < 8 ? T1 : T2);
-          const bool first = (hs == 0 || hs == 4 || hs == 8);  // every accumulator starts from zero (a.Wa joins in the epilogue math)
+          const bool first = (hs == 8);  // the c2q accumulators start from the stored a.Wa term, concat from zero
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t wsl = smem_u32(sB + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT);
