@@ -48,10 +48,17 @@ int stage_check_device_error(void* stream);
 size_t stage_packed_weight_bytes(int n, int k, int kc);
 int stage_pack_weight(const float* w, int n, int k, int kc, void* packed, void* stream);
 
+/* LayerNorm folded into the Linear that follows it (LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * cs) + cb):
+ * packs W*gamma like stage_pack_weight and writes cs[n] = sum_k W[n,k] gamma[k], cb[n] = sum_k W[n,k] beta[k] + bias[n]. */
+int stage_pack_weight_ln(const float* w, int n, int k, int kc, const float* ln_g, const float* ln_b, const float* bias,
+                         void* packed, float* cs, float* cb, void* stream);
+
 /* ---- row-wise Linear with fused prologue / epilogue -------------------------------------------------------------
  * y = LN_out( act( LN_in( l2norm?(x) ) W^T + b ) ), each piece optional.  Stands in for the nn.Sequential stacks
  * bert_word_encoding_fc / vid_fc / input_embedding (model/stage.py:85-91,98-104,115-120) and F.normalize at
- * model/stage.py:256, and for LinearWrapper (model/stage.py:15-32).  n <= 304, k % 4 == 0. */
+ * model/stage.py:256, and for LinearWrapper (model/stage.py:15-32).  n <= 304, k % 4 == 0.
+ * The raw rows are streamed from HBM once; LN_in / l2norm are applied in the epilogue from row statistics gathered on
+ * the way (so a weight used with LN_in must come from stage_pack_weight_ln, together with its cs / cb vectors). */
 typedef struct {
   int64_t m;             /* rows */
   int k, n;              /* in / out features */
@@ -59,10 +66,10 @@ typedef struct {
   int l2norm_in;         /* 1: x <- x / max(||x||_2, 1e-12) first */
   int relu;              /* 1: ReLU after bias */
   const float* x;        /* [m,k] */
-  const void* w_packed;  /* stage_pack_weight(W[n,k]) */
-  const float* bias;     /* [n] */
-  const float* ln_in_g;  /* [k] or NULL */
-  const float* ln_in_b;
+  const void* w_packed;  /* stage_pack_weight(W[n,k]) or, with LN_in, stage_pack_weight_ln */
+  const float* bias;     /* [n]; ignored when ln_in_cs is given (cb contains it) */
+  const float* ln_in_cs; /* [n] from stage_pack_weight_ln, or NULL = no LayerNorm in front */
+  const float* ln_in_cb;
   const float* ln_out_g; /* [n] or NULL */
   const float* ln_out_b;
   float* y;              /* [m,n] */

@@ -30,6 +30,8 @@ CASES = [
     (5, 128, 1, True, False, False, False),        # LinearWrapper(128 -> 1)
     (40000, 768, 300, True, True, False, True),    # many tiles per CTA (persistent loop, phase wrap)
     (129, 384, 128, True, False, False, True),     # c2q-like
+    (257, 300, 300, False, False, True, False),    # F.normalize alone
+    (9000, 300, 128, False, True, False, True),    # input_embedding, many tiles (5 chunks, prefetch wraps tiles)
 ]
 
 
@@ -40,15 +42,19 @@ def test_linear_matches_reference(m, k, n, ln_in, ln_out, l2, relu):
     x = torch.randn(m, k, generator=g)
     if m > 10:
         x[3].zero_()  # zero padded row, as pad_sequences_2d produces
+        x[5] += 40.0  # a row with a large common offset (the one-pass variance is shifted by its first element)
+        x[7] = 3.0    # a constant row: LayerNorm must give exactly beta
     w = torch.randn(n, k, generator=g) / k ** 0.5
     b = torch.randn(n, generator=g) * 0.1
     li = (torch.rand(k, generator=g) + 0.5, torch.randn(k, generator=g) * 0.1) if ln_in else None
     lo = (torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g) * 0.1) if ln_out else None
     want = ref_linear(x, w, b, li, lo, l2, relu)
     dev = torch.device("cuda:0")
-    wp = ops.pack_weight(w.to(dev))
-    got = ops.linear_fwd(x.to(dev), wp, b.to(dev), n,
-                         ln_in=tuple(t.to(dev) for t in li) if li else None,
+    if li:
+        wp, cs, cb = ops.pack_weight_ln(w.to(dev), b.to(dev), li[0].to(dev), li[1].to(dev))
+    else:
+        wp, cs, cb = ops.pack_weight(w.to(dev)), None, None
+    got = ops.linear_fwd(x.to(dev), wp, None if li else b.to(dev), n, ln_in=(cs, cb) if li else None,
                          ln_out=tuple(t.to(dev) for t in lo) if lo else None, l2norm_in=l2, relu=relu)
     torch.cuda.synchronize()
     _lib.check_device_error()

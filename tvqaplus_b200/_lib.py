@@ -19,7 +19,7 @@ _f = C.c_void_p  # device pointers travel as integers
 
 class LinearArgs(C.Structure):
     _fields_ = [("m", C.c_int64), ("k", C.c_int), ("n", C.c_int), ("kc", C.c_int), ("l2norm_in", C.c_int),
-                ("relu", C.c_int), ("x", _f), ("w_packed", _f), ("bias", _f), ("ln_in_g", _f), ("ln_in_b", _f),
+                ("relu", C.c_int), ("x", _f), ("w_packed", _f), ("bias", _f), ("ln_in_cs", _f), ("ln_in_cb", _f),
                 ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f)]
 
 
@@ -71,6 +71,7 @@ SYMBOLS = {
     "stage_check_device_error": (C.c_int, [C.c_void_p]),
     "stage_packed_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "stage_pack_weight_ln": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "stage_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "stage_encoder_block_fwd": (C.c_int, [C.POINTER(EncoderArgs), C.c_void_p]),
     "stage_mha_fwd": (C.c_int, [C.POINTER(MhaArgs), C.c_void_p]),

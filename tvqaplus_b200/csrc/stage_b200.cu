@@ -93,21 +93,36 @@ int stage_pack_weight(const float* w, int n, int k, int kc, void* packed, void* 
   return check_launch("pack_weight");
 }
 
+int stage_pack_weight_ln(const float* w, int n, int k, int kc, const float* ln_g, const float* ln_b, const float* bias,
+                         void* packed, float* cs, float* cb, void* stream) {
+  STG_REQUIRE(w && ln_g && ln_b && bias && packed && cs && cb, STAGE_E_BADARG, "pack_weight_ln: null pointer");
+  STG_REQUIRE(n > 0 && n <= 304 && k > 0 && (kc == 32 || kc == 64), STAGE_E_UNSUPPORTED, "pack_weight_ln: n=%d k=%d kc=%d", n, k, kc);
+  STG_REQUIRE(aligned16(packed), STAGE_E_BADARG, "pack_weight_ln: packed buffer not 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PackGeom g = pack_geom(n, k, kc);
+  const int total = (g.kpad / 8) * g.npad;
+  pack_weight_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, k, 0, ln_g, g, static_cast<uint8_t*>(packed));
+  fold_layernorm_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(w, n, k, ln_g, ln_b, bias, cs, cb);
+  return check_launch("pack_weight_ln");
+}
+
 int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
-  STG_REQUIRE(a && a->x && a->w_packed && a->bias && a->y, STAGE_E_BADARG, "linear: null pointer");
+  STG_REQUIRE(a && a->x && a->w_packed && a->y, STAGE_E_BADARG, "linear: null pointer");
   STG_REQUIRE(a->m > 0 && a->k > 0 && a->n > 0, STAGE_E_BADARG, "linear: m=%lld k=%d n=%d", (long long)a->m, a->k, a->n);
   STG_REQUIRE(a->k % 4 == 0, STAGE_E_UNSUPPORTED, "linear: k=%d must be a multiple of 4", a->k);
   STG_REQUIRE(a->n <= 304, STAGE_E_UNSUPPORTED, "linear: n=%d > 304", a->n);
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->w_packed), STAGE_E_BADARG, "linear: pointers must be 16-byte aligned");
-  STG_REQUIRE((a->ln_in_g == nullptr) == (a->ln_in_b == nullptr) && (a->ln_out_g == nullptr) == (a->ln_out_b == nullptr),
-              STAGE_E_BADARG, "linear: LayerNorm gamma/beta must come in pairs");
+  STG_REQUIRE((a->ln_in_cs == nullptr) == (a->ln_in_cb == nullptr) && (a->ln_out_g == nullptr) == (a->ln_out_b == nullptr),
+              STAGE_E_BADARG, "linear: LayerNorm vectors must come in pairs");
+  STG_REQUIRE(a->ln_in_cs != nullptr || a->bias != nullptr, STAGE_E_BADARG, "linear: null bias");
   const int want_kc = a->n <= 128 ? 64 : 32;
   STG_REQUIRE(a->kc == want_kc, STAGE_E_UNSUPPORTED, "linear: weight for n=%d must be packed with kc=%d", a->n, want_kc);
   PackGeom g = pack_geom(a->n, a->k, a->kc);
   LinearDev d;
-  d.x = a->x; d.w = static_cast<const uint8_t*>(a->w_packed); d.bias = a->bias;
-  d.ln_in_g = a->ln_in_g; d.ln_in_b = a->ln_in_b; d.ln_out_g = a->ln_out_g; d.ln_out_b = a->ln_out_b;
+  d.x = a->x; d.w = static_cast<const uint8_t*>(a->w_packed); d.bias = a->bias; d.cs = a->ln_in_cs; d.cb = a->ln_in_cb;
+  d.ln_out_g = a->ln_out_g; d.ln_out_b = a->ln_out_b;
   d.y = a->y; d.m = a->m; d.k = a->k; d.n = a->n; d.n_chunks = g.n_chunks; d.l2norm_in = a->l2norm_in; d.relu = a->relu;
+  d.out_blocked = 0; d.rows_per_block = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->n <= 128) return launch_linear<128, 64, 3>(d, s);
   return launch_linear<304, 32, 3>(d, s);
@@ -246,9 +261,9 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   // 2. frame-invariant third of c2q: Za = a . (Wc*gamma)[:, :128]^T
   {
     LinearDev d;
-    d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.ln_in_g = nullptr; d.ln_in_b = nullptr;
+    d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.cs = nullptr; d.cb = nullptr;
     d.ln_out_g = nullptr; d.ln_out_b = nullptr; d.y = za; d.m = static_cast<long long>(a->n) * 5 * a->lq;
-    d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0;
+    d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0; d.out_blocked = 0; d.rows_per_block = 1;
     int rc = launch_linear<128, 64, 3>(d, s);
     if (rc) return rc;
   }

@@ -21,3 +21,20 @@ def packed(param: torch.Tensor, kc: int) -> torch.Tensor:
     img = ops.pack_weight(param.detach(), kc)
     _cache[key] = (tag, img, weakref.ref(param, lambda _r, k=key: _cache.pop(k, None)))
     return img
+
+
+_cache_ln: Dict[int, Tuple[tuple, tuple, "weakref.ref"]] = {}
+
+
+def packed_ln(lin, ln, kc: int):
+    """(image of W*gamma, cs, cb) for ``lin`` (nn.Linear) applied after ``ln`` (nn.LayerNorm); cached on the versions of
+    all four parameters."""
+    params = (lin.weight, lin.bias, ln.weight, ln.bias)
+    key = id(lin.weight)
+    tag = tuple((t.data_ptr(), t._version, str(t.device)) for t in params) + (kc,)
+    hit = _cache_ln.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is lin.weight:
+        return hit[1]
+    out = ops.pack_weight_ln(lin.weight, lin.bias, ln.weight, ln.bias, kc)
+    _cache_ln[key] = (tag, out, weakref.ref(lin.weight, lambda _r, k=key: _cache_ln.pop(k, None)))
+    return out

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ._packing import packed
+from ._packing import packed, packed_ln
 from .cnn import DepthwiseSeparableConv
 from .context_query_attention import StructuredAttention
 from .encoder import StackedEncoder, _no_train_dropout
@@ -48,8 +48,11 @@ class LinearWrapper(nn.Module):
         _no_train_dropout(self, self.p)
         lin = self.conv[-1]
         ln = self.conv[0] if isinstance(self.conv[0], nn.LayerNorm) else None
-        return ops.linear_fwd(x, packed(lin.weight, ops.kc_for(lin.out_features)), lin.bias, lin.out_features,
-                              ln_in=_ln_pair(ln) if ln is not None else None, relu=self.relu)
+        kc = ops.kc_for(lin.out_features)
+        if ln is None:
+            return ops.linear_fwd(x, packed(lin.weight, kc), lin.bias, lin.out_features, relu=self.relu)
+        img, cs, cb = packed_ln(lin, ln, kc)
+        return ops.linear_fwd(x, img, None, lin.out_features, ln_in=(cs, cb), relu=self.relu)
 
 
 class ConvLinear(nn.Module):
@@ -162,14 +165,15 @@ class STAGE(nn.Module):
 
     def _text_fc(self, x):
         fc, emb = self.bert_word_encoding_fc, self.input_embedding
-        h = ops.linear_fwd(x, packed(fc[2].weight, 32), fc[2].bias, self.bridge_hsz, ln_in=_ln_pair(fc[0]), relu=True,
-                           ln_out=_ln_pair(fc[4]))
+        img, cs, cb = packed_ln(fc[2], fc[0], 32)
+        h = ops.linear_fwd(x, img, None, self.bridge_hsz, ln_in=(cs, cb), relu=True, ln_out=_ln_pair(fc[4]))
         return ops.linear_fwd(h, packed(emb[1].weight, 64), emb[1].bias, self.hsz, relu=True, ln_out=_ln_pair(emb[3]))
 
     def _vid_fc(self, x):
         fc, emb = self.vid_fc, self.input_embedding
-        h = ops.linear_fwd(x, packed(fc[2].weight, 32), fc[2].bias, self.bridge_hsz, ln_in=_ln_pair(fc[0]), relu=True,
-                           ln_out=_ln_pair(fc[4]), l2norm_in=True)  # F.normalize of model/stage.py:256 fused in
+        img, cs, cb = packed_ln(fc[2], fc[0], 32)
+        h = ops.linear_fwd(x, img, None, self.bridge_hsz, ln_in=(cs, cb), relu=True, ln_out=_ln_pair(fc[4]),
+                           l2norm_in=True)  # F.normalize of model/stage.py:256 fused in
         return ops.linear_fwd(h, packed(emb[1].weight, 64), emb[1].bias, self.hsz, relu=True, ln_out=_ln_pair(emb[3]))
 
     @classmethod
@@ -262,8 +266,9 @@ class STAGE(nn.Module):
         num_img = ctx_mask.shape[2]
         qa_rep = qa_embed.expand(-1, -1, num_img, -1, -1)
         c2q = self.c2q_down_projection
-        mixed = ops.linear_fwd(torch.cat([qa_rep, u_a, qa_rep * u_a], dim=-1), packed(c2q[2].weight, 64), c2q[2].bias,
-                               self.hsz, ln_in=_ln_pair(c2q[0]), relu=True)
+        img, cs, cb = packed_ln(c2q[2], c2q[0], 64)
+        mixed = ops.linear_fwd(torch.cat([qa_rep, u_a, qa_rep * u_a], dim=-1), img, None, self.hsz, ln_in=(cs, cb),
+                               relu=True)
         return mixed, (s_mask.sum(-1) != 0).float(), raw_s, s_norm
 
     def get_ts_loss(self, temporal_scores, ts_labels, answer_indices):

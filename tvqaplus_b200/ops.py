@@ -50,16 +50,37 @@ def pack_weight(w: torch.Tensor, kc: Optional[int] = None) -> torch.Tensor:
     return out
 
 
-def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, n: int, *, kc: Optional[int] = None,
+def pack_weight_ln(w: torch.Tensor, bias: torch.Tensor, ln_g: torch.Tensor, ln_b: torch.Tensor, kc: Optional[int] = None):
+    """Weight of a Linear that follows a LayerNorm: the image of W*gamma plus the two epilogue vectors cs / cb
+    (stage_pack_weight_ln).  Returns (image, cs, cb)."""
+    w, bias, ln_g, ln_b = _f32(w.detach()), _f32(bias.detach()), _f32(ln_g.detach()), _f32(ln_b.detach())
+    n, k = w.shape
+    kc = kc or kc_for(n)
+    nbytes = lib().stage_packed_weight_bytes(n, k, kc)
+    if nbytes == 0:
+        raise RuntimeError("tvqaplus_b200: unsupported weight shape %s" % (tuple(w.shape),))
+    img = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    cs = torch.empty(n, dtype=torch.float32, device=w.device)
+    cb = torch.empty(n, dtype=torch.float32, device=w.device)
+    check(lib().stage_pack_weight_ln(ptr(w), n, k, kc, ptr(ln_g), ptr(ln_b), ptr(bias), ptr(img), ptr(cs), ptr(cb),
+                                     current_stream()), "stage_pack_weight_ln")
+    _count(2)
+    return img, cs, cb
+
+
+def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n: int, *, kc: Optional[int] = None,
                ln_in=None, ln_out=None, l2norm_in: bool = False, relu: bool = False) -> torch.Tensor:
-    """y = LN_out(relu?(LN_in(l2norm?(x)) W^T + b)) over the last axis of x (stage_linear_fwd)."""
+    """y = LN_out(relu?(LN_in(l2norm?(x)) W^T + b)) over the last axis of x (stage_linear_fwd).
+
+    ``ln_in`` is the (cs, cb) pair ``pack_weight_ln`` returned together with ``w_packed`` (the LayerNorm is folded into
+    the weight); ``ln_out`` is a plain (gamma, beta) pair."""
     x = _f32(x)
     k = x.shape[-1]
     m = x.numel() // k
     y = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
     a = _lib.LinearArgs(m=m, k=k, n=n, kc=kc or kc_for(n), l2norm_in=int(l2norm_in), relu=int(relu),
-                        x=ptr(x), w_packed=ptr(w_packed), bias=ptr(_f32(bias)),
-                        ln_in_g=ptr(_f32(ln_in[0])) if ln_in else None, ln_in_b=ptr(_f32(ln_in[1])) if ln_in else None,
+                        x=ptr(x), w_packed=ptr(w_packed), bias=ptr(_f32(bias)) if bias is not None else None,
+                        ln_in_cs=ptr(_f32(ln_in[0])) if ln_in else None, ln_in_cb=ptr(_f32(ln_in[1])) if ln_in else None,
                         ln_out_g=ptr(_f32(ln_out[0])) if ln_out else None,
                         ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y))
     check(lib().stage_linear_fwd(C.byref(a), current_stream()), "stage_linear_fwd")
