@@ -73,6 +73,7 @@ typedef struct {
   const float* ln_out_g; /* [n] or NULL */
   const float* ln_out_b;
   float* y;              /* [m,n] */
+  long long* timeline;   /* optional debug: [32][8] SM clock stamps of CTA 0 (tools/linear_timeline.py), else NULL */
 } StageLinearArgs;
 int stage_linear_fwd(const StageLinearArgs* a, void* stream);
 

@@ -20,7 +20,7 @@ _f = C.c_void_p  # device pointers travel as integers
 class LinearArgs(C.Structure):
     _fields_ = [("m", C.c_int64), ("k", C.c_int), ("n", C.c_int), ("kc", C.c_int), ("l2norm_in", C.c_int),
                 ("relu", C.c_int), ("x", _f), ("w_packed", _f), ("bias", _f), ("ln_in_cs", _f), ("ln_in_cb", _f),
-                ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f)]
+                ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f), ("timeline", _f)]
 
 
 class EncoderArgs(C.Structure):

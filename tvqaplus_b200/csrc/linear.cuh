@@ -25,6 +25,12 @@
 
 namespace stg {
 
+#define LIN_STAMP(tile_idx, idx)                                                           \
+  do {                                                                                     \
+    if (p.timeline != nullptr && blockIdx.x == 0 && (tile_idx) < 32)                        \
+      p.timeline[(tile_idx) * 8 + (idx)] = clock64();                                       \
+  } while (0)
+
 template <int NPAD, int KC, int STAGES>
 struct LinearCfg {
   static constexpr int K8 = KC / 8;
@@ -63,6 +69,7 @@ struct LinearDev {
   long long m;
   int k, n, n_chunks;
   int l2norm_in, relu;
+  long long* timeline;    // optional debug: [32 tiles][8] SM clock stamps of block 0 (tools/linear_timeline.py)
   int out_blocked;        // 1: y is written as [m / rows_per_block][n / 4][rows_per_block] float4 (see cqa.cuh, Za)
   int rows_per_block;
 };
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
       const uint32_t b = tile_it % Cfg::ACC_BUFS, use = tile_it / Cfg::ACC_BUFS;
       mbar_wait(&acc_full[b], use & 1u, 11);
       tc_fence_after();
+      if (tid == 0) LIN_STAMP(tile_it, 4);
       const int r = warp * 32 + lane;
       const long long row0 = tile * 128 + warp * 32;  // first global row of this warp
       const uint32_t trow = tbase + b * Cfg::ACC_STRIDE + ((warp * 32u) << 16);
@@ -138,90 +146,145 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
           gm = -rstd * d * inv;
         }
       }
-      float mean = 0.f, rstd = 1.f;
-      if (ln) {  // exact two-pass statistics of the activated row
-        float s = 0.f;
-        for (int c0 = 0; c0 < NPAD; c0 += 32) {
-          float v[32];
-          tmem_ld16(trow + c0, v);
-          if (c0 + 16 < NPAD) tmem_ld16(trow + c0 + 16, v + 16);
-          tmem_wait_ld();
+      // activated value of column c:  t = act(ga * acc + gm * cs[c] + cb[c]); 32 columns per TMEM round trip, the next
+      // block's tcgen05.ld is always in flight while the current one is processed
+      // (the block loops below are deliberately NOT unrolled: fully unrolled they are ~250 KB of code that is executed once
+      //  per tile and streams through the instruction cache)
+      constexpr int NBLK = (NPAD + 31) / 32;
+      auto load_blk = [&](int blk, float (&v)[32]) {
+        tmem_ld16(trow + blk * 32, v);
+        if (blk * 32 + 16 < NPAD) tmem_ld16(trow + blk * 32 + 16, v + 16);
+      };
+      auto activate = [&](int blk, float (&v)[32]) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c < p.n) {
-              float t = fmaf(ga, v[j], fmaf(gm, vec[c], vec[NPAD + c]));
-              if (p.relu) t = fmaxf(t, 0.f);
-              s += t;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int c = blk * 32 + j4 * 4;
+          if (c < NPAD) {
+            const float4 cs = *reinterpret_cast<const float4*>(vec + c);
+            const float4 cb = *reinterpret_cast<const float4*>(vec + NPAD + c);
+            v[j4 * 4 + 0] = fmaf(ga, v[j4 * 4 + 0], fmaf(gm, cs.x, cb.x));
+            v[j4 * 4 + 1] = fmaf(ga, v[j4 * 4 + 1], fmaf(gm, cs.y, cb.y));
+            v[j4 * 4 + 2] = fmaf(ga, v[j4 * 4 + 2], fmaf(gm, cs.z, cb.z));
+            v[j4 * 4 + 3] = fmaf(ga, v[j4 * 4 + 3], fmaf(gm, cs.w, cb.w));
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = fmaxf(v[j4 * 4 + e], 0.f);
             }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = 0.f;
           }
         }
-        mean = s * inv_n;
-        float q = 0.f;
-        for (int c0 = 0; c0 < NPAD; c0 += 32) {
-          float v[32];
-          tmem_ld16(trow + c0, v);
-          if (c0 + 16 < NPAD) tmem_ld16(trow + c0 + 16, v + 16);
-          tmem_wait_ld();
+      };
+      float mean = 0.f, rstd = 1.f;
+      if (ln) {
+        // LN_out statistics in one pass, shifted by the row's first activated value (rows reaching here are O(1) ReLU /
+        // linear outputs; the shift keeps E[(t-t0)^2] - mean^2 exact for rows with a common offset)
+        float s = 0.f, q = 0.f, t0 = 0.f;
+        float va[32], vb[32];
+        auto accumulate = [&](int blk, float (&v)[32]) {
+          activate(blk, v);
+          if (blk == 0) t0 = v[0];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c < p.n) {
-              float t = fmaf(ga, v[j], fmaf(gm, vec[c], vec[NPAD + c]));
-              if (p.relu) t = fmaxf(t, 0.f);
-              t -= mean;
+            if (blk * 32 + j < p.n) {
+              const float t = v[j] - t0;
+              s += t;
               q = fmaf(t, t, q);
             }
           }
-        }
-        rstd = 1.f / sqrtf(q * inv_n + 1e-5f);
-      }
-      for (int c0 = 0; c0 < NPAD; c0 += 32) {
-        float v[32];
-        tmem_ld16(trow + c0, v);
-        if (c0 + 16 < NPAD) tmem_ld16(trow + c0 + 16, v + 16);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = c0 + j;
-          float t = 0.f;
-          if (c < NPAD) {
-            t = fmaf(ga, v[j], fmaf(gm, vec[c], vec[NPAD + c]));
-            if (p.relu) t = fmaxf(t, 0.f);
-            if (ln) t = fmaf((t - mean) * rstd, vec[2 * NPAD + c], vec[3 * NPAD + c]);
+        };
+        load_blk(0, va);
+#pragma unroll 1
+        for (int blk = 0; blk < NBLK; blk += 2) {
+          tmem_wait_ld();
+          if (blk + 1 < NBLK) load_blk(blk + 1, vb);
+          accumulate(blk, va);
+          if (blk + 1 < NBLK) {
+            tmem_wait_ld();
+            if (blk + 2 < NBLK) load_blk(blk + 2, va);
+            accumulate(blk + 1, vb);
           }
-          v[j] = t;
         }
-        // 32 rows x 32 columns through the warp's transpose buffer: afterwards lane = (row % 4 group, 4-column slot)
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(tr + lane * Cfg::TS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
+        const float d = s * inv_n;
+        mean = t0 + d;
+        rstd = 1.f / sqrtf(fmaxf(q * inv_n - d * d, 0.f) + 1e-5f);
+      }
+      {
+        // after the 32x32 transpose lane = (row % 4 group, 4-column slot); its 8 rows' output offsets are fixed per tile
         const int c4 = lane & 7, rsub = lane >> 3;
-        const int col = c0 + c4 * 4;
+        const bool vec_ok = p.out_blocked || (p.n & 3) == 0;
+        long long off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub;
-          const long long gr = row0 + rr;
-          const float4 o = *reinterpret_cast<const float4*>(tr + rr * Cfg::TS + c4 * 4);
-          if (gr < p.m && col < p.n) {
-            if (p.out_blocked) {
-              const long long blk = gr / p.rows_per_block;
-              const int rl = static_cast<int>(gr - blk * p.rows_per_block);
-              *reinterpret_cast<float4*>(p.y + ((blk * (p.n >> 2) + (col >> 2)) * p.rows_per_block + rl) * 4) = o;
-            } else if ((p.n & 3) == 0) {
-              *reinterpret_cast<float4*>(p.y + gr * p.n + col) = o;
-            } else {
-              const float ov[4] = {o.x, o.y, o.z, o.w};
-              for (int e = 0; e < 4; ++e)
-                if (col + e < p.n) p.y[gr * p.n + col + e] = ov[e];
+          const long long gr = row0 + i * 4 + rsub;
+          if (gr >= p.m) {
+            off[i] = -1;
+          } else if (p.out_blocked) {
+            const long long bk = gr / p.rows_per_block;
+            off[i] = (bk * (p.n >> 2) * p.rows_per_block + (gr - bk * p.rows_per_block)) * 4;
+          } else {
+            off[i] = gr * p.n;
+          }
+        }
+        const int cmul = p.out_blocked ? p.rows_per_block * 4 : 4;
+        const float nm = -mean * rstd;
+        float va[32], vb[32];
+        auto emit = [&](int blk, float (&v)[32]) {
+          activate(blk, v);
+          if (ln) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int c = blk * 32 + j4 * 4;
+              if (c < NPAD) {
+                const float4 g = *reinterpret_cast<const float4*>(vec + 2 * NPAD + c);
+                const float4 bb = *reinterpret_cast<const float4*>(vec + 3 * NPAD + c);
+                v[j4 * 4 + 0] = fmaf(fmaf(v[j4 * 4 + 0], rstd, nm), g.x, bb.x);
+                v[j4 * 4 + 1] = fmaf(fmaf(v[j4 * 4 + 1], rstd, nm), g.y, bb.y);
+                v[j4 * 4 + 2] = fmaf(fmaf(v[j4 * 4 + 2], rstd, nm), g.z, bb.z);
+                v[j4 * 4 + 3] = fmaf(fmaf(v[j4 * 4 + 3], rstd, nm), g.w, bb.w);
+              }
             }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tr + lane * Cfg::TS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int col = blk * 32 + c4 * 4;
+          if (col < p.n) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 o = *reinterpret_cast<const float4*>(tr + (i * 4 + rsub) * Cfg::TS + c4 * 4);
+              if (off[i] >= 0) {
+                if (vec_ok) {
+                  *reinterpret_cast<float4*>(p.y + off[i] + static_cast<long long>(col >> 2) * cmul) = o;
+                } else {
+                  const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll 1
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.n) p.y[off[i] + col + e] = ov[e];
+                }
+              }
+            }
+          }
+        };
+        load_blk(0, va);
+#pragma unroll 1
+        for (int blk = 0; blk < NBLK; blk += 2) {
+          tmem_wait_ld();
+          if (blk + 1 < NBLK) load_blk(blk + 1, vb);
+          emit(blk, va);
+          if (blk + 1 < NBLK) {
+            tmem_wait_ld();
+            if (blk + 2 < NBLK) load_blk(blk + 2, va);
+            emit(blk + 1, vb);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
+      if (tid == 0) LIN_STAMP(tile_it, 5);
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ producers
@@ -268,6 +331,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_STAGE;
           const int kleft = p.k - (c * KC + k8 * 8);  // valid columns of my 8-column slot in this chunk
+          if (ptid == 0 && c == 0) LIN_STAMP(tl, 0);
           HL8 hl[NI];
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
@@ -324,6 +388,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
           if (ptid != 0) mbar_arrive(&full_bar[s]);
           ++it;
           if (++c == p.n_chunks) {
+            if (ptid == 0) LIN_STAMP(tl, 1);
             c = 0;
             ++tl;
           }
@@ -339,6 +404,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
       const uint32_t b = tile_it % Cfg::ACC_BUFS, ause = tile_it / Cfg::ACC_BUFS;
       mbar_wait(&acc_empty[b], (ause & 1u) ^ 1u, 12);
       tc_fence_after();
+      LIN_STAMP(tile_it, 2);
       const uint32_t dcol = tbase + b * Cfg::ACC_STRIDE;
       for (int c = 0; c < p.n_chunks; ++c, ++it) {
         const uint32_t s = it % STAGES, use = it / STAGES;
@@ -365,6 +431,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
         umma_commit(&empty_bar[s]);
       }
       umma_commit(&acc_full[b]);
+      LIN_STAMP(tile_it, 3);
     }
   }
 

@@ -69,7 +69,8 @@ def pack_weight_ln(w: torch.Tensor, bias: torch.Tensor, ln_g: torch.Tensor, ln_b
 
 
 def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n: int, *, kc: Optional[int] = None,
-               ln_in=None, ln_out=None, l2norm_in: bool = False, relu: bool = False) -> torch.Tensor:
+               ln_in=None, ln_out=None, l2norm_in: bool = False, relu: bool = False,
+               timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = LN_out(relu?(LN_in(l2norm?(x)) W^T + b)) over the last axis of x (stage_linear_fwd).
 
     ``ln_in`` is the (cs, cb) pair ``pack_weight_ln`` returned together with ``w_packed`` (the LayerNorm is folded into
@@ -82,7 +83,7 @@ def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Ten
                         x=ptr(x), w_packed=ptr(w_packed), bias=ptr(_f32(bias)) if bias is not None else None,
                         ln_in_cs=ptr(_f32(ln_in[0])) if ln_in else None, ln_in_cb=ptr(_f32(ln_in[1])) if ln_in else None,
                         ln_out_g=ptr(_f32(ln_out[0])) if ln_out else None,
-                        ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y))
+                        ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y), timeline=ptr(timeline))
     check(lib().stage_linear_fwd(C.byref(a), current_stream()), "stage_linear_fwd")
     _count()
     return y
