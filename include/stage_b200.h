@@ -107,6 +107,7 @@ typedef struct {
   const float* final_ln_g;
   const float* final_ln_b;
   float* y;
+  long long* timeline; /* optional debug: [32][16] SM clock stamps of CTA 0 (tools/encoder_timeline.py), else NULL */
 } StageEncoderArgs;
 int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream);
 

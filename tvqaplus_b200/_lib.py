@@ -28,7 +28,7 @@ class EncoderArgs(C.Structure):
                 ("out_mode", C.c_int), ("flags", C.c_int), ("x", _f), ("mask", _f), ("pe", _f),
                 ("ln_g", _f * MAX_CONV), ("ln_b", _f * MAX_CONV), ("dw_w", _f * MAX_CONV), ("dw_b", _f * MAX_CONV),
                 ("pw_packed", _f * MAX_CONV), ("pw_b", _f * MAX_CONV),
-                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f)]
+                ("final_ln_g", _f), ("final_ln_b", _f), ("y", _f), ("timeline", _f)]
 
 
 class MhaArgs(C.Structure):

@@ -55,9 +55,15 @@ struct EncDev {
   float* y;
   long long n_seq;
   int L, n_conv, out_mode, flags;
+  long long* timeline;  // optional debug: [32 tiles][16] SM clock stamps of thread 0 of CTA 0 (tools/encoder_timeline.py)
 };
 
 #define STG_NEG (-1e10f)
+#define ENC_STAMP(idx)                                                                   \
+  do {                                                                                   \
+    if (p.timeline != nullptr && blockIdx.x == 0 && tid == 0 && tl_tile < 32)             \
+      p.timeline[tl_tile * 16 + (idx)] = clock64();                                       \
+  } while (0)
 
 template <int KS>
 __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
@@ -96,6 +102,7 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
   const uint32_t tbase = tmem_slot;
   const uint32_t idesc = make_idesc_f16(128);
   uint32_t w_count = 0, mma_count = 0, x_count = 0;
+  int tl_tile = 0;
 
   auto rows_of = [&](long long tile) -> int {
     const long long seq0 = tile * G;
@@ -110,29 +117,47 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
     bulk_g2s(sW, p.pw[0], EncCfg::W_BYTES, &w_bar);
   }
 
+  // position-encoding rows (the same for every tile) and masks of my 8 rows of a tile: plain L2 loads (shared memory
+  // takes the whole L1 carve-out), requested one phase ahead so that their latency never sits in phase 0
+  float4 pe_r[RW];
+  float m_r[RW];
+  auto prefetch_rows = [&](long long tile) {
+    const int nv = rows_of(tile);
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+      const int r = warp * RW + rr;
+      pe_r[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+      m_r[rr] = 0.f;
+      if (r < nv) {
+        const int pos = r - (r / L) * L;
+        if (!(p.flags & STAGE_ENC_NO_PE)) pe_r[rr] = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
+        if (p.mask != nullptr) m_r[rr] = __ldg(p.mask + tile * G * L + r);
+      }
+    }
+  };
+  prefetch_rows(blockIdx.x);
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long seq0 = tile * G;
     const int n_valid = rows_of(tile);
     const int n_here = n_valid / L;
 
     // ---- phase 0: raw rows (smem, prefetched) + pe -> X, first LayerNorm statistics.  warp per row, lane = 4 channels
+    //      (the position rows and masks of this tile were requested from L2 under the previous tile's tail)
+    ENC_STAMP(0);
     mbar_wait(&x_bar, x_count & 1u, 22);
     ++x_count;
+    ENC_STAMP(1);
     {
       const float4* raw = reinterpret_cast<const float4*>(sA);
 #pragma unroll
       for (int rr = 0; rr < RW; ++rr) {
         const int r = warp * RW + rr;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float m = 0.f;
         if (r < n_valid) {
           v = raw[r * 32 + lane];
-          const int pos = r - row_sid[r] * L;
-          if (!(p.flags & STAGE_ENC_NO_PE)) {
-            const float4 e = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
-            v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
-          }
-          if (p.mask != nullptr) m = __ldg(p.mask + seq0 * L + r);
+          const float4 e = pe_r[rr];
+          v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
         }
         *reinterpret_cast<float4*>(X + r * EncCfg::XS + lane * 4) = v;
         const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
@@ -141,11 +166,12 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
         if (lane == 0) {
           const float rs = 1.f / sqrtf(var + 1e-5f);
           row_stat[r] = make_float2(mean * rs, rs);
-          row_mask[r] = m;
+          row_mask[r] = m_r[rr];
         }
       }
     }
     __syncthreads();
+    ENC_STAMP(2);
 
     for (int ci = 0; ci < p.n_conv; ++ci) {
       // ---- conv: LayerNorm applied once per row into a register window, k-tap FIR, split -> A image
@@ -197,8 +223,10 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
           *reinterpret_cast<uint2*>(dst + EncCfg::A_PART) = lo;
         }
       }
+      ENC_STAMP(3 + ci * 5);
       fence_async_smem();
       __syncthreads();
+      ENC_STAMP(4 + ci * 5);
 
       // ---- pointwise GEMM  D[128 x 128] = A[128 x 128] . W^T   (8 K-steps x 3 MMAs)
       if (tid == 0) {
@@ -220,6 +248,7 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
       mbar_wait(&mma_bar, mma_count & 1u, 21);
       ++mma_count;
       tc_fence_after();
+      ENC_STAMP(5 + ci * 5);
       if (tid == 0) {
         // weights of the next conv (or conv 0 of this CTA's next tile) stream in under the epilogue; after the last conv
         // the A region is free as well and receives the next tile's raw rows
@@ -263,6 +292,7 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
         xq[0][qd][r] = s1;
         xq[1][qd][r] = s2;
       }
+      ENC_STAMP(6 + ci * 5);
       tc_fence_before();
       __syncthreads();
       if (tid < 128) {
@@ -272,7 +302,9 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
         row_stat[tid] = make_float2(mean * rs, rs);
       }
       __syncthreads();
+      ENC_STAMP(7 + ci * 5);
     }
+    prefetch_rows(tile + gridDim.x);  // (a tile past the end has no rows: every load is predicated off)
 
     // ---- closing LayerNorm (+ store, or mask_logits written back to X for the max-pool).  warp per row
     {
@@ -312,7 +344,10 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
         }
       }
     }
+    ENC_STAMP(14);
     __syncthreads();
+    ENC_STAMP(15);
+    ++tl_tile;
   }
 
   tc_fence_before();

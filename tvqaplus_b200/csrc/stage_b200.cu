@@ -139,7 +139,7 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
   EncDev d;
   d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;
-  d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode; d.flags = a->flags;
+  d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode; d.flags = a->flags; d.timeline = a->timeline;
   for (int i = 0; i < STAGE_MAX_CONV; ++i) {
     const bool on = i < a->n_conv;
     if (on) STG_REQUIRE((a->ln_g[i] == nullptr) == (a->ln_b[i] == nullptr) && a->dw_w[i] && a->dw_b[i] && a->pw_packed[i] && a->pw_b[i], STAGE_E_BADARG,

@@ -97,7 +97,7 @@ def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
 
 
 def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optional[torch.Tensor], convs: Sequence[dict],
-                      final_ln, ksize: int, *, out_mode: int = 0,
+                      final_ln, ksize: int, *, out_mode: int = 0, timeline: Optional[torch.Tensor] = None,
                       conv_only: bool = False, pre_ln_only: bool = False, relu: bool = True,
                       skip_final_ln: bool = False) -> torch.Tensor:
     """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
@@ -129,7 +129,8 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
                          flags=flags, x=ptr(x), mask=ptr(mask_c), pe=ptr(pe_c),
                          ln_g=_arr(cols["ln_g"]), ln_b=_arr(cols["ln_b"]), dw_w=_arr(cols["dw_w"]),
                          dw_b=_arr(cols["dw_b"]), pw_packed=_arr([ptr(c["pw_packed"]) for c in convs]),
-                         pw_b=_arr(cols["pw_b"]), final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y))
+                         pw_b=_arr(cols["pw_b"]), final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y),
+                         timeline=ptr(timeline))
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
     _count()
     return y
