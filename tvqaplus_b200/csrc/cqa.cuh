@@ -1,4 +1,5 @@
-// Fused QA<->context attention + fusion MLPs, one persistent CTA per (example, frame), looping over the 5 answers.
+// Fused QA<->context attention + fusion MLPs, one persistent CTA per (example, frame), looping over the 128-row tiles
+// into which the 5 x Lq answer rows of the example are packed (4 tiles instead of 5 at Lq = 100).
 //
 //   S   = (a . ctx^T) * inv|a| * inv|ctx|  - 1e10*(1 - mask)      StructuredAttention.similarity   (cqa.py:95-100)
 //   P   = softmax(scale * S) * mask ;  U = P . ctx                 StructuredAttention.forward      (cqa.py:59-61,81)
@@ -67,9 +68,10 @@ struct CqaCfg {
 
 struct CqaDev {
   int n, t, lq, ls, r, ls_pad, r_pad;
+  int n_pt;                   // 128-row tiles per (example, frame): the 5*lq answer rows of an example are packed
   float scale;
   const float* a_embed;       // [n,5,lq,128] fp32 (for the a*U products)
-  const uint8_t* a_blob;      // [n*5] ABLOB_BYTES
+  const uint8_t* a_blob;      // [n*n_pt] ABLOB_BYTES: packed answer rows [128*j, 128*j + 128) of example n
   const uint8_t* ctx_blob;    // [n*t] CTX_BYTES
   const float* za;            // [n*5, lq, 128]  a (Wc*gamma)[:, :128]^T
   const uint8_t* c2q_w;       // packed (Wc*gamma)[:, 128:384], kc=32: 8 chunks
@@ -87,7 +89,7 @@ struct CqaDev {
 // prep: fp32 rows -> split-fp16 operand images + per-row data (one warp per row, lane = 4 channels)
 // ------------------------------------------------------------------------------------------------------------------
 struct CqaPrepDev {
-  int n, t, lq, ls, r, ls_pad, r_pad;
+  int n, t, lq, ls, r, ls_pad, r_pad, n_pt;
   const float* a_embed; const float* a_mask;
   const float* sub_embed; const float* sub_mask;
   const float* vid_embed; const float* vid_mask;
@@ -97,7 +99,7 @@ struct CqaPrepDev {
 __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_a = static_cast<long long>(p.n) * 5 * 128;
+  const long long n_a = static_cast<long long>(p.n) * p.n_pt * 128;
   const long long n_s = static_cast<long long>(p.n) * p.t * p.ls_pad;
   const long long n_v = static_cast<long long>(p.n) * p.t * p.r_pad;
   if (warp >= n_a + n_s + n_v) return;
@@ -108,13 +110,18 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   float *inv_out, *mask_out, *sum_out = nullptr, *sq_out = nullptr;
   int j;
   if (warp < n_a) {
-    const long long na = warp / 128;
+    const long long nj = warp / 128;  // (example, packed tile)
     j = static_cast<int>(warp % 128);
-    uint8_t* blob = p.a_blob + na * CqaCfg::ABLOB_BYTES;
+    const long long ex = nj / p.n_pt;
+    const int prow = static_cast<int>(nj - ex * p.n_pt) * 128 + j;  // packed row of the example: answer = prow / lq
+    uint8_t* blob = p.a_blob + nj * CqaCfg::ABLOB_BYTES;
     img = blob; lbo = CqaCfg::LBO_A; part = CqaCfg::AQ_PART;
     float* rd = reinterpret_cast<float*>(blob + CqaCfg::ABLOB_ROWDATA);
     inv_out = rd; mask_out = rd + 128; sum_out = rd + 256; sq_out = rd + 384;
-    if (j < p.lq) { src = p.a_embed + (na * p.lq + j) * 128; m = __ldg(p.a_mask + na * p.lq + j); }
+    if (prow < 5 * p.lq) {  // a_embed / a_mask are [n,5,lq,..] = [n, 5*lq, ..]
+      src = p.a_embed + (ex * 5 * p.lq + prow) * 128;
+      m = __ldg(p.a_mask + ex * 5 * p.lq + prow);
+    }
   } else if (warp < n_a + n_s) {
     const long long w = warp - n_a, f = w / p.ls_pad;
     j = static_cast<int>(w % p.ls_pad);
@@ -229,7 +236,6 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     const int row = (warp & 3) * 32 + lane, qd = warp >> 2;
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
     const uint32_t coff = lane_off + qd * 32;
-    const bool live = row < p.lq;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
     [[maybe_unused]] int tl_tile = (tid == 0) ? 0 : 64;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
@@ -258,12 +264,17 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
-      for (int a_i = 0; a_i < 5; ++a_i) {
-        const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
-        const size_t tile = na * p.t + t_i;
-        const size_t orow = (tile * p.lq + row) * 128 + qd * 32;  // my 32 columns of this tile's output row
+      for (int a_i = 0; a_i < p.n_pt; ++a_i) {
+        // my row of this tile: packed row prow of example n_i = row (prow % lq) of answer (prow / lq)
+        const int prow = a_i * 128 + row;
+        const bool live = prow < 5 * p.lq;
+        const int ans = live ? prow / p.lq : 0;
+        const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
+        const uint32_t arow = static_cast<uint32_t>(n_i) * 5u * p.lq + (live ? prow : 0);  // row of a_embed / za
+        const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);  // output row
+#define orow (static_cast<size_t>(srow) * 128 + qd * 32) /* my 32 columns of the output row */
         CQA_STAMP(0, 0);
-        const float* rd = reinterpret_cast<const float*>(p.a_blob + na * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
+        const float* rd = reinterpret_cast<const float*>(p.a_blob + nj * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row);
         if (a_i == 0) {
           mbar_wait(&ctx_full, frame_cnt & 1u, 30);  // ctx blob (images + inv norms + masks) has landed
@@ -284,10 +295,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(0, 2);
         {
-          float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + (tile * p.lq + row) * p.ls : nullptr;
-          float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + (tile * p.lq + row) * p.r : nullptr;
-          float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + (tile * p.lq + row) * p.ls : nullptr;
-          float* nrm_v = (p.vid_norm_s && live) ? p.vid_norm_s + (tile * p.lq + row) * p.r : nullptr;
+          float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + static_cast<size_t>(srow) * p.ls : nullptr;
+          float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + static_cast<size_t>(srow) * p.r : nullptr;
+          float* nrm_s = (p.sub_norm_s && live) ? p.sub_norm_s + static_cast<size_t>(srow) * p.ls : nullptr;
+          float* nrm_v = (p.vid_norm_s && live) ? p.vid_norm_s + static_cast<size_t>(srow) * p.r : nullptr;
 #define CQA_SLOT(k)                                                                   \
   const bool vid = (qd == 3) || (qd == 2 && (k) == 1);                                 \
   const int ch = qd < 2 ? 3 * qd + (k) : (qd == 2 ? ((k) == 0 ? 6 : 0) : (k) + 1);      \
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
         float a_reg[32];
         {
-          const float4* src = reinterpret_cast<const float4*>(p.a_embed + (na * p.lq + row) * 128 + qd * 32);
+          const float4* src = reinterpret_cast<const float4*>(p.a_embed + static_cast<size_t>(arow) * 128 + qd * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      c2q MMAs accumulate on top of it
         float za[32];
         {
-          const float4* zsrc = reinterpret_cast<const float4*>(p.za + (na * p.lq + row) * 128 + qd * 32);
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za + static_cast<size_t>(arow) * 128 + qd * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -425,7 +436,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             CQA_SLOT(k)
             float* nrm = vid ? p.vid_norm_s : p.sub_norm_s;
             if (on && live && nrm != nullptr) {
-              nrm += (tile * p.lq + row) * n_real;
+              nrm += static_cast<size_t>(srow) * n_real;
               for (int j = 0; j < 16; ++j)
                 if (ch * 16 + j < n_real) nrm[ch * 16 + j] *= (vid ? iv : is);
             }
@@ -603,13 +614,14 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             }
           }
           // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
-          if (live && qd == 0) p.statement_mask[tile * p.lq + row] = (ma * any_v != 0.f) ? 1.f : 0.f;
+          if (live && qd == 0) p.statement_mask[srow] = (ma * any_v != 0.f) ? 1.f : 0.f;
         }
         tc_fence_before();
         // no barrier here: the next tile first writes xq[0..1] (softmax sums), which every thread finished reading before the
         // barrier above; xq[2..3] are rewritten only after the next tile's c2q production, which needs all 512 threads
         CQA_STAMP(0, 11);
         if constexpr (TIMELINE) ++tl_tile;
+#undef orow
       }
     }
 #undef CQA_SEG_PUT
@@ -622,7 +634,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
     const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
-      for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
+      for (int a_i = 0; a_i < p.n_pt; ++a_i, ++tile_cnt) {
         CQA_STAMP(1, 0);
         if (a_i == 0) mbar_wait(&ctx_full, frame_cnt & 1u, 40);
         mbar_wait(&aq_full, tile_cnt & 1u, 41);
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         }
         umma_commit(&mma_done);  // D2
         umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
-        if (a_i == 4) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
+        if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         CQA_STAMP(1, 4);
         // ---- GEMMs: 14 K=64 A stages (4 c2q sub, 4 c2q vid, 6 concat), each against two K=32 weight slots
         for (int hs = 0; hs < CqaCfg::HALF_SEGS; ++hs) {
@@ -714,11 +726,11 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
       if (frame_cnt > 0) mbar_wait(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
       mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
       bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
-      for (int a_i = 0; a_i < 5; ++a_i, ++tile_cnt) {
-        const size_t na = static_cast<size_t>(n_i) * 5 + a_i;
+      for (int a_i = 0; a_i < p.n_pt; ++a_i, ++tile_cnt) {
+        const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
         if (tile_cnt > 0) mbar_wait(&aq_free, (tile_cnt - 1u) & 1u, 51);  // previous tile's concat MMAs have drained the A stages
         mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
-        bulk_g2s(sAQ, p.a_blob + na * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
+        bulk_g2s(sAQ, p.a_blob + nj * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
         mbar_wait(&b_free, tile_cnt & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
         for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
           const uint32_t i = q_cnt + q, slot = i % CqaCfg::W_SLOTS, use = i / CqaCfg::W_SLOTS;

@@ -224,7 +224,8 @@ static size_t align128(size_t x) { return (x + 127) & ~static_cast<size_t>(127);
 
 size_t stage_cqa_workspace_bytes(int n, int t, int lq) {
   if (n <= 0 || t <= 0 || lq <= 0) return 0;
-  return align128(static_cast<size_t>(n) * 5 * CqaCfg::ABLOB_BYTES) + align128(static_cast<size_t>(n) * t * CqaCfg::CTX_BYTES) +
+  const size_t n_pt = (5 * static_cast<size_t>(lq) + 127) / 128;
+  return align128(static_cast<size_t>(n) * n_pt * CqaCfg::ABLOB_BYTES) + align128(static_cast<size_t>(n) * t * CqaCfg::CTX_BYTES) +
          align128(static_cast<size_t>(n) * 5 * lq * 128 * sizeof(float));
 }
 
@@ -244,16 +245,17 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   const float* vec = reinterpret_cast<const float*>(wb + WB_VEC);
   uint8_t* ws = static_cast<uint8_t*>(a->workspace);
   uint8_t* a_blob = ws;
-  uint8_t* ctx_blob = a_blob + align128(static_cast<size_t>(a->n) * 5 * CqaCfg::ABLOB_BYTES);
+  const int n_pt = (5 * a->lq + 127) / 128;
+  uint8_t* ctx_blob = a_blob + align128(static_cast<size_t>(a->n) * n_pt * CqaCfg::ABLOB_BYTES);
   float* za = reinterpret_cast<float*>(ctx_blob + align128(static_cast<size_t>(a->n) * a->t * CqaCfg::CTX_BYTES));
   const int ls_pad = round_up(a->ls, 16), r_pad = round_up(a->r, 16);
   // 1. operand images
   {
     CqaPrepDev d;
-    d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad;
+    d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.n_pt = n_pt;
     d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
     d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask; d.a_blob = a_blob; d.ctx_blob = ctx_blob;
-    const long long warps = static_cast<long long>(a->n) * 5 * 128 + static_cast<long long>(a->n) * a->t * (ls_pad + r_pad);
+    const long long warps = static_cast<long long>(a->n) * n_pt * 128 + static_cast<long long>(a->n) * a->t * (ls_pad + r_pad);
     cqa_prep_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(d);
     int rc = check_launch("cqa_prep");
     if (rc) return rc;
@@ -269,7 +271,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   }
   // 3. the fused kernel
   CqaDev d;
-  d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.scale = a->scale;
+  d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.n_pt = n_pt; d.scale = a->scale;
   d.a_embed = a->a_embed; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.za = za;
   d.c2q_w = wb + WB_WU; d.c2q_cs = vec; d.c2q_cb = vec + 128; d.cat_w = wb + WB_WF; d.cat_cs = vec + 256; d.cat_cb = vec + 384;
   d.out_g = a->cat_out_ln_g; d.out_b = a->cat_out_ln_b;
