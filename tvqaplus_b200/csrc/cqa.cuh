@@ -70,10 +70,10 @@ struct CqaDev {
   int n, t, lq, ls, r, ls_pad, r_pad;
   int n_pt;                   // 128-row tiles per (example, frame): the 5*lq answer rows of an example are packed
   float scale;
-  const float* a_embed;       // [n,5,lq,128] fp32 (for the a*U products)
+  const float* a_blk;         // fp32 answers, blocked [n][32][5*lq] float4 (for the a*U products; lanes = rows read 512 B runs)
   const uint8_t* a_blob;      // [n*n_pt] ABLOB_BYTES: packed answer rows [128*j, 128*j + 128) of example n
   const uint8_t* ctx_blob;    // [n*t] CTX_BYTES
-  const float* za;            // [n*5, lq, 128]  a (Wc*gamma)[:, :128]^T
+  const float* za;            // a (Wc*gamma)[:, :128]^T in the same blocked layout [n][32][5*lq] float4
   const uint8_t* c2q_w;       // packed (Wc*gamma)[:, 128:384], kc=32: 8 chunks
   const float* c2q_cs; const float* c2q_cb;
   const uint8_t* cat_w;       // packed (Wf*gamma), kc=32: 12 chunks
@@ -94,6 +94,7 @@ struct CqaPrepDev {
   const float* sub_embed; const float* sub_mask;
   const float* vid_embed; const float* vid_mask;
   uint8_t* a_blob; uint8_t* ctx_blob;
+  float* a_blk;  // fp32 copy of a_embed in the blocked layout [example][4-column group (32)][packed row (5*lq)] float4
 };
 
 __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   const long long n_v = static_cast<long long>(p.n) * p.t * p.r_pad;
   if (warp >= n_a + n_s + n_v) return;
   const float* src = nullptr;
+  float4* blk_dst = nullptr;
   float m = 0.f;
   uint8_t* img;
   uint32_t lbo, part;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
     if (prow < 5 * p.lq) {  // a_embed / a_mask are [n,5,lq,..] = [n, 5*lq, ..]
       src = p.a_embed + (ex * 5 * p.lq + prow) * 128;
       m = __ldg(p.a_mask + ex * 5 * p.lq + prow);
+      blk_dst = reinterpret_cast<float4*>(p.a_blk) + (ex * 32 + lane) * (5 * p.lq) + prow;
     }
   } else if (warp < n_a + n_s) {
     const long long w = warp - n_a, f = w / p.ls_pad;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   }
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (src != nullptr) v = __ldg(reinterpret_cast<const float4*>(src) + lane);
+  if (blk_dst != nullptr) *blk_dst = v;
   const float ss = warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
   const float sm = warp_sum((v.x + v.y) + (v.z + v.w));
   uint2 hi, lo;
@@ -270,7 +274,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         const bool live = prow < 5 * p.lq;
         const int ans = live ? prow / p.lq : 0;
         const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
-        const uint32_t arow = static_cast<uint32_t>(n_i) * 5u * p.lq + (live ? prow : 0);  // row of a_embed / za
+        // my first float4 of a_blk / za (blocked [example][4-column group][packed row]): group stride = 5*lq float4
+        const uint32_t arow = (static_cast<uint32_t>(n_i) * 32u + qd * 8u) * (5u * p.lq) + (live ? prow : 0);
         const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);  // output row
 #define orow (static_cast<size_t>(srow) * 128 + qd * 32) /* my 32 columns of the output row */
         CQA_STAMP(0, 0);
@@ -393,10 +398,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
         float a_reg[32];
         {
-          const float4* src = reinterpret_cast<const float4*>(p.a_embed + static_cast<size_t>(arow) * 128 + qd * 32);
+          const float4* src = reinterpret_cast<const float4*>(p.a_blk) + arow;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 v = live ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = live ? __ldg(src + j * (5 * p.lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
             a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
           }
         }
@@ -406,10 +411,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      c2q MMAs accumulate on top of it
         float za[32];
         {
-          const float4* zsrc = reinterpret_cast<const float4*>(p.za + static_cast<size_t>(arow) * 128 + qd * 32);
+          const float4* zsrc = reinterpret_cast<const float4*>(p.za) + arow;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 v = live ? __ldg(zsrc + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = live ? __ldg(zsrc + j * (5 * p.lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
             za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
           }
         }

@@ -226,7 +226,7 @@ size_t stage_cqa_workspace_bytes(int n, int t, int lq) {
   if (n <= 0 || t <= 0 || lq <= 0) return 0;
   const size_t n_pt = (5 * static_cast<size_t>(lq) + 127) / 128;
   return align128(static_cast<size_t>(n) * n_pt * CqaCfg::ABLOB_BYTES) + align128(static_cast<size_t>(n) * t * CqaCfg::CTX_BYTES) +
-         align128(static_cast<size_t>(n) * 5 * lq * 128 * sizeof(float));
+         2 * align128(static_cast<size_t>(n) * 5 * lq * 128 * sizeof(float));  // a.Wa and the blocked fp32 answers
 }
 
 int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
@@ -248,13 +248,14 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   const int n_pt = (5 * a->lq + 127) / 128;
   uint8_t* ctx_blob = a_blob + align128(static_cast<size_t>(a->n) * n_pt * CqaCfg::ABLOB_BYTES);
   float* za = reinterpret_cast<float*>(ctx_blob + align128(static_cast<size_t>(a->n) * a->t * CqaCfg::CTX_BYTES));
+  float* a_blk = za + align128(static_cast<size_t>(a->n) * 5 * a->lq * 128 * sizeof(float)) / sizeof(float);
   const int ls_pad = round_up(a->ls, 16), r_pad = round_up(a->r, 16);
   // 1. operand images
   {
     CqaPrepDev d;
     d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.n_pt = n_pt;
     d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
-    d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask; d.a_blob = a_blob; d.ctx_blob = ctx_blob;
+    d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.a_blk = a_blk;
     const long long warps = static_cast<long long>(a->n) * n_pt * 128 + static_cast<long long>(a->n) * a->t * (ls_pad + r_pad);
     cqa_prep_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(d);
     int rc = check_launch("cqa_prep");
@@ -265,14 +266,14 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
     LinearDev d;
     d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.cs = nullptr; d.cb = nullptr;
     d.ln_out_g = nullptr; d.ln_out_b = nullptr; d.y = za; d.m = static_cast<long long>(a->n) * 5 * a->lq;
-    d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0; d.out_blocked = 0; d.rows_per_block = 1; d.timeline = nullptr;
+    d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0; d.out_blocked = 1; d.rows_per_block = 5 * a->lq; d.timeline = nullptr;
     int rc = launch_linear<128, 64, 3>(d, s);
     if (rc) return rc;
   }
   // 3. the fused kernel
   CqaDev d;
   d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.n_pt = n_pt; d.scale = a->scale;
-  d.a_embed = a->a_embed; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.za = za;
+  d.a_blk = a_blk; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.za = za;
   d.c2q_w = wb + WB_WU; d.c2q_cs = vec; d.c2q_cb = vec + 128; d.cat_w = wb + WB_WF; d.cat_cs = vec + 256; d.cat_cb = vec + 384;
   d.out_g = a->cat_out_ln_g; d.out_b = a->cat_out_ln_b;
   d.statement = a->statement; d.statement_mask = a->statement_mask;
