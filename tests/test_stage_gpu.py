@@ -95,3 +95,56 @@ def test_module_level_drop_ins():
     assert torch.equal(mask_logits(x.to(dev), m.to(dev)).cpu(), O.mask_logits(x, m))
     torch.cuda.synchronize()
     _lib.check_device_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dense", [True, False])
+def test_full_size_shape_against_oracle(dense):
+    """BASELINE configs[1] shapes (T=300, R=20, Lq=Ls=100) for one example against the CPU oracle."""
+    from tvqaplus_b200.model import STAGE
+    opt = O.default_opt()
+    torch.manual_seed(2018)
+    model = STAGE(opt).eval()
+    batch = O.make_synthetic_batch(1, 300, 20, 100, 100, seed=7, dense=dense)
+    want = O.stage_forward({k: v.clone() for k, v in model.state_dict().items()}, opt, batch, keep=True)
+    model, (answer, _, _, t_loss, t_probs) = run_product(model, batch)
+    errs = dict(answer=H.max_rel(answer.cpu(), want["answer"]), t_probs=H.max_rel(t_probs.cpu(), want["t_probs"]),
+                t_loss=abs(t_loss.item() - want["temporal_loss"].item()) / abs(want["temporal_loss"].item()))
+    print("full size dense=%s" % dense, {k: "%.2e" % v for k, v in errs.items()})
+    assert all(v < H.REL_TOL for v in errs.values()), errs
+    assert torch.equal(answer.argmax(1).cpu(), want["answer"].argmax(1))
+    assert torch.equal(model._last_spans.cpu().long(), want["spans"])
+
+
+@pytest.mark.gpu
+def test_full_size_batch_properties():
+    """Size-independent properties at the BASELINE shapes (batch 6): examples are independent (a batch gives bit-identical
+    results to its shards — the data-parallel contract), span probabilities are distributions over the valid frames, spans
+    are ordered and inside the clip."""
+    from tvqaplus_b200 import host
+    from tvqaplus_b200.model import STAGE
+    opt = O.default_opt()
+    torch.manual_seed(2018)
+    dev = torch.device("cuda:0")
+    model = STAGE(opt).to(dev).eval()
+    batch = O.make_synthetic_batch(6, 300, 20, 100, 100, seed=11, dense=False)
+    full = model(H.batch_to(batch, dev))
+    spans_full = model._last_spans.clone()
+    parts, spans = [], []
+    for r in range(3):
+        sh = host.shard_batch(batch, 3, r)
+        parts.append(model(H.batch_to(sh, dev)))
+        spans.append(model._last_spans.clone())
+    torch.cuda.synchronize()
+    _lib.check_device_error()
+    assert torch.equal(torch.cat([p[0] for p in parts]), full[0]), "answers differ between a batch and its shards"
+    assert torch.equal(torch.cat([p[4] for p in parts]), full[4]), "span probabilities differ between a batch and its shards"
+    assert torch.equal(torch.cat(spans), spans_full)
+    probs = full[4].cpu()  # (N, 5, T, 2)
+    ts = batch.ts_label_mask
+    assert torch.allclose(probs.sum(2), torch.ones(6, 5, 2), atol=1e-5)
+    assert torch.equal(probs[(ts == 0)[:, None, :, None].expand_as(probs)], torch.zeros(int((ts == 0).sum()) * 10))
+    sp = spans_full.cpu().view(6, 5, 2).long()
+    n_frames = ts.sum(1).long()
+    assert (sp[..., 0] <= sp[..., 1]).all() and (sp[..., 0] >= 0).all() and (sp[..., 1] < n_frames[:, None]).all()
+    assert torch.isfinite(full[0]).all()
