@@ -276,13 +276,14 @@ def main():
         sub_embed = model.base_encoder(dbatch.sub_bert.view(N * T, Ls, 768), dbatch.sub_mask.view(N * T, Ls), model._text_fc, None, model.input_encoder).view(N, T, Ls, H)
         vid_embed = model.base_encoder(dbatch.vid.view(N * T, R, 300), dbatch.vid_mask.view(N * T, R), model._vid_fc, None, model.input_encoder).view(N, T, R, H)
         w = model._cqa_weights()
-        ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale)
+        blk = ops.blocked_fits(Lq)  # the same statement layout STAGE.forward uses
+        ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale, blocked=blk)
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
         k0.record()
         for _ in range(reps):
-            ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale)
+            ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale, blocked=blk)
         k1.record()
         torch.cuda.synchronize()
     cqa_ms = k0.elapsed_time(k1) / reps

@@ -87,6 +87,12 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream);
 #define STAGE_ENC_NO_RESIDUAL 2  /* x <- act(conv(x)) instead of x <- x + act(conv(LN x)) */
 #define STAGE_ENC_NO_FINAL_LN 4  /* skip the closing LayerNorm */
 #define STAGE_ENC_NO_RELU 8      /* pointwise conv without ReLU (DepthwiseSeparableConv(relu=False), model/cnn.py:45-46) */
+#define STAGE_ENC_IN_BLOCKED 16  /* x (and pe) come in the blocked tile layout below instead of row-major */
+/* Blocked tile layout (internal fast path between stage_cqa_fused_fwd and the cls encoder): sequence i of length L is a
+ * block of 32 x S float4, element (row, 4-column group c4) at float4 index (i*32 + c4)*S + row, S = stage_blocked_stride(L)
+ * (>= L, == 1 mod 8 so that both a row-per-lane writer and reader are bank-conflict free).  With STAGE_ENC_IN_BLOCKED the
+ * position table is passed in the same form: float4 index c4*L + pos. */
+int stage_blocked_stride(int L);
 /* a conv whose ln_g/ln_b are NULL takes its input without LayerNorm (plain DepthwiseSeparableConv, model/cnn.py:37-47;
  * with them and NO_PE|NO_RESIDUAL|NO_FINAL_LN it is ConvLinear, model/stage.py:35-52) */
 typedef struct {
@@ -160,7 +166,8 @@ typedef struct {
   const float* cat_out_ln_g;   /* [128] concat_fc.4 */
   const float* cat_out_ln_b;
   void* workspace;             /* stage_cqa_workspace_bytes(n, t, lq) bytes, 128-byte aligned */
-  float* statement;            /* [n,5,t,lq,128] */
+  int statement_blocked;       /* 0: statement is [n,5,t,lq,128]; 1: blocked tile layout, n*5*t blocks (see stage_blocked_stride) */
+  float* statement;            /* [n,5,t,lq,128] or n*5*t*32*S float4 */
   float* statement_mask;       /* [n,5,t,lq]  (the vid mixed_mask, model/stage.py:280-282) */
   float* vid_raw_s;            /* optional [n,5,t,lq,r] (other_outputs["vid_raw_s"], model/stage.py:273) */
   float* sub_raw_s;            /* optional [n,5,t,lq,ls] */

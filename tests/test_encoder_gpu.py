@@ -61,3 +61,36 @@ def test_encoder_block(n_seq, L, n_conv, k):
     if (~dead).any():
         errp = (got_p[~dead] - want_p[~dead]).abs().max().item() / want_p[~dead].abs().max().item()
         assert errp < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_seq,L,k", [(7, 100, 5), (10, 40, 5), (130, 1, 5), (9, 33, 7), (4, 128, 5)])
+def test_encoder_block_blocked_input(n_seq, L, k):
+    """The blocked tile layout (the internal hand-over format from the fused CQA kernel) gives the row-major result."""
+    if not ops.blocked_fits(L):
+        pytest.skip("L=%d does not fit the blocked tile buffer" % L)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n_seq + L)
+    sd = random_block("enc", 2, k, g)
+    x = torch.randn(n_seq, L, 128, generator=g)
+    lens = torch.randint(0, L + 1, (n_seq,), generator=g)
+    mask = (torch.arange(L)[None] < lens[:, None]).float()
+    want = run_gpu(x, mask, sd, "enc", 2, k, 1)
+    S = ops.blocked_stride(L)
+    assert S >= L and S % 8 == 1
+    blk = torch.full((n_seq, 32, S, 4), float("nan"))          # padding rows are never read
+    blk[:, :, :L, :] = x.view(n_seq, L, 32, 4).permute(0, 2, 1, 3)
+    d = {kk: v.to(dev) for kk, v in sd.items()}
+    convs = [dict(ln_g=d["enc.layer_norm.%d.weight" % i], ln_b=d["enc.layer_norm.%d.bias" % i],
+                  dw_w=d["enc.conv.%d.depthwise_conv.weight" % i], dw_b=d["enc.conv.%d.depthwise_conv.bias" % i],
+                  pw_packed=ops.pack_weight(d["enc.conv.%d.pointwise_conv.weight" % i], 64),
+                  pw_b=d["enc.conv.%d.pointwise_conv.bias" % i]) for i in range(2)]
+    got = ops.encoder_block_fwd(blk.reshape(-1).to(dev), mask.to(dev), ops.blocked_pe(d["enc.position_encoding.pe"], L), convs,
+                                (d["enc.final_layer_norm.weight"], d["enc.final_layer_norm.bias"]), k, out_mode=1,
+                                blocked_in=(n_seq, L)).cpu()
+    torch.cuda.synchronize()
+    _lib.check_device_error()
+    dead = lens == 0
+    assert torch.equal(got[dead], want[dead])
+    if (~dead).any():
+        assert (got[~dead] - want[~dead]).abs().max().item() / want[~dead].abs().max().item() < 1e-5

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstage_b200.so")
 
 MAX_CONV = 4
-ENC_NO_PE, ENC_NO_RESIDUAL, ENC_NO_FINAL_LN, ENC_NO_RELU = 1, 2, 4, 8
+ENC_NO_PE, ENC_NO_RESIDUAL, ENC_NO_FINAL_LN, ENC_NO_RELU, ENC_IN_BLOCKED = 1, 2, 4, 8, 16
 
 _f = C.c_void_p  # device pointers travel as integers
 
@@ -41,7 +41,7 @@ class CqaArgs(C.Structure):
     _fields_ = [("n", C.c_int), ("t", C.c_int), ("lq", C.c_int), ("ls", C.c_int), ("r", C.c_int), ("scale", C.c_float),
                 ("a_embed", _f), ("a_mask", _f), ("sub_embed", _f), ("sub_mask", _f), ("vid_embed", _f), ("vid_mask", _f),
                 ("wblob", _f), ("cat_out_ln_g", _f), ("cat_out_ln_b", _f), ("workspace", _f),
-                ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
+                ("statement_blocked", C.c_int), ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
                 ("vid_norm_s", _f), ("sub_norm_s", _f), ("att_vid", _f), ("att_sub", _f),
                 ("mixed_vid", _f), ("mixed_sub", _f), ("timeline", _f)]
 
@@ -73,6 +73,7 @@ SYMBOLS = {
     "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_pack_weight_ln": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "stage_linear_fwd": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "stage_blocked_stride": (C.c_int, [C.c_int]),
     "stage_encoder_block_fwd": (C.c_int, [C.POINTER(EncoderArgs), C.c_void_p]),
     "stage_mha_fwd": (C.c_int, [C.POINTER(MhaArgs), C.c_void_p]),
     "stage_cqa_weight_blob_bytes": (C.c_size_t, []),

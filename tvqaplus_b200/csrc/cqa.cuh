@@ -80,6 +80,7 @@ struct CqaDev {
   const float* cat_cs; const float* cat_cb;
   const float* out_g; const float* out_b;
   float* statement; float* statement_mask;
+  int stmt_stride;            // 0: row-major statement; else S of the blocked tile layout
   float* vid_raw_s; float* sub_raw_s; float* vid_norm_s; float* sub_norm_s;
   float* att_vid; float* att_sub; float* mixed_vid; float* mixed_sub;
   long long* timeline;  // optional [2][64][16] clock64 stamps of block 0 (compute thread 0 / MMA thread), first 64 tiles
@@ -610,10 +611,19 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           if (live) {
             const float4* g4p = reinterpret_cast<const float4*>(&pvec[4][qd * 32]);
             const float4* b4p = reinterpret_cast<const float4*>(&pvec[5][qd * 32]);
+            // row-major: my 32 columns are 128 contiguous bytes of the row (a warp touches 32 lines per store);
+            // blocked: float4 c4 of row r sits at (tile*32 + c4)*S + r, so the 32 rows of a warp write 512-byte runs
+            float4* dst = reinterpret_cast<float4*>(p.statement) + (orow >> 2);
+            size_t dstep = 1;
+            if (p.stmt_stride != 0) {
+              const uint32_t trow = srow / p.lq;  // (example, answer, frame) tile index
+              dst = reinterpret_cast<float4*>(p.statement) + (static_cast<size_t>(trow) * 32 + qd * 8) * p.stmt_stride + (srow - trow * p.lq);
+              dstep = p.stmt_stride;
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 g = g4p[j >> 2], b = b4p[j >> 2];
-              *reinterpret_cast<float4*>(p.statement + orow + j) =
+              dst[(j >> 2) * dstep] =
                   make_float4(fmaf(fmaf(o[j], rstd, nmr), g.x, b.x), fmaf(fmaf(o[j + 1], rstd, nmr), g.y, b.y),
                               fmaf(fmaf(o[j + 2], rstd, nmr), g.z, b.z), fmaf(fmaf(o[j + 3], rstd, nmr), g.w, b.w));
             }

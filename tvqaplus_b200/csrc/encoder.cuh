@@ -55,6 +55,7 @@ struct EncDev {
   float* y;
   long long n_seq;
   int L, n_conv, out_mode, flags;
+  int S;  // row stride of the blocked input layout (STAGE_ENC_IN_BLOCKED)
   long long* timeline;  // optional debug: [32 tiles][16] SM clock stamps of thread 0 of CTA 0 (tools/encoder_timeline.py)
 };
 
@@ -109,10 +110,15 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
     const long long n_here = (p.n_seq - seq0) < G ? (p.n_seq - seq0) : G;
     return static_cast<int>(n_here) * L;
   };
-  if (tid == 0 && static_cast<long long>(blockIdx.x) < n_tiles) {
-    const uint32_t bytes = static_cast<uint32_t>(rows_of(blockIdx.x)) * 512u;
+  const bool blocked = (p.flags & STAGE_ENC_IN_BLOCKED) != 0;
+  const long long seq_floats = blocked ? 128ll * p.S : 128ll * L;  // floats one sequence occupies in x
+  auto fetch_tile = [&](long long tile) {  // thread 0: ONE bulk copy brings the whole tile (contiguous in either layout)
+    const uint32_t bytes = static_cast<uint32_t>(rows_of(tile) / L) * static_cast<uint32_t>(seq_floats) * 4u;
     mbar_arrive_expect_tx(&x_bar, bytes);
-    bulk_g2s(sA, p.x + static_cast<long long>(blockIdx.x) * G * L * 128, bytes, &x_bar);
+    bulk_g2s(sA, p.x + tile * G * seq_floats, bytes, &x_bar);
+  };
+  if (tid == 0 && static_cast<long long>(blockIdx.x) < n_tiles) {
+    fetch_tile(blockIdx.x);
     mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
     bulk_g2s(sW, p.pw[0], EncCfg::W_BYTES, &w_bar);
   }
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
       m_r[rr] = 0.f;
       if (r < nv) {
         const int pos = r - (r / L) * L;
-        if (!(p.flags & STAGE_ENC_NO_PE)) pe_r[rr] = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
+        if (!(p.flags & STAGE_ENC_NO_PE) && !blocked) pe_r[rr] = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
         if (p.mask != nullptr) m_r[rr] = __ldg(p.mask + tile * G * L + r);
       }
     }
@@ -148,7 +154,40 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
     mbar_wait(&x_bar, x_count & 1u, 22);
     ++x_count;
     ENC_STAMP(1);
-    {
+    if (blocked) {
+      // blocked input: thread = (row, column quarter) like the epilogue; raw float4 (row, c4) at (g*32 + c4)*S + pos, the
+      // position table at c4*L + pos -> lanes (= rows) read consecutive addresses in shared and global memory alike
+      const int r = (warp & 3) * 32 + lane, qd = warp >> 2;
+      const int g = row_sid[r], pos = r - g * L;
+      const float4* raw = reinterpret_cast<const float4*>(sA) + (g * 32 + qd * 8) * p.S + pos;
+      const float4* pe4 = reinterpret_cast<const float4*>(p.pe) + (qd * 8) * L + pos;
+      float* xr = X + r * EncCfg::XS + qd * 32;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n_valid) {
+          v = raw[j * p.S];
+          if (!(p.flags & STAGE_ENC_NO_PE)) {
+            const float4 e = __ldg(pe4 + j * L);
+            v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+          }
+        }
+        *reinterpret_cast<float4*>(xr + j * 4) = v;
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+      }
+      xq[0][qd][r] = s1;
+      xq[1][qd][r] = s2;
+      if (qd == 0) row_mask[r] = (r < n_valid && p.mask != nullptr) ? __ldg(p.mask + seq0 * L + r) : 0.f;
+      __syncthreads();
+      if (tid < 128) {
+        const float mean = ((xq[0][0][tid] + xq[0][1][tid]) + (xq[0][2][tid] + xq[0][3][tid])) * (1.f / 128.f);
+        const float ex2 = ((xq[1][0][tid] + xq[1][1][tid]) + (xq[1][2][tid] + xq[1][3][tid])) * (1.f / 128.f);
+        const float rs = 1.f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+        row_stat[tid] = make_float2(mean * rs, rs);
+      }
+    } else {
       const float4* raw = reinterpret_cast<const float4*>(sA);
 #pragma unroll
       for (int rr = 0; rr < RW; ++rr) {
@@ -258,12 +297,7 @@ __global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
           mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
           bulk_g2s(sW, p.pw[nxt < p.n_conv ? nxt : 0], EncCfg::W_BYTES, &w_bar);
         }
-        if (nxt == p.n_conv && more) {
-          const long long nt = tile + gridDim.x;
-          const uint32_t bytes = static_cast<uint32_t>(rows_of(nt)) * 512u;
-          mbar_arrive_expect_tx(&x_bar, bytes);
-          bulk_g2s(sA, p.x + nt * G * L * 128, bytes, &x_bar);
-        }
+        if (nxt == p.n_conv && more) fetch_tile(tile + gridDim.x);
       }
 
       // ---- epilogue  X += relu(D + b)   (thread = row x column quarter) + statistics of the new row

@@ -128,6 +128,8 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
   return launch_linear<304, 32, 3>(d, s);
 }
 
+int stage_blocked_stride(int L) { return L <= 0 ? 0 : L + ((9 - L % 8) % 8); }
+
 int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(a && a->x && a->y, STAGE_E_BADARG, "encoder: null pointer");
   STG_REQUIRE((a->flags & STAGE_ENC_NO_PE) || a->pe, STAGE_E_BADARG, "encoder: null position-encoding table");
@@ -137,7 +139,12 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(a->n_conv >= 1 && a->n_conv <= STAGE_MAX_CONV, STAGE_E_UNSUPPORTED, "encoder: n_conv=%d", a->n_conv);
   STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
+  const int S = stage_blocked_stride(a->L);
+  if (a->flags & STAGE_ENC_IN_BLOCKED)
+    STG_REQUIRE(static_cast<size_t>(128 / a->L) * 32 * S * 16 <= EncCfg::A_BYTES, STAGE_E_UNSUPPORTED,
+                "encoder: blocked input with L=%d does not fit the tile buffer (use the row-major layout)", a->L);
   EncDev d;
+  d.S = S;
   d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;
   d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode; d.flags = a->flags; d.timeline = a->timeline;
   for (int i = 0; i < STAGE_MAX_CONV; ++i) {
@@ -277,6 +284,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
   d.c2q_w = wb + WB_WU; d.c2q_cs = vec; d.c2q_cb = vec + 128; d.cat_w = wb + WB_WF; d.cat_cs = vec + 256; d.cat_cb = vec + 384;
   d.out_g = a->cat_out_ln_g; d.out_b = a->cat_out_ln_b;
   d.statement = a->statement; d.statement_mask = a->statement_mask;
+  d.stmt_stride = a->statement_blocked ? stage_blocked_stride(a->lq) : 0;
   d.vid_raw_s = a->vid_raw_s; d.sub_raw_s = a->sub_raw_s; d.vid_norm_s = a->vid_norm_s; d.sub_norm_s = a->sub_norm_s;
   d.att_vid = a->att_vid; d.att_sub = a->att_sub; d.mixed_vid = a->mixed_vid; d.mixed_sub = a->mixed_sub;
   d.timeline = a->timeline;

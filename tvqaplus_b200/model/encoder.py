@@ -37,17 +37,26 @@ class EncoderBlock(nn.Module):
             self.multi_head_attn = MultiHeadedAttention(nh=num_heads, d_model=n_filters)
             self.attn_layer_norm = nn.LayerNorm(n_filters)
 
-    def forward(self, x, mask, pool: bool = False):
+    def _blocked_pe(self, L):
+        pe = self.position_encoding.pe
+        tag = (L, pe.data_ptr(), pe._version)
+        if getattr(self, "_pe_blk_tag", None) != tag:
+            self._pe_blk, self._pe_blk_tag = ops.blocked_pe(pe, L), tag
+        return self._pe_blk
+
+    def forward(self, x, mask, pool: bool = False, blocked_in=None):
         """x (N, L, D), mask (N, L) -> (N, L, D); ``pool=True`` returns max_l mask_logits(out, mask) (N, D) instead
-        (the fused tail of STAGE.classfier_head_multi_proposal)."""
+        (the fused tail of STAGE.classfier_head_multi_proposal).  ``blocked_in=(N, L)``: x is the flat blocked tile buffer
+        ``ops.cqa_fused_fwd(blocked=True)`` produced (internal fast path of STAGE.forward)."""
         _no_train_dropout(self, self.dropout)
         convs = [c.conv_args(ln) for c, ln in zip(self.conv, self.layer_norm)]
         fin = (self.final_layer_norm.weight, self.final_layer_norm.bias)
-        pe = self.position_encoding.pe
+        pe = self.position_encoding.pe if blocked_in is None else self._blocked_pe(blocked_in[1])
         if self.num_heads == 0:
-            return ops.encoder_block_fwd(x, mask, pe, convs, fin, self.kernel_size, out_mode=1 if pool else 0)
+            return ops.encoder_block_fwd(x, mask, pe, convs, fin, self.kernel_size, out_mode=1 if pool else 0,
+                                         blocked_in=blocked_in)
         # convs (no closing LN) -> LN + MHA + residual -> closing LN (+ pool)
-        y = ops.encoder_block_fwd(x, mask, pe, convs, None, self.kernel_size, skip_final_ln=True)
+        y = ops.encoder_block_fwd(x, mask, pe, convs, None, self.kernel_size, skip_final_ln=True, blocked_in=blocked_in)
         return ops.mha_fwd(y, mask, self.multi_head_attn.attn_args(self.attn_layer_norm), self.num_heads, residual=True,
                            final_ln=fin, pool=pool)
 
@@ -60,7 +69,7 @@ class StackedEncoder(nn.Module):
             EncoderBlock(n_conv=n_conv, kernel_size=kernel_size, n_filters=hidden_size, dropout=dropout,
                          num_heads=num_heads) for _ in range(n_blocks)])
 
-    def forward(self, x, mask, pool: bool = False):
+    def forward(self, x, mask, pool: bool = False, blocked_in=None):
         for i, blk in enumerate(self.stacked_encoderBlocks):
-            x = blk(x, mask, pool=pool and i == self.n_blocks - 1)
+            x = blk(x, mask, pool=pool and i == self.n_blocks - 1, blocked_in=blocked_in if i == 0 else None)
         return x

@@ -220,12 +220,13 @@ class STAGE(nn.Module):
                                       self._vid_fc, None, self.input_encoder).view(bsz, T, R, hsz)
 
         need_raw = self.inference_mode
+        blocked = ops.blocked_fits(Lq)  # the statement goes to the cls encoder in the blocked tile layout (never seen outside)
         cq = ops.cqa_fused_fwd(a_embed, qas_mask.view(bsz, num_a, Lq), sub_embed, sub_mask, vid_embed, vid_mask,
-                               self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else ())
+                               self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else (), blocked=blocked)
         other_outputs = {"vid_raw_s": cq.get("vid_raw_s")}
         out, target, t_scores, t_probs = self.classfier_head_multi_proposal(
             cq["statement"], cq["statement_mask"], batch.target, batch.ts_label, batch.ts_label_mask,
-            extra_span_length=self.extra_span_length)
+            extra_span_length=self.extra_span_length, _blocked=blocked)
         other_outputs["temporal_scores"] = t_scores
 
         if self.inference_mode:
@@ -239,13 +240,18 @@ class STAGE(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ heads
     def classfier_head_multi_proposal(self, statement, statement_mask, targets, ts_labels, ts_labels_mask,
-                                      max_num_proposal=1, ce_prob_thd=0.01, iou_thd=0.5, extra_span_length=3):
+                                      max_num_proposal=1, ce_prob_thd=0.01, iou_thd=0.5, extra_span_length=3, _blocked=False):
         """statement (N,5,Li,Lqa,D), statement_mask (N,5,Li,Lqa) -> answer scores (N,5), targets, masked span logits
         (N,5,Li,2) [+ their softmax over Li].  cls_encoder + masked max-pool is one kernel, everything after it another
         (eval branch of the reference, model/stage.py:484-537 with get_proposals :439-467)."""
         bsz, num_a, num_img, num_words = statement_mask.shape
-        max_statement = self.cls_encoder(statement.view(bsz * num_a * num_img, num_words, -1),
-                                         statement_mask.view(bsz * num_a * num_img, num_words), pool=True)
+        n_seq = bsz * num_a * num_img
+        if _blocked:  # statement = flat blocked tile buffer of cqa_fused_fwd(blocked=True)
+            max_statement = self.cls_encoder(statement, statement_mask.view(n_seq, num_words), pool=True,
+                                             blocked_in=(n_seq, num_words))
+        else:
+            max_statement = self.cls_encoder(statement.view(n_seq, num_words, -1), statement_mask.view(n_seq, num_words),
+                                             pool=True)
         head = ops.span_head_fwd(max_statement.view(bsz * num_a, num_img, -1), statement_mask, ts_labels_mask.float(),
                                  self._head_weights(), add_local=self.add_local, extra_span_length=extra_span_length)
         self._last_spans = head["spans"]

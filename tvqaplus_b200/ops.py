@@ -98,6 +98,7 @@ def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
 
 def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optional[torch.Tensor], convs: Sequence[dict],
                       final_ln, ksize: int, *, out_mode: int = 0, timeline: Optional[torch.Tensor] = None,
+                      blocked_in: Optional[tuple] = None,
                       conv_only: bool = False, pre_ln_only: bool = False, relu: bool = True,
                       skip_final_ln: bool = False) -> torch.Tensor:
     """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
@@ -106,17 +107,23 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
     ``conv_only``: just the depthwise-separable convs (no PE / LayerNorm / residual) — DepthwiseSeparableConv;
     ``pre_ln_only``: LayerNorm -> conv without PE / residual / final LN — ConvLinear."""
     x = _f32(x)
-    n_seq, L, D = x.shape
+    if blocked_in is not None:  # x is the flat blocked tile buffer of cqa_fused_fwd(blocked=True); pe is blocked_pe(pe, L)
+        n_seq, L = blocked_in
+        D = HSZ
+        if x.numel() != n_seq * 128 * blocked_stride(L):
+            raise RuntimeError("tvqaplus_b200: blocked buffer size does not match (n_seq=%d, L=%d)" % (n_seq, L))
+    else:
+        n_seq, L, D = x.shape
     if D != HSZ:
         raise RuntimeError("tvqaplus_b200: hidden size %d != %d" % (D, HSZ))
-    flags = 0
+    flags = _lib.ENC_IN_BLOCKED if blocked_in is not None else 0
     if conv_only or pre_ln_only:
         flags |= _lib.ENC_NO_PE | _lib.ENC_NO_RESIDUAL | _lib.ENC_NO_FINAL_LN
     if not relu:
         flags |= _lib.ENC_NO_RELU
     if skip_final_ln:
         flags |= _lib.ENC_NO_FINAL_LN
-    if not (flags & _lib.ENC_NO_PE) and pe.shape[0] < L:
+    if not (flags & _lib.ENC_NO_PE) and blocked_in is None and pe.shape[0] < L:
         raise RuntimeError("tvqaplus_b200: sequence length %d exceeds the position-encoding table (%d)" % (L, pe.shape[0]))
     y = torch.empty((n_seq, L, D) if out_mode == 0 else (n_seq, D), dtype=torch.float32, device=x.device)
     names = ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")
@@ -147,8 +154,23 @@ def cqa_prepare_weights(c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, ca
     return blob
 
 
+def blocked_stride(L: int) -> int:
+    """Row stride S of the blocked tile layout (stage_blocked_stride)."""
+    return int(lib().stage_blocked_stride(int(L)))
+
+
+def blocked_fits(L: int) -> bool:
+    """Can the encoder kernel take sequences of length L in the blocked layout (whole tile in one 66 KB buffer)?"""
+    return 0 < L <= 128 and (128 // L) * 32 * blocked_stride(L) * 16 <= 66048
+
+
+def blocked_pe(pe: torch.Tensor, L: int) -> torch.Tensor:
+    """Position table rows [0, L) in the blocked form the encoder reads with STAGE_ENC_IN_BLOCKED: [32][L] float4."""
+    return _f32(pe[:L]).view(L, 32, 4).permute(1, 0, 2).contiguous()
+
+
 def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
-                  want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None) -> dict:
+                  want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None, blocked: bool = False) -> dict:
     """Fused StructuredAttention x2 + c2q_down_projection x2 + concat_fc (stage_cqa_fused_fwd).
 
     a_embed (N,5,Lq,128), a_mask (N,5,Lq), sub_embed (N,T,Ls,128), sub_mask (N,T,Ls), vid_embed (N,T,R,128),
@@ -164,7 +186,10 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
     if A != 5 or D != HSZ:
         raise RuntimeError("tvqaplus_b200: a_embed must be (N,5,Lq,128)")
     dev = a_embed.device
-    out = {"statement": torch.empty(N, 5, T, Lq, D, dtype=torch.float32, device=dev),
+    # ``blocked``: the statement leaves in the blocked tile layout the cls encoder consumes directly (a flat buffer of
+    # N*5*T tiles of 32 x S float4); the padding rows [Lq, S) of a tile are never read
+    out = {"statement": torch.empty(N * 5 * T * 128 * blocked_stride(Lq), dtype=torch.float32, device=dev) if blocked
+           else torch.empty(N, 5, T, Lq, D, dtype=torch.float32, device=dev),
            "statement_mask": torch.empty(N, 5, T, Lq, dtype=torch.float32, device=dev)}
     shapes = {"vid_raw_s": (N, 5, T, Lq, R), "sub_raw_s": (N, 5, T, Lq, Ls), "vid_norm_s": (N, 5, T, Lq, R),
               "sub_norm_s": (N, 5, T, Lq, Ls), "att_vid": (N, 5, T, Lq, D), "att_sub": (N, 5, T, Lq, D),
@@ -178,7 +203,8 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
                      a_embed=ptr(a_embed), a_mask=ptr(a_mask), sub_embed=ptr(sub_embed), sub_mask=ptr(sub_mask),
                      vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask), wblob=ptr(w["wblob"]),
                      cat_out_ln_g=ptr(_f32(w["cat_out_ln_g"])), cat_out_ln_b=ptr(_f32(w["cat_out_ln_b"])),
-                     workspace=ws_ptr, statement=ptr(out["statement"]), statement_mask=ptr(out["statement_mask"]),
+                     workspace=ws_ptr, statement_blocked=int(blocked), statement=ptr(out["statement"]),
+                     statement_mask=ptr(out["statement_mask"]),
                      timeline=ptr(timeline), **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
     _count(3)
