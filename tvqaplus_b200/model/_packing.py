@@ -23,14 +23,14 @@ def packed(param: torch.Tensor, kc: int) -> torch.Tensor:
     return img
 
 
-_cache_ln: Dict[int, Tuple[tuple, tuple, "weakref.ref"]] = {}
+_cache_ln: Dict[tuple, Tuple[tuple, tuple, "weakref.ref"]] = {}
 
 
 def packed_ln(lin, ln, kc: int):
     """(image of W*gamma, cs, cb) for ``lin`` (nn.Linear) applied after ``ln`` (nn.LayerNorm); cached on the versions of
     all four parameters."""
     params = (lin.weight, lin.bias, ln.weight, ln.bias)
-    key = id(lin.weight)
+    key = (id(lin.weight), id(ln.weight))
     tag = tuple((t.data_ptr(), t._version, str(t.device)) for t in params) + (kc,)
     hit = _cache_ln.get(key)
     if hit is not None and hit[0] == tag and hit[2]() is lin.weight:
