@@ -9,18 +9,25 @@
 // LayerNorm(384) is folded into the GEMM that follows it:
 //        LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * cs) + cb ,  cs = (W*gamma) 1,  cb = W beta + b
 // so the A operand is the RAW [p, q, p*q] row (one pass over TMEM, statistics accumulated on the fly), and the
-// frame-invariant third of c2q, Za = a (Wc*gamma)[:, :128]^T, is computed once per (example, answer) and pre-loaded into
-// the accumulator with tcgen05.st (executed FLOPs of c2q drop by a third; algorithmic FLOPs are still quoted in full).
+// frame-invariant third of c2q, Za = a (Wc*gamma)[:, :128]^T, is computed once per (example, answer), loaded under the
+// U MMAs and written into both c2q accumulators with tcgen05.st (executed FLOPs of c2q drop by a third; algorithmic FLOPs
+// are still quoted in full).  The softmax is normalised late: P' = exp2(scale*log2e*S - shift) goes to the tensor cores
+// un-normalised and U = P'.ctx is divided by the row sum when it is read back, so the softmax phase needs no barrier.
 //
 // Everything between the fp32 encoder outputs and the statement tile stays on chip:
 //   shared memory: split-fp16 images of the frame's ctx tiles (one cp.async.bulk per frame; read K-major for S and
-//                  MN-major for U), the answer image (one bulk copy per tile), P, and the A / W pipelines of the GEMMs
-//   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator, T1 = S_vid -> c2q(vid), T2 = U_sub -> concat accumulator,
-//                  T3 = U_vid
-// Warp roles (544 threads): warps 0-15 compute (thread = row x column quarter; 4 warps per scheduler hide the FP and
-// TMEM latencies of the epilogue math), warp 16 = MMA issue + all bulk copies.
+//                  MN-major for U), the answer image (one bulk copy per tile), P', two K=64 A stages and a 4-slot ring of
+//                  K=32 weight chunks for the three 384->128 GEMMs
+//   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator -> activated ms,  T1 = S_vid -> c2q(vid) -> activated mv,
+//                  T2 = U_sub -> concat accumulator,  T3 = U_vid
+// Warp roles (576 threads): warps 0-15 compute (thread = row x column quarter; everything is produced 16 columns at a
+// time so that the 96-register budget of an 18-warp CTA is never exceeded: shared memory takes the whole L1 carve-out, a
+// spill would be an L2 round trip), warp 16 = MMA issue (never waits for a completion), warp 17 = all bulk copies.
+// The 5 x Lq answer rows of an example are packed into 128-row tiles (4 tiles instead of 5 at Lq = 100); per-thread
+// global accesses (fp32 answers, Za, and optionally the statement) use a blocked [4-column group][row] layout so that a
+// warp's 32 rows touch whole lines.
 //
-// Algorithmic work per (answer, frame) tile with Lq rows: 4*128*Lq*(Ls+R) + 3*(2*384*128)*Lq FLOP.
+// Algorithmic work per (answer, frame) with Lq rows: 4*128*Lq*(Ls+R) + 3*(2*384*128)*Lq FLOP.
 #pragma once
 #include "umma.cuh"
 
