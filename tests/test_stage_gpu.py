@@ -148,3 +148,20 @@ def test_full_size_batch_properties():
     n_frames = ts.sum(1).long()
     assert (sp[..., 0] <= sp[..., 1]).all() and (sp[..., 0] >= 0).all() and (sp[..., 1] < n_frames[:, None]).all()
     assert torch.isfinite(full[0]).all()
+
+
+@pytest.mark.gpu
+def test_long_context_shape_against_oracle():
+    """BASELINE configs[4] shapes (T=600 frames, R=40 regions, Lq=Ls=100), one example, ragged masks."""
+    from tvqaplus_b200.model import STAGE
+    opt = O.default_opt()
+    torch.manual_seed(2018)
+    model = STAGE(opt).eval()
+    batch = O.make_synthetic_batch(1, 600, 40, 100, 100, seed=5, dense=False)
+    want = O.stage_forward({k: v.clone() for k, v in model.state_dict().items()}, opt, batch, keep=True)
+    model, (answer, _, _, t_loss, t_probs) = run_product(model, batch)
+    errs = dict(answer=H.max_rel(answer.cpu(), want["answer"]), t_probs=H.max_rel(t_probs.cpu(), want["t_probs"]))
+    print("long context", {k: "%.2e" % v for k, v in errs.items()})
+    assert all(v < H.REL_TOL for v in errs.values()), errs
+    assert torch.equal(answer.argmax(1).cpu(), want["answer"].argmax(1))
+    assert torch.equal(model._last_spans.cpu().long(), want["spans"])
