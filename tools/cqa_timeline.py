@@ -7,7 +7,7 @@ import torch  # noqa: E402
 
 from tvqaplus_b200 import ops  # noqa: E402
 
-N, T, Lq, Ls, R = 2, 300, 100, 100, 20
+N, T, Lq, Ls, R = 8, 300, 100, 100, 20  # CTA 0 sees 17 frames x 4 packed tiles >= the 64 stamped tiles
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 a = torch.randn(N, 5, Lq, 128, generator=g).to(dev)
@@ -31,7 +31,7 @@ for tile in range(2, 8):
     print("tile", tile)
     print("  compute:", "  ".join("%s %d" % (names_c[i], int(c[tile][i]) - t0) for i in range(12)))
     print("  mma    :", "  ".join("%s %d" % (names_m[i], int(m[tile][i]) - t0) for i in range(9)))
-d = (c[3:40, 1:12] - c[3:40, 0:11]).float().mean(0)
-print("compute mean phase cycles:", {names_c[i + 1]: int(d[i]) for i in range(11)}, "tile total", int((c[4:40, 0] - c[3:39, 0]).float().mean()))
-dm = (m[3:40, 1:9] - m[3:40, 0:8]).float().mean(0)
+d = (c[3:60, 1:12] - c[3:60, 0:11]).float().mean(0)
+print("compute mean phase cycles:", {names_c[i + 1]: int(d[i]) for i in range(11)}, "tile total", int((c[4:60, 0] - c[3:59, 0]).float().mean()))
+dm = (m[3:60, 1:9] - m[3:60, 0:8]).float().mean(0)
 print("mma mean phase cycles:", {names_m[i + 1]: int(dm[i]) for i in range(8)})
