@@ -28,14 +28,14 @@ def kmajor_image(x: np.ndarray, lbo: int) -> np.ndarray:
     return img
 
 
-def run_probe(a_img, b_img, n, k_steps, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, b_mn=0, use_bulk=0):
+def run_probe(a_img, b_img, n, k_steps, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, b_mn=0, use_bulk=0, a_mn=0):
     dev = torch.device("cuda:0")
     ta = torch.from_numpy(a_img).to(dev)
     tb = torch.from_numpy(b_img).to(dev)
     d = torch.full((128, n), float("nan"), device=dev)
     args = _lib.ProbeArgs(a_img=ta.data_ptr(), b_img=tb.data_ptr(), a_bytes=ta.numel(), b_bytes=tb.numel(),
                           a_lbo=a_lbo, a_sbo=a_sbo, a_step=a_step, b_lbo=b_lbo, b_sbo=b_sbo, b_step=b_step,
-                          a_mn=0, b_mn=b_mn, k_steps=k_steps, n=n, use_bulk=use_bulk, d_out=d.data_ptr())
+                          a_mn=a_mn, b_mn=b_mn, k_steps=k_steps, n=n, use_bulk=use_bulk, d_out=d.data_ptr())
     _lib.check(_lib.lib().stage_umma_probe(args, _lib.current_stream()), "stage_umma_probe")
     torch.cuda.synchronize()
     _lib.check_device_error()
@@ -76,6 +76,18 @@ def test_umma_conventions():
         got = run_probe(pi, ci, 128, J // 16, p_lbo, 128, 2 * p_lbo, 128, c_lbo, 256, b_mn=1)
         report["mnmajor_j%d" % J] = relerr(got, want)
         print("mnmajor", J, report["mnmajor_j%d" % J], flush=True)
+
+    # ---- A operand from tensor memory (row r in lane r, two fp16 per 32-bit column), B K-major in shared memory
+    for n, ksteps in [(128, 2), (128, 8), (64, 4)]:
+        Kt = 16 * ksteps
+        At = rng.standard_normal((128, Kt)).astype(np.float16)
+        B = rng.standard_normal((n, Kt)).astype(np.float16)
+        want = At.astype(np.float32) @ B.astype(np.float32).T
+        b_lbo = n * 16
+        bi = kmajor_image(B, b_lbo)
+        got = run_probe(np.ascontiguousarray(At).view(np.uint8).reshape(-1), bi, n, ksteps, 0, 0, 0, b_lbo, 128, 2 * b_lbo, a_mn=2)
+        report["a_tmem_n%d_k%d" % (n, Kt)] = relerr(got, want)
+        print("a_tmem", n, Kt, report["a_tmem_n%d_k%d" % (n, Kt)], flush=True)
 
     # ---- B sub-tile addressed by start-address offset (N split 304 = 160 + 144)
     n_full = 304

@@ -17,6 +17,8 @@ struct ProbeArgs {
   uint32_t k_steps;
   uint32_t n;          // MMA N (multiple of 16, <= 256)
   uint32_t use_bulk;   // 1: B image arrives through cp.async.bulk + mbarrier, 0: generic stores
+  uint32_t a_tmem;     // 1: A comes from TENSOR MEMORY: a_img is row-major fp16 [128][16*k_steps]; thread r packs its row two
+                       //    k values per 32-bit column and stores it with tcgen05.st at columns [256 + 8*ks, +8)
   float* d_out;        // [128][n]
 };
 
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
     mbar_init(&bar_tx, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -50,6 +52,16 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
     for (uint32_t i = tid * 16; i < p.b_bytes; i += 128 * 16)
       *reinterpret_cast<uint4*>(sb + i) = *reinterpret_cast<const uint4*>(p.b_img + i);
   }
+  if (p.a_tmem) {
+    const uint32_t r = warp * 32 + lane;
+    for (uint32_t ks = 0; ks < p.k_steps; ++ks) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.a_img + (static_cast<size_t>(r) * p.k_steps + ks) * 32);
+      const uint4 q0 = src[0], q1 = src[1];
+      tmem_st8(tbase + ((warp * 32u) << 16) + 256 + ks * 8, q0, q1);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+  }
   fence_async_smem();
   __syncthreads();
 
@@ -59,7 +71,8 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
     for (uint32_t ks = 0; ks < p.k_steps; ++ks) {
       uint64_t ad = make_smem_desc(smem_u32(sa) + ks * p.a_step, p.a_lbo, p.a_sbo);
       uint64_t bd = make_smem_desc(smem_u32(sb) + ks * p.b_step, p.b_lbo, p.b_sbo);
-      umma_f16(tbase, ad, bd, p.idesc, ks > 0 ? 1u : 0u);
+      if (p.a_tmem) umma_f16_ts(tbase, tbase + 256 + ks * 8, bd, p.idesc, ks > 0 ? 1u : 0u);
+      else umma_f16(tbase, ad, bd, p.idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(&bar_mma);
   }
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tbase);
+  if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
 }  // namespace stg

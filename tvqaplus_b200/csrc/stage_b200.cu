@@ -67,7 +67,8 @@ int stage_umma_probe(const StageProbeArgs* a, void* stream) {
   p.a_img = a->a_img; p.b_img = a->b_img; p.a_bytes = a->a_bytes; p.b_bytes = a->b_bytes;
   p.a_lbo = a->a_lbo; p.a_sbo = a->a_sbo; p.a_step = a->a_step;
   p.b_lbo = a->b_lbo; p.b_sbo = a->b_sbo; p.b_step = a->b_step;
-  p.idesc = make_idesc_f16(a->n, a->a_mn, a->b_mn);
+  p.a_tmem = (a->a_mn == 2u) ? 1u : 0u;  /* a_mn = 2: A operand from tensor memory (K-major by construction) */
+  p.idesc = make_idesc_f16(a->n, p.a_tmem ? 0u : a->a_mn, a->b_mn);
   p.k_steps = a->k_steps; p.n = a->n; p.use_bulk = a->use_bulk; p.d_out = a->d_out;
   size_t smem = ((a->a_bytes + 1023u) & ~1023u) + a->b_bytes + 1024;
   STG_REQUIRE(smem <= 200 * 1024, STAGE_E_UNSUPPORTED, "probe: smem %zu", smem);
