@@ -8,7 +8,7 @@ import torch  # noqa: E402
 from tvqaplus_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-n_seq, L, k = 148 * 24, 100, 5
+n_seq, L, k = 148 * 2 * 26, 100, 5
 x = torch.randn(n_seq, L, 128, device=dev)
 mask = torch.ones(n_seq, L, device=dev)
 pe = torch.randn(500, 128, device=dev)
@@ -21,9 +21,9 @@ for _ in range(2):
     ops.encoder_block_fwd(x, mask, pe, convs, fin, k, out_mode=1, timeline=tl)
 torch.cuda.synchronize()
 t = tl.cpu()
-names = ["start", "rows landed", "phase0", "conv0", "sync", "mma0", "epi0", "stat0", "conv1", "sync", "mma1", "epi1", "stat1",
-         "-", "tail", "end"]
+names = ["start", "phase0", "conv0", "mma0", "epi0", "-", "conv1", "mma1", "epi1", "-", "-", "-", "lnorm", "pool", "end", "-"]
+order = [0, 1, 2, 3, 4, 6, 7, 8, 12, 13, 14]
 for i in range(3, 6):
-    print("tile", i, " ".join("%s %d" % (names[j], int(t[i][j]) - int(t[i][0])) for j in range(16) if j != 13))
-d = (t[4:20, 1:] - t[4:20, :-1]).float().mean(0)
-print("mean phase cycles:", {names[j + 1]: int(d[j]) for j in range(15) if j not in (12, 13)}, "period", int((t[20][0] - t[4][0]) / 16))
+    print("tile", i, " ".join("%s %d" % (names[j], int(t[i][j]) - int(t[i][0])) for j in order))
+d = {names[b]: int((t[4:20, b] - t[4:20, a]).float().mean()) for a, b in zip(order[:-1], order[1:])}
+print("mean phase cycles:", d, "period", int((t[20][0] - t[4][0]) / 16))

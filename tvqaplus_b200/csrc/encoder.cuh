@@ -1,19 +1,25 @@
 // EncoderBlock on one SM-resident tile:  x + pe -> n_conv x [LN -> depthwise conv -> pointwise GEMM -> ReLU -> +res] -> LN
-// (model/encoder.py:29-52).  A tile is 128 rows = floor(128/L) whole sequences; the fp32 residual stream never leaves
+// (model/encoder.py:29-52).  A tile is 128 rows = floor(128/L) whole sequences; the fp32 residual stream X never leaves
 // shared memory, the pointwise 128x128 GEMM runs on tcgen05 (split-fp16, accumulator in TMEM).
 //
-// 512 threads, one CTA per SM, persistent over tiles:
-//   phase 0   the tile's raw rows were prefetched by ONE cp.async.bulk (they are contiguous in HBM) into the region
-//             that later holds the A image; warp-per-row: + position encoding -> X (fp32, smem) and the row's LayerNorm
-//             statistics from the same registers
-//   conv      warp = 8 consecutive rows, lane = 4 channels: a register sliding window of LayerNorm-ed rows feeds the
-//             k-tap depthwise FIR (each row is normalised once, 2 FMA per element); result split to fp16 (hi, lo) and
-//             stored as the tcgen05 A operand image
-//   GEMM      thread 0: 8 K-steps x 3 MMAs (split product), weights of the conv arrive by one bulk copy that was
-//             launched under the previous epilogue
-//   epilogue  thread = (row, column quarter): X += relu(D + b); the NEXT LayerNorm's statistics are accumulated from the
-//             values being written (no extra pass over X)
+// v3: TWO CTAs per SM.  The latency chain of a tile (produce A -> MMA -> read accumulator, twice) cannot be shortened, so
+// the kernel is built to fit twice on an SM and let the hardware interleave two tiles:
+//   * the A operand of the pointwise GEMM lives in TENSOR MEMORY (tcgen05.st, two fp16 per 32-bit column, hi and lo parts
+//     64 columns each) instead of a 66 KB shared-memory image; with the 128-column accumulator a CTA owns 256 of the 512
+//     TMEM columns;
+//   * the pointwise weights stream through a 2 x 16 KB ring of K=32 chunks (cp.async.bulk from L2) instead of a resident
+//     64 KB image;
+//   * shared memory per CTA = X (66 KB) + ring (32 KB) + per-channel parameter tables (<= 13 KB)  ->  ~113 KB.
+// Thread = (row, column half) for every phase (the TMEM lane a thread may touch fixes its row), so there is no warp
+// shuffle anywhere; the two halves of a row meet through the 16 padding bytes of the row in X.
+//   phase 0   raw rows + position encoding -> X, LayerNorm statistics of the row
+//   conv      out[r,c] = db + g*sum_j w[c,j]*(x[r+j-P,c]*rstd_j - mean_j*rstd_j) + beta*sum_j w[c,j]   (taps outside the row's
+//             own sequence dropped), i.e. the LayerNorm is applied tap by tap from per-row scalars; split to fp16 (hi, lo),
+//             16 columns at a time straight into the TMEM A operand
+//   GEMM      MMA thread: 4 ring chunks x 2 K-steps x 3 MMAs (split product, A from TMEM, B from the ring)
+//   epilogue  X += relu(D + b), statistics of the NEXT LayerNorm from the values being written
 //   tail      closing LayerNorm -> store, or mask_logits + max over the sequence (model/stage.py:503)
+// Warp roles (320 threads): warps 0-7 compute, warp 8 = MMA issue, warp 9 = weight-ring copies.
 //
 // Padded tokens are processed like real ones (the reference never masks before the convs, SURVEY.md §7 quirk i); the
 // depthwise conv sees zeros outside [0, L) of its own sequence only.
@@ -25,19 +31,22 @@
 namespace stg {
 
 struct EncCfg {
-  static constexpr int XS = 132;                       // padded fp32 row stride (floats): conflict-free float4 row access
+  static constexpr int XS = 132;                       // padded fp32 row stride (floats): conflict-free row-per-lane float4 access;
+                                                       // the 4 padding floats of a row carry the half-row partial statistics
   static constexpr uint32_t X_BYTES = 128u * XS * 4u;  // 67584
-  static constexpr uint32_t LBO_A = 128u * 16u + 16u;
-  static constexpr uint32_t A_PART = 16u * LBO_A;      // 33024
-  static constexpr uint32_t A_BYTES = 2u * A_PART;     // 66048 >= 128 raw rows (65536)
-  static constexpr uint32_t LBO_B = 128u * 16u;
-  static constexpr uint32_t W_CHUNK = 2u * 8u * LBO_B;  // one kc=64 chunk: hi | lo
-  static constexpr uint32_t W_BYTES = 2u * W_CHUNK;     // 65536
-  static constexpr uint32_t OFF_A = (X_BYTES + 127u) & ~127u;
-  static constexpr uint32_t OFF_W = OFF_A + ((A_BYTES + 127u) & ~127u);
-  static constexpr uint32_t SMEM_BYTES = OFF_W + W_BYTES + 1024u;
-  static constexpr int THREADS = 512;
-  static constexpr int ROWS_PER_WARP = 8;
+  static constexpr uint32_t LBO_B = 128u * 16u;        // 2048
+  static constexpr uint32_t W_HALF = 4u * LBO_B;       // 8192: hi (or lo) part of a K=32 chunk
+  static constexpr uint32_t W_SLOT = 2u * W_HALF;      // 16384
+  static constexpr int W_SLOTS = 2;
+  static constexpr uint32_t W_SRC_CHUNK = 32768;       // stage_pack_weight(kc=64): [chunk][hi 8 k-groups | lo 8 k-groups]
+  static constexpr uint32_t OFF_W = X_BYTES;
+  static constexpr uint32_t OFF_P = OFF_W + W_SLOTS * W_SLOT;  // 100352
+  static constexpr int P_SLOTS = 2;                    // parameter tables of two convs are resident
+  static constexpr int p_floats(int ks) { return (ks + 5) * 128; }  // w[ks][128], sum_j w, ln g, ln b, dw bias, pw bias
+  static constexpr uint32_t smem_bytes(int ks) { return OFF_P + (P_SLOTS * p_floats(ks) + 2 * 128) * 4u; }
+  static constexpr int THREADS = 320;
+  static constexpr int COMPUTE = 256;
+  static constexpr uint32_t TMEM_COLS = 256;           // D 0..127 | A_hi 128..191 | A_lo 192..255
 };
 
 struct EncDev {
@@ -65,328 +74,372 @@ struct EncDev {
     if (p.timeline != nullptr && blockIdx.x == 0 && tid == 0 && tl_tile < 32)             \
       p.timeline[tl_tile * 16 + (idx)] = clock64();                                       \
   } while (0)
+#define ENC_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
 template <int KS>
-__global__ void __launch_bounds__(512, 1) encoder_kernel(EncDev p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t w_bar, mma_bar, x_bar;
+__global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t a_full, mma_done, w_full[EncCfg::W_SLOTS], w_empty[EncCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 row_stat[128];   // (mean * rstd, rstd) of the LayerNorm that reads X next
-  __shared__ float row_mask[128];
-  __shared__ int row_sid[128];       // sequence index of a tile row (r / L)
-  __shared__ float xq[2][4][128];    // cross-quarter exchange of the epilogue: [sum | sum of squares][quarter][row]
+  __shared__ float2 row_stat[128];  // (rstd, -mean*rstd) of the LayerNorm that reads X next; max-pool partials in the tail
 
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
   float* X = reinterpret_cast<float*>(smem);
-  uint8_t* sA = smem + EncCfg::OFF_A;
   uint8_t* sW = smem + EncCfg::OFF_W;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* PT = reinterpret_cast<float*>(smem + EncCfg::OFF_P);
+  constexpr int PF = (KS + 5) * 128;  // == EncCfg::p_floats(KS)
+  float* FIN = PT + EncCfg::P_SLOTS * PF;  // closing LayerNorm gamma | beta
+  constexpr int XS = EncCfg::XS;
   constexpr int P = KS / 2;
-  constexpr int RW = EncCfg::ROWS_PER_WARP;
-  constexpr int WIN = RW + 2 * P;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int L = p.L;
   const int G = 128 / L;  // sequences per tile
   const long long n_tiles = (p.n_seq + G - 1) / G;
+  const long long n_my = static_cast<long long>(blockIdx.x) < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (tid == 0) {
-    mbar_init(&w_bar, 1);
-    mbar_init(&mma_bar, 1);
-    mbar_init(&x_bar, 1);
+    mbar_init(&a_full, EncCfg::COMPUTE);
+    mbar_init(&mma_done, 1);
+    for (int i = 0; i < EncCfg::W_SLOTS; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
     mbar_fence_init();
   }
-  if (tid < 128) row_sid[tid] = static_cast<int>(tid) / L;
-  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (warp == 8) tmem_alloc<EncCfg::TMEM_COLS>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  const uint32_t idesc = make_idesc_f16(128);
-  uint32_t w_count = 0, mma_count = 0, x_count = 0;
-  int tl_tile = 0;
 
-  auto rows_of = [&](long long tile) -> int {
-    const long long seq0 = tile * G;
-    const long long n_here = (p.n_seq - seq0) < G ? (p.n_seq - seq0) : G;
-    return static_cast<int>(n_here) * L;
-  };
-  const bool blocked = (p.flags & STAGE_ENC_IN_BLOCKED) != 0;
-  const long long seq_floats = blocked ? 128ll * p.S : 128ll * L;  // floats one sequence occupies in x
-  auto fetch_tile = [&](long long tile) {  // thread 0: ONE bulk copy brings the whole tile (contiguous in either layout)
-    const uint32_t bytes = static_cast<uint32_t>(rows_of(tile) / L) * static_cast<uint32_t>(seq_floats) * 4u;
-    mbar_arrive_expect_tx(&x_bar, bytes);
-    bulk_g2s(sA, p.x + tile * G * seq_floats, bytes, &x_bar);
-  };
-  if (tid == 0 && static_cast<long long>(blockIdx.x) < n_tiles) {
-    fetch_tile(blockIdx.x);
-    mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
-    bulk_g2s(sW, p.pw[0], EncCfg::W_BYTES, &w_bar);
-  }
-
-  // position-encoding rows (the same for every tile) and masks of my 8 rows of a tile: plain L2 loads (shared memory
-  // takes the whole L1 carve-out), requested one phase ahead so that their latency never sits in phase 0
-  float4 pe_r[RW];
-  float m_r[RW];
-  auto prefetch_rows = [&](long long tile) {
-    const int nv = rows_of(tile);
+  if (warp < 8) {
+    // =================================================================== compute warps: thread = (row, column half)
+    const int r = (warp & 3) * 32 + lane, h = warp >> 2;
+    const uint32_t lane_off = ((warp & 3) * 32u) << 16;
+    const int sq = r / L, pos = r - sq * L;  // my row's sequence within the tile and position within the sequence
+    // tap j of the depthwise conv lies inside my row's own sequence.  Rows behind the last sequence of a tile belong to no
+    // sequence; nothing reads what they produce, so they run as interior rows (every tap on, neighbours clamped to the tile)
+    uint32_t vbits = 0;
 #pragma unroll
-    for (int rr = 0; rr < RW; ++rr) {
-      const int r = warp * RW + rr;
-      pe_r[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-      m_r[rr] = 0.f;
-      if (r < nv) {
-        const int pos = r - (r / L) * L;
-        if (!(p.flags & STAGE_ENC_NO_PE) && !blocked) pe_r[rr] = __ldg(reinterpret_cast<const float4*>(p.pe + pos * 128) + lane);
-        if (p.mask != nullptr) m_r[rr] = __ldg(p.mask + tile * G * L + r);
-      }
+    for (int j = 0; j < KS; ++j) {
+      const int pp = pos + j - P;
+      if (sq >= G || (pp >= 0 && pp < L)) vbits |= 1u << j;
     }
-  };
-  prefetch_rows(blockIdx.x);
+    const bool interior = vbits == (1u << KS) - 1u;
+    float* xrow = X + r * XS;
+    float* xh = xrow + h * 64;
+    const bool blocked = (p.flags & STAGE_ENC_IN_BLOCKED) != 0;
+    const bool use_pe = !(p.flags & STAGE_ENC_NO_PE);
+    const bool fin = !(p.flags & STAGE_ENC_NO_FINAL_LN);
+    const bool resident = p.n_conv <= EncCfg::P_SLOTS;
+    uint32_t done_cnt = 0;
+    int tl_tile = 0;
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long seq0 = tile * G;
-    const int n_valid = rows_of(tile);
-    const int n_here = n_valid / L;
-
-    // ---- phase 0: raw rows (smem, prefetched) + pe -> X, first LayerNorm statistics.  warp per row, lane = 4 channels
-    //      (the position rows and masks of this tile were requested from L2 under the previous tile's tail)
-    ENC_STAMP(0);
-    mbar_wait(&x_bar, x_count & 1u, 22);
-    ++x_count;
-    ENC_STAMP(1);
-    if (blocked) {
-      // blocked input: thread = (row, column quarter) like the epilogue; raw float4 (row, c4) at (g*32 + c4)*S + pos, the
-      // position table at c4*L + pos -> lanes (= rows) read consecutive addresses in shared and global memory alike
-      const int r = (warp & 3) * 32 + lane, qd = warp >> 2;
-      const int g = row_sid[r], pos = r - g * L;
-      const float4* raw = reinterpret_cast<const float4*>(sA) + (g * 32 + qd * 8) * p.S + pos;
-      const float4* pe4 = reinterpret_cast<const float4*>(p.pe) + (qd * 8) * L + pos;
-      float* xr = X + r * EncCfg::XS + qd * 32;
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n_valid) {
-          v = raw[j * p.S];
-          if (!(p.flags & STAGE_ENC_NO_PE)) {
-            const float4 e = __ldg(pe4 + j * L);
-            v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
-          }
-        }
-        *reinterpret_cast<float4*>(xr + j * 4) = v;
-        s1 += (v.x + v.y) + (v.z + v.w);
-        s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
-      }
-      xq[0][qd][r] = s1;
-      xq[1][qd][r] = s2;
-      if (qd == 0) row_mask[r] = (r < n_valid && p.mask != nullptr) ? __ldg(p.mask + seq0 * L + r) : 0.f;
-      __syncthreads();
+    // per-channel tables of conv ci -> parameter slot s (threads 0..127, one channel each)
+    auto load_params = [&](int ci, int s) {
       if (tid < 128) {
-        const float mean = ((xq[0][0][tid] + xq[0][1][tid]) + (xq[0][2][tid] + xq[0][3][tid])) * (1.f / 128.f);
-        const float ex2 = ((xq[1][0][tid] + xq[1][1][tid]) + (xq[1][2][tid] + xq[1][3][tid])) * (1.f / 128.f);
-        const float rs = 1.f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
-        row_stat[tid] = make_float2(mean * rs, rs);
-      }
-    } else {
-      const float4* raw = reinterpret_cast<const float4*>(sA);
+        float* T = PT + s * PF;
+        const int c = tid;
+        float sw = 0.f;
 #pragma unroll
-      for (int rr = 0; rr < RW; ++rr) {
-        const int r = warp * RW + rr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n_valid) {
-          v = raw[r * 32 + lane];
-          const float4 e = pe_r[rr];
-          v = make_float4(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+        for (int j = 0; j < KS; ++j) {
+          const float w = __ldg(p.dw_w[ci] + c * KS + j);
+          T[j * 128 + c] = w;
+          sw += w;
         }
-        *reinterpret_cast<float4*>(X + r * EncCfg::XS + lane * 4) = v;
-        const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-        const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 128.f);
-        if (lane == 0) {
-          const float rs = 1.f / sqrtf(var + 1e-5f);
-          row_stat[r] = make_float2(mean * rs, rs);
-          row_mask[r] = m_r[rr];
-        }
+        T[KS * 128 + c] = sw;
+        T[(KS + 1) * 128 + c] = p.ln_g[ci] ? __ldg(p.ln_g[ci] + c) : 1.f;
+        T[(KS + 2) * 128 + c] = p.ln_b[ci] ? __ldg(p.ln_b[ci] + c) : 0.f;
+        T[(KS + 3) * 128 + c] = __ldg(p.dw_b[ci] + c);
+        T[(KS + 4) * 128 + c] = __ldg(p.pw_b[ci] + c);
       }
+    };
+    if (resident)
+      for (int ci = 0; ci < p.n_conv; ++ci) load_params(ci, ci);
+    if (tid < 128) {
+      FIN[tid] = fin ? __ldg(p.fin_g + tid) : 1.f;
+      FIN[128 + tid] = fin ? __ldg(p.fin_b + tid) : 0.f;
     }
-    __syncthreads();
-    ENC_STAMP(2);
+    ENC_BAR();
 
-    for (int ci = 0; ci < p.n_conv; ++ci) {
-      // ---- conv: LayerNorm applied once per row into a register window, k-tap FIR, split -> A image
-      {
-        const bool idn = (p.ln_g[ci] == nullptr);  // no LayerNorm in front of this conv
-        const float4 g4 = idn ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(reinterpret_cast<const float4*>(p.ln_g[ci]) + lane);
-        const float4 b4 = idn ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.ln_b[ci]) + lane);
-        const float4 db = __ldg(reinterpret_cast<const float4*>(p.dw_b[ci]) + lane);
-        float wt[4][KS];
+    // statistics of my row from the two half-row partials parked in the row's padding: (rstd, -mean*rstd)
+    auto combine = [&]() -> float2 {
+      const float4 q = *reinterpret_cast<const float4*>(xrow + 128);
+      const float mean = (q.x + q.z) * (1.f / 128.f);
+      const float ex2 = (q.y + q.w) * (1.f / 128.f);
+      const float rs = 1.f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+      return make_float2(rs, -mean * rs);
+    };
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long seq0 = tile * G;
+      const int n_here = static_cast<int>((p.n_seq - seq0) < G ? (p.n_seq - seq0) : G);
+      const int n_valid = n_here * L;
+      const bool live = r < n_valid;
+      ENC_STAMP(0);
+      const float m_row = (live && p.mask != nullptr) ? __ldg(p.mask + seq0 * L + r) : 0.f;
+
+      // ---- phase 0: raw rows (+ position encoding) -> X, first LayerNorm statistics
+      float s1 = 0.f, s2 = 0.f;
+      if (blocked) {
+        // float4 (row, c4) of sequence i at (i*32 + c4)*S + row, the position table at c4*L + pos: lanes = rows read runs
+        const float4* src = reinterpret_cast<const float4*>(p.x) + ((seq0 + sq) * 32 + h * 16) * p.S + pos;
+        const float4* pe4 = reinterpret_cast<const float4*>(p.pe) + (h * 16) * L + pos;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int b = 0; b < 2; ++b) {
+          float4 v[8], e[8];
 #pragma unroll
-          for (int j = 0; j < KS; ++j) wt[c][j] = __ldg(p.dw_w[ci] + (lane * 4 + c) * KS + j);
-        const int r0 = warp * RW;
-        float4 win[WIN];
-        int sid[WIN];
+          for (int j = 0; j < 8; ++j) {
+            v[j] = live ? __ldg(src + static_cast<size_t>(b * 8 + j) * p.S) : make_float4(0.f, 0.f, 0.f, 0.f);
+            e[j] = (live && use_pe) ? __ldg(pe4 + (b * 8 + j) * L) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-        for (int i = 0; i < WIN; ++i) {
-          const int q = r0 - P + i;
-          win[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          sid[i] = -1;
-          if (q >= 0 && q < 128) {
-            const float4 v = *reinterpret_cast<const float4*>(X + q * EncCfg::XS + lane * 4);
-            const float2 st = idn ? make_float2(0.f, 1.f) : row_stat[q];
-            win[i] = make_float4(fmaf(fmaf(v.x, st.y, -st.x), g4.x, b4.x), fmaf(fmaf(v.y, st.y, -st.x), g4.y, b4.y),
-                                 fmaf(fmaf(v.z, st.y, -st.x), g4.z, b4.z), fmaf(fmaf(v.w, st.y, -st.x), g4.w, b4.w));
-            sid[i] = row_sid[q];
+          for (int j = 0; j < 8; ++j) {
+            const float4 o = make_float4(v[j].x + e[j].x, v[j].y + e[j].y, v[j].z + e[j].z, v[j].w + e[j].w);
+            *reinterpret_cast<float4*>(xh + (b * 8 + j) * 4) = o;
+            s1 += (o.x + o.y) + (o.z + o.w);
+            s2 = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, s2))));
           }
         }
+      } else {
+        // row-major input: warp per row so that a row is one 512-byte request, 4 rows in flight per warp
 #pragma unroll
-        for (int o = 0; o < RW; ++o) {
-          const int r = r0 + o;
-          const int me = sid[o + P];
-          float o0 = db.x, o1 = db.y, o2 = db.z, o3 = db.w;
+        for (int b = 0; b < 4; ++b) {
+          float4 v[4], e[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = static_cast<int>(warp) + 8 * (b * 4 + i);
+            const bool on = rr < n_valid;
+            v[i] = on ? __ldg(reinterpret_cast<const float4*>(p.x + (seq0 * L + rr) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            e[i] = (on && use_pe) ? __ldg(reinterpret_cast<const float4*>(p.pe + (rr - (rr / L) * L) * 128) + lane)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = static_cast<int>(warp) + 8 * (b * 4 + i);
+            *reinterpret_cast<float4*>(X + rr * XS + lane * 4) =
+                make_float4(v[i].x + e[i].x, v[i].y + e[i].y, v[i].z + e[i].z, v[i].w + e[i].w);
+          }
+        }
+        ENC_BAR();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 o = *reinterpret_cast<const float4*>(xh + j * 4);
+          s1 += (o.x + o.y) + (o.z + o.w);
+          s2 = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, s2))));
+        }
+      }
+      *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1, s2);
+      ENC_BAR();
+      float2 my_stat = combine();
+      if (h == 0) row_stat[r] = my_stat;
+      ENC_BAR();
+      ENC_STAMP(1);
+
+      for (int ci = 0; ci < p.n_conv; ++ci) {
+        const int ps = resident ? ci : (ci & 1);
+        if (!resident) {  // more convs than parameter slots: (re)load this conv's tables
+          load_params(ci, ps);
+          ENC_BAR();
+        }
+        const float* T = PT + ps * PF;
+        // ---- conv: LayerNorm applied tap by tap from the per-row scalars, k-tap FIR, split -> TMEM A operand
+        {
+          const bool idn = (p.ln_g[ci] == nullptr);  // no LayerNorm in front of this conv
+          float rs[KS], nm[KS];
+          int xo[KS];
 #pragma unroll
           for (int j = 0; j < KS; ++j) {
-            if (sid[o + j] == me) {  // warp-uniform: the tap lies inside this row's own sequence
-              o0 = fmaf(wt[0][j], win[o + j].x, o0);
-              o1 = fmaf(wt[1][j], win[o + j].y, o1);
-              o2 = fmaf(wt[2][j], win[o + j].z, o2);
-              o3 = fmaf(wt[3][j], win[o + j].w, o3);
+            const int q = min(max(r + j - P, 0), 127);
+            const bool on = (vbits >> j) & 1u;
+            const float2 st = idn ? make_float2(1.f, 0.f) : row_stat[q];
+            rs[j] = on ? st.x : 0.f;
+            nm[j] = on ? st.y : 0.f;
+            xo[j] = q * XS + h * 64;
+          }
+          const float* Th = T + h * 64;
+#pragma unroll 1
+          for (int cg = 0; cg < 4; ++cg) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int col = cg * 16 + c4 * 4;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < KS; ++j) {
+                const float4 xv = *reinterpret_cast<const float4*>(X + xo[j] + col);
+                const float4 w = *reinterpret_cast<const float4*>(Th + j * 128 + col);
+                acc.x = fmaf(w.x, fmaf(xv.x, rs[j], nm[j]), acc.x);
+                acc.y = fmaf(w.y, fmaf(xv.y, rs[j], nm[j]), acc.y);
+                acc.z = fmaf(w.z, fmaf(xv.z, rs[j], nm[j]), acc.z);
+                acc.w = fmaf(w.w, fmaf(xv.w, rs[j], nm[j]), acc.w);
+              }
+              float4 sw = *reinterpret_cast<const float4*>(Th + KS * 128 + col);
+              if (!interior) {  // a row near a sequence end: beta reaches the output only through the taps that exist
+#pragma unroll
+                for (int j = 0; j < KS; ++j) {
+                  if (!((vbits >> j) & 1u)) {  // at most P taps per row, and only in the warps that hold a sequence end
+                    const float4 w = *reinterpret_cast<const float4*>(Th + j * 128 + col);
+                    sw.x -= w.x; sw.y -= w.y; sw.z -= w.z; sw.w -= w.w;
+                  }
+                }
+              }
+              const float4 g4 = *reinterpret_cast<const float4*>(Th + (KS + 1) * 128 + col);
+              const float4 b4 = *reinterpret_cast<const float4*>(Th + (KS + 2) * 128 + col);
+              const float4 d4 = *reinterpret_cast<const float4*>(Th + (KS + 3) * 128 + col);
+              const float o0 = fmaf(g4.x, acc.x, fmaf(b4.x, sw.x, d4.x));
+              const float o1 = fmaf(g4.y, acc.y, fmaf(b4.y, sw.y, d4.y));
+              const float o2 = fmaf(g4.z, acc.z, fmaf(b4.z, sw.z, d4.z));
+              const float o3 = fmaf(g4.w, acc.w, fmaf(b4.w, sw.w, d4.w));
+              split2(o0, o1, hi[c4 * 2], lo[c4 * 2]);
+              split2(o2, o3, hi[c4 * 2 + 1], lo[c4 * 2 + 1]);
+            }
+            const uint32_t ta = tbase + lane_off + 128 + h * 32 + cg * 8;
+            tmem_st8(ta, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+            tmem_st8(ta + 64, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&a_full);
+        if (ci < 2) ENC_STAMP(2 + ci * 4);
+
+        // ---- pointwise GEMM on the MMA warp
+        mbar_wait(&mma_done, done_cnt & 1u, 21);
+        ++done_cnt;
+        tc_fence_after();
+        if (ci < 2) ENC_STAMP(3 + ci * 4);
+
+        // ---- epilogue  X += relu(D + b)  + statistics of the new row
+        {
+          const float* pwb = T + (KS + 4) * 128 + h * 64;
+          const bool relu = !(p.flags & STAGE_ENC_NO_RELU), resid = !(p.flags & STAGE_ENC_NO_RESIDUAL);
+          s1 = 0.f;
+          s2 = 0.f;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld16(tbase + lane_off + h * 64 + half * 32, v);
+            tmem_ld16(tbase + lane_off + h * 64 + half * 32 + 16, v + 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(pwb + half * 32 + j);
+              float4 xv = *reinterpret_cast<float4*>(xh + half * 32 + j);
+              float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+              if (relu) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
+              if (resid) xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
+              else xv = dv;
+              *reinterpret_cast<float4*>(xh + half * 32 + j) = xv;
+              s1 += (xv.x + xv.y) + (xv.z + xv.w);
+              s2 = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, s2))));
             }
           }
-          uint2 hi, lo;
-          split2(o0, o1, hi.x, lo.x);
-          split2(o2, o3, hi.y, lo.y);
-          uint8_t* dst = sA + (lane >> 1) * EncCfg::LBO_A + r * 16 + (lane & 1) * 8;
-          *reinterpret_cast<uint2*>(dst) = hi;
-          *reinterpret_cast<uint2*>(dst + EncCfg::A_PART) = lo;
+          *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1, s2);
         }
-      }
-      ENC_STAMP(3 + ci * 5);
-      fence_async_smem();
-      __syncthreads();
-      ENC_STAMP(4 + ci * 5);
-
-      // ---- pointwise GEMM  D[128 x 128] = A[128 x 128] . W^T   (8 K-steps x 3 MMAs)
-      if (tid == 0) {
-        mbar_wait(&w_bar, w_count & 1u, 20);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA), w0 = smem_u32(sW);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t wa = w0 + (ks >> 2) * EncCfg::W_CHUNK + (ks & 3) * 2 * EncCfg::LBO_B;
-          const uint64_t a_hi = make_smem_desc(a0 + ks * 2 * EncCfg::LBO_A, EncCfg::LBO_A, 128);
-          const uint64_t a_lo = make_smem_desc(a0 + EncCfg::A_PART + ks * 2 * EncCfg::LBO_A, EncCfg::LBO_A, 128);
-          const uint64_t b_hi = make_smem_desc(wa, EncCfg::LBO_B, 128);
-          const uint64_t b_lo = make_smem_desc(wa + EncCfg::W_CHUNK / 2, EncCfg::LBO_B, 128);
-          umma_split3(tbase, a_hi, a_lo, b_hi, b_lo, idesc, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(&mma_bar);
-      }
-      ++w_count;
-      mbar_wait(&mma_bar, mma_count & 1u, 21);
-      ++mma_count;
-      tc_fence_after();
-      ENC_STAMP(5 + ci * 5);
-      if (tid == 0) {
-        // weights of the next conv (or conv 0 of this CTA's next tile) stream in under the epilogue; after the last conv
-        // the A region is free as well and receives the next tile's raw rows
-        const int nxt = ci + 1;
-        const bool more = tile + gridDim.x < n_tiles;
-        if (nxt < p.n_conv || more) {
-          mbar_arrive_expect_tx(&w_bar, EncCfg::W_BYTES);
-          bulk_g2s(sW, p.pw[nxt < p.n_conv ? nxt : 0], EncCfg::W_BYTES, &w_bar);
-        }
-        if (nxt == p.n_conv && more) fetch_tile(tile + gridDim.x);
+        tc_fence_before();
+        ENC_BAR();
+        my_stat = combine();
+        if (h == 0) row_stat[r] = my_stat;
+        ENC_BAR();
+        if (ci < 2) ENC_STAMP(4 + ci * 4);
       }
 
-      // ---- epilogue  X += relu(D + b)   (thread = row x column quarter) + statistics of the new row
+      // ---- closing LayerNorm (in place; mask_logits for the max-pool), then coalesced store / column-wise max
       {
-        const int r = (warp & 3) * 32 + lane, qd = warp >> 2;
-        const int cb = qd * 32;
-        const uint32_t trow = tbase + (((warp & 3) * 32u) << 16) + cb;
-        float* xr = X + r * EncCfg::XS + cb;
-        float v[32];
-        tmem_ld16(trow, v);
-        tmem_ld16(trow + 16, v + 16);
-        tmem_wait_ld();
-        float s1 = 0.f, s2 = 0.f;
+        const float rsn = fin ? my_stat.x : 1.f, nmn = fin ? my_stat.y : 0.f;
+        const float off = (1.f - m_row) * STG_NEG;  // mask_logits: x*m + (1-m)*(-1e10)
+        const float* fg = FIN + h * 64;
+        const float* fb = FIN + 128 + h * 64;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.pw_b[ci] + cb + j));
-          float4 xv = *reinterpret_cast<float4*>(xr + j);
-          float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
-          if (!(p.flags & STAGE_ENC_NO_RELU)) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
-          if (p.flags & STAGE_ENC_NO_RESIDUAL) xv = dv;
-          else xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
-          *reinterpret_cast<float4*>(xr + j) = xv;
-          s1 += (xv.x + xv.y) + (xv.z + xv.w);
-          s2 = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, s2))));
+        for (int j = 0; j < 64; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(xh + j);
+          const float4 g4 = *reinterpret_cast<const float4*>(fg + j), b4 = *reinterpret_cast<const float4*>(fb + j);
+          float4 o = make_float4(fmaf(fmaf(v.x, rsn, nmn), g4.x, b4.x), fmaf(fmaf(v.y, rsn, nmn), g4.y, b4.y),
+                                 fmaf(fmaf(v.z, rsn, nmn), g4.z, b4.z), fmaf(fmaf(v.w, rsn, nmn), g4.w, b4.w));
+          if (p.out_mode != 0) o = make_float4(o.x * m_row + off, o.y * m_row + off, o.z * m_row + off, o.w * m_row + off);
+          *reinterpret_cast<float4*>(xh + j) = o;
         }
-        xq[0][qd][r] = s1;
-        xq[1][qd][r] = s2;
       }
-      ENC_STAMP(6 + ci * 5);
-      tc_fence_before();
-      __syncthreads();
-      if (tid < 128) {
-        const float mean = ((xq[0][0][tid] + xq[0][1][tid]) + (xq[0][2][tid] + xq[0][3][tid])) * (1.f / 128.f);
-        const float ex2 = ((xq[1][0][tid] + xq[1][1][tid]) + (xq[1][2][tid] + xq[1][3][tid])) * (1.f / 128.f);
-        const float rs = 1.f / sqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
-        row_stat[tid] = make_float2(mean * rs, rs);
+      ENC_BAR();
+      ENC_STAMP(12);
+      if (p.out_mode == 0) {
+        for (int rr = warp; rr < n_valid; rr += 8)
+          *reinterpret_cast<float4*>(p.y + (seq0 * L + rr) * 128 + lane * 4) = *reinterpret_cast<const float4*>(X + rr * XS + lane * 4);
+      } else {
+        const int c = tid & 127, part = tid >> 7;
+        float* pm = reinterpret_cast<float*>(row_stat);  // [2][128]; row_stat is dead until the next tile's phase 0
+        if (G == 1) {  // one long sequence: the two thread halves take half the rows each
+          const int half_rows = (L + 1) >> 1;
+          const int lo = part * half_rows, hi = min(L, lo + half_rows);
+          float mx = -3.0e38f;
+#pragma unroll 4
+          for (int rr = lo; rr < hi; ++rr) mx = fmaxf(mx, X[rr * XS + c]);
+          pm[part * 128 + c] = mx;
+          ENC_BAR();
+          if (part == 0 && n_here > 0) p.y[seq0 * 128 + c] = fmaxf(pm[c], pm[128 + c]);
+        } else {       // several short sequences: they alternate between the thread halves
+          for (int g = part; g < n_here; g += 2) {
+            float mx = -3.0e38f;
+            for (int rr = g * L; rr < g * L + L; ++rr) mx = fmaxf(mx, X[rr * XS + c]);
+            p.y[(seq0 + g) * 128 + c] = mx;
+          }
+        }
       }
-      __syncthreads();
-      ENC_STAMP(7 + ci * 5);
+      ENC_STAMP(13);
+      ENC_BAR();  // X / row_stat are rewritten by the next tile's phase 0
+      ENC_STAMP(14);
+      ++tl_tile;
     }
-    prefetch_rows(tile + gridDim.x);  // (a tile past the end has no rows: every load is predicated off)
-
-    // ---- closing LayerNorm (+ store, or mask_logits written back to X for the max-pool).  warp per row
-    {
-      const bool fin = !(p.flags & STAGE_ENC_NO_FINAL_LN);
-      const float4 g4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_g) + lane) : make_float4(1.f, 1.f, 1.f, 1.f);
-      const float4 b4 = fin ? __ldg(reinterpret_cast<const float4*>(p.fin_b) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (warp == 8 && lane == 0) {
+    // =================================================================== MMA issue (one thread)
+    const uint32_t idesc = make_idesc_f16(128);
+    const uint32_t w0 = smem_u32(sW);
+    uint32_t q = 0, ph = 0;
+    for (long long t = 0; t < n_my; ++t) {
+      for (int ci = 0; ci < p.n_conv; ++ci) {
+        mbar_wait(&a_full, ph & 1u, 22);  // all 256 producers have stored (and fenced) their part of A; D has been read
+        ++ph;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c, ++q) {
+          const uint32_t slot = q & 1u;
+          mbar_wait(&w_full[slot], (q >> 1) & 1u, 23);
+          tc_fence_after();
 #pragma unroll
-      for (int rr = 0; rr < RW; ++rr) {
-        const int r = warp * RW + rr;
-        const float4 v = *reinterpret_cast<const float4*>(X + r * EncCfg::XS + lane * 4);
-        const float2 st = fin ? row_stat[r] : make_float2(0.f, 1.f);
-        float4 o = make_float4(fmaf(fmaf(v.x, st.y, -st.x), g4.x, b4.x), fmaf(fmaf(v.y, st.y, -st.x), g4.y, b4.y),
-                               fmaf(fmaf(v.z, st.y, -st.x), g4.z, b4.z), fmaf(fmaf(v.w, st.y, -st.x), g4.w, b4.w));
-        if (p.out_mode == 0) {
-          if (r < n_valid) *reinterpret_cast<float4*>(p.y + (seq0 * L + r) * 128 + lane * 4) = o;
-        } else {
-          const float m = row_mask[r], off = (1.f - m) * STG_NEG;  // mask_logits: x*m + (1-m)*(-1e10)
-          o = make_float4(o.x * m + off, o.y * m + off, o.z * m + off, o.w * m + off);
-          *reinterpret_cast<float4*>(X + r * EncCfg::XS + lane * 4) = o;
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const uint32_t ks = c * 2 + k2;
+            const uint32_t a_hi = tbase + 128 + ks * 8, a_lo = tbase + 192 + ks * 8;
+            const uint32_t wa = w0 + slot * EncCfg::W_SLOT + k2 * 2 * EncCfg::LBO_B;
+            const uint64_t b_hi = make_smem_desc(wa, EncCfg::LBO_B, 128);
+            const uint64_t b_lo = make_smem_desc(wa + EncCfg::W_HALF, EncCfg::LBO_B, 128);
+            umma_f16_ts(tbase, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+            umma_f16_ts(tbase, a_hi, b_lo, idesc, 1u);
+            umma_f16_ts(tbase, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&w_empty[slot]);
         }
+        umma_commit(&mma_done);
       }
     }
-    if (p.out_mode != 0) {
-      __syncthreads();
-      // column-wise max over each sequence: thread = (channel, quarter of the sequence's rows), quarters merged through xq
-      const int c = tid & 127, part = tid >> 7;
-      const int span = (L + 3) / 4;
-      for (int g = 0; g < n_here; ++g) {
-        const int lo = g * L + part * span;
-        const int hi = min(g * L + L, lo + span);
-        float mx = -3.0e38f;
-        for (int r = lo; r < hi; ++r) mx = fmaxf(mx, X[r * EncCfg::XS + c]);
-        xq[g & 1][part][c] = mx;
-        __syncthreads();
-        if (part == 0) {
-          p.y[(seq0 + g) * 128 + c] = fmaxf(fmaxf(xq[g & 1][0][c], xq[g & 1][1][c]), fmaxf(xq[g & 1][2][c], xq[g & 1][3][c]));
-        }
-      }
+  } else if (warp == 9 && lane == 0) {
+    // =================================================================== weight ring (one thread): chunk q = (tile, conv, K=32 chunk)
+    const long long total = n_my * p.n_conv * 4;
+    for (long long q = 0; q < total; ++q) {
+      const uint32_t slot = static_cast<uint32_t>(q & 1), use = static_cast<uint32_t>(q >> 1);
+      if (use > 0) mbar_wait(&w_empty[slot], (use - 1u) & 1u, 24);  // the MMAs that read the slot's previous chunk have completed
+      const int ci = static_cast<int>((q >> 2) % p.n_conv), c = static_cast<int>(q & 3);
+      const uint8_t* src = p.pw[ci] + (c >> 1) * EncCfg::W_SRC_CHUNK + (c & 1) * EncCfg::W_HALF;
+      uint8_t* dst = sW + slot * EncCfg::W_SLOT;
+      mbar_arrive_expect_tx(&w_full[slot], EncCfg::W_SLOT);
+      bulk_g2s(dst, src, EncCfg::W_HALF, &w_full[slot]);                                         // hi part: k-groups 4*(c&1)..+4
+      bulk_g2s(dst + EncCfg::W_HALF, src + EncCfg::W_SRC_CHUNK / 2, EncCfg::W_HALF, &w_full[slot]);  // lo part
     }
-    ENC_STAMP(14);
-    __syncthreads();
-    ENC_STAMP(15);
-    ++tl_tile;
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tbase);
+  if (warp == 8) tmem_dealloc<EncCfg::TMEM_COLS>(tbase);
 }
 
 }  // namespace stg

@@ -31,12 +31,14 @@ static int launch_linear(const LinearDev& d, cudaStream_t s) {
 
 template <int KS>
 static int launch_encoder(const EncDev& d, cudaStream_t s) {
-  int rc = set_smem(encoder_kernel<KS>, EncCfg::SMEM_BYTES, "encoder");
+  constexpr size_t smem = EncCfg::smem_bytes(KS);
+  int rc = set_smem(encoder_kernel<KS>, smem, "encoder");
   if (rc) return rc;
   const int G = 128 / d.L;
   const long long tiles = (d.n_seq + G - 1) / G;
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  encoder_kernel<KS><<<grid, EncCfg::THREADS, EncCfg::SMEM_BYTES, s>>>(d);
+  const long long slots = 2ll * num_sms();  // two CTAs fit on an SM (shared memory, 256 TMEM columns each)
+  const int grid = static_cast<int>(tiles < slots ? tiles : slots);
+  encoder_kernel<KS><<<grid, EncCfg::THREADS, smem, s>>>(d);
   return check_launch("encoder");
 }
 }  // namespace
@@ -141,9 +143,6 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
   const int S = stage_blocked_stride(a->L);
-  if (a->flags & STAGE_ENC_IN_BLOCKED)
-    STG_REQUIRE(static_cast<size_t>(128 / a->L) * 32 * S * 16 <= EncCfg::A_BYTES, STAGE_E_UNSUPPORTED,
-                "encoder: blocked input with L=%d does not fit the tile buffer (use the row-major layout)", a->L);
   EncDev d;
   d.S = S;
   d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;

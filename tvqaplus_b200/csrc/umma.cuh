@@ -42,24 +42,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out: with the default
+// hint a waiting thread comes back every few dozen cycles and its polling loop competes with the working warps for issue
+// slots (measured: 30 % of all executed instructions of the encoder kernel), so every wait passes an explicit, long hint.
+#define STG_MBAR_SUSPEND_NS 20000u
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(STG_MBAR_SUSPEND_NS)
       : "memory");
   return ok;
 }
-// Bounded wait: try_wait suspends in hardware for a while per attempt, so ~4M attempts is seconds.
-// On timeout the error flag is raised and the caller carries on with garbage (host checks the flag).
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait (4 s of wall clock).  On timeout the error flag is raised and the caller carries on with garbage (the host
+// checks the flag) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned code = 1) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
-    if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      atomicMax(&g_dev_error, 0x100u + code);
+      return;
+    }
   }
-  atomicMax(&g_dev_error, 0x100u + code);
 }
 
 // ------------------------------------------------------------------------------------------------

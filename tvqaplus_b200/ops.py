@@ -160,8 +160,9 @@ def blocked_stride(L: int) -> int:
 
 
 def blocked_fits(L: int) -> bool:
-    """Can the encoder kernel take sequences of length L in the blocked layout (whole tile in one 66 KB buffer)?"""
-    return 0 < L <= 128 and (128 // L) * 32 * blocked_stride(L) * 16 <= 66048
+    """Can the encoder kernel take sequences of length L in the blocked layout?  (Any tile-sized sequence: the kernel reads
+    the blocked rows straight from global memory, one row per lane.)"""
+    return 0 < L <= 128
 
 
 def blocked_pe(pe: torch.Tensor, L: int) -> torch.Tensor:
