@@ -177,10 +177,17 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
       const int n_valid = n_here * L;
       const bool live = r < n_valid;
       ENC_STAMP(0);
+      if (tid == 0 && tile + gridDim.x < n_tiles) {  // the next tile of this CTA starts its way into L2 now (contiguous in both layouts)
+        const long long nseq0 = (tile + gridDim.x) * G;
+        const long long nn = (p.n_seq - nseq0) < G ? (p.n_seq - nseq0) : G;
+        const float* nx = p.x + nseq0 * (blocked ? 128ll * p.S : 128ll * L);
+        const uint32_t nbytes = static_cast<uint32_t>(nn) * (blocked ? 512u * p.S : 512u * L);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(nbytes) : "memory");
+      }
       const float m_row = (live && p.mask != nullptr) ? __ldg(p.mask + seq0 * L + r) : 0.f;
 
       // ---- phase 0: raw rows (+ position encoding) -> X, first LayerNorm statistics
-      float s1 = 0.f, s2 = 0.f;
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);  // packed partial sums: (even, odd) float2 lanes
       if (blocked) {
         // float4 (row, c4) of sequence i at (i*32 + c4)*S + row, the position table at c4*L + pos: lanes = rows read runs
         const float4* src = reinterpret_cast<const float4*>(p.x) + ((seq0 + sq) * 32 + h * 16) * p.S + pos;
@@ -195,10 +202,10 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 o = make_float4(v[j].x + e[j].x, v[j].y + e[j].y, v[j].z + e[j].z, v[j].w + e[j].w);
-            *reinterpret_cast<float4*>(xh + (b * 8 + j) * 4) = o;
-            s1 += (o.x + o.y) + (o.z + o.w);
-            s2 = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, s2))));
+            const float2 a = add2(lo2(v[j]), lo2(e[j])), c = add2(hi2(v[j]), hi2(e[j]));
+            *reinterpret_cast<float4*>(xh + (b * 8 + j) * 4) = make_float4(a.x, a.y, c.x, c.y);
+            s1 = add2(s1, add2(a, c));
+            s2 = fma2(a, a, fma2(c, c, s2));
           }
         }
       } else {
@@ -225,11 +232,11 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 o = *reinterpret_cast<const float4*>(xh + j * 4);
-          s1 += (o.x + o.y) + (o.z + o.w);
-          s2 = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, s2))));
+          s1 = add2(s1, add2(lo2(o), hi2(o)));
+          s2 = fma2(lo2(o), lo2(o), fma2(hi2(o), hi2(o), s2));
         }
       }
-      *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1, s2);
+      *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1.x + s1.y, s2.x + s2.y);
       ENC_BAR();
       float2 my_stat = combine();
       if (h == 0) row_stat[r] = my_stat;
@@ -246,15 +253,15 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
         // ---- conv: LayerNorm applied tap by tap from the per-row scalars, k-tap FIR, split -> TMEM A operand
         {
           const bool idn = (p.ln_g[ci] == nullptr);  // no LayerNorm in front of this conv
-          float rs[KS], nm[KS];
+          float2 rs[KS], nm[KS];  // (rstd, rstd), (-mean*rstd, -mean*rstd) of the tap rows; 0 for a tap outside the sequence
           int xo[KS];
 #pragma unroll
           for (int j = 0; j < KS; ++j) {
             const int q = min(max(r + j - P, 0), 127);
             const bool on = (vbits >> j) & 1u;
             const float2 st = idn ? make_float2(1.f, 0.f) : row_stat[q];
-            rs[j] = on ? st.x : 0.f;
-            nm[j] = on ? st.y : 0.f;
+            rs[j] = dup2(on ? st.x : 0.f);
+            nm[j] = dup2(on ? st.y : 0.f);
             xo[j] = q * XS + h * 64;
           }
           const float* Th = T + h * 64;
@@ -264,35 +271,31 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int col = cg * 16 + c4 * 4;
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
               for (int j = 0; j < KS; ++j) {
                 const float4 xv = *reinterpret_cast<const float4*>(X + xo[j] + col);
                 const float4 w = *reinterpret_cast<const float4*>(Th + j * 128 + col);
-                acc.x = fmaf(w.x, fmaf(xv.x, rs[j], nm[j]), acc.x);
-                acc.y = fmaf(w.y, fmaf(xv.y, rs[j], nm[j]), acc.y);
-                acc.z = fmaf(w.z, fmaf(xv.z, rs[j], nm[j]), acc.z);
-                acc.w = fmaf(w.w, fmaf(xv.w, rs[j], nm[j]), acc.w);
+                a0 = fma2(lo2(w), fma2(lo2(xv), rs[j], nm[j]), a0);
+                a1 = fma2(hi2(w), fma2(hi2(xv), rs[j], nm[j]), a1);
               }
-              float4 sw = *reinterpret_cast<const float4*>(Th + KS * 128 + col);
+              const float4 sw4 = *reinterpret_cast<const float4*>(Th + KS * 128 + col);
+              float2 sw0 = lo2(sw4), sw1 = hi2(sw4);
               if (!interior) {  // a row near a sequence end: beta reaches the output only through the taps that exist
 #pragma unroll
                 for (int j = 0; j < KS; ++j) {
                   if (!((vbits >> j) & 1u)) {  // at most P taps per row, and only in the warps that hold a sequence end
                     const float4 w = *reinterpret_cast<const float4*>(Th + j * 128 + col);
-                    sw.x -= w.x; sw.y -= w.y; sw.z -= w.z; sw.w -= w.w;
+                    sw0 = fma2(lo2(w), make_float2(-1.f, -1.f), sw0);
+                    sw1 = fma2(hi2(w), make_float2(-1.f, -1.f), sw1);
                   }
                 }
               }
               const float4 g4 = *reinterpret_cast<const float4*>(Th + (KS + 1) * 128 + col);
               const float4 b4 = *reinterpret_cast<const float4*>(Th + (KS + 2) * 128 + col);
               const float4 d4 = *reinterpret_cast<const float4*>(Th + (KS + 3) * 128 + col);
-              const float o0 = fmaf(g4.x, acc.x, fmaf(b4.x, sw.x, d4.x));
-              const float o1 = fmaf(g4.y, acc.y, fmaf(b4.y, sw.y, d4.y));
-              const float o2 = fmaf(g4.z, acc.z, fmaf(b4.z, sw.z, d4.z));
-              const float o3 = fmaf(g4.w, acc.w, fmaf(b4.w, sw.w, d4.w));
-              split2(o0, o1, hi[c4 * 2], lo[c4 * 2]);
-              split2(o2, o3, hi[c4 * 2 + 1], lo[c4 * 2 + 1]);
+              split2p(fma2(lo2(g4), a0, fma2(lo2(b4), sw0, lo2(d4))), hi[c4 * 2], lo[c4 * 2]);
+              split2p(fma2(hi2(g4), a1, fma2(hi2(b4), sw1, hi2(d4))), hi[c4 * 2 + 1], lo[c4 * 2 + 1]);
             }
             const uint32_t ta = tbase + lane_off + 128 + h * 32 + cg * 8;
             tmem_st8(ta, make_uint4(hi[0], hi[1], hi[2], hi[3]), make_uint4(hi[4], hi[5], hi[6], hi[7]));
@@ -314,8 +317,8 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
         {
           const float* pwb = T + (KS + 4) * 128 + h * 64;
           const bool relu = !(p.flags & STAGE_ENC_NO_RELU), resid = !(p.flags & STAGE_ENC_NO_RESIDUAL);
-          s1 = 0.f;
-          s2 = 0.f;
+          s1 = make_float2(0.f, 0.f);
+          s2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float v[32];
@@ -325,17 +328,16 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(pwb + half * 32 + j);
-              float4 xv = *reinterpret_cast<float4*>(xh + half * 32 + j);
-              float4 dv = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
-              if (relu) dv = make_float4(fmaxf(dv.x, 0.f), fmaxf(dv.y, 0.f), fmaxf(dv.z, 0.f), fmaxf(dv.w, 0.f));
-              if (resid) xv = make_float4(xv.x + dv.x, xv.y + dv.y, xv.z + dv.z, xv.w + dv.w);
-              else xv = dv;
-              *reinterpret_cast<float4*>(xh + half * 32 + j) = xv;
-              s1 += (xv.x + xv.y) + (xv.z + xv.w);
-              s2 = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, s2))));
+              const float4 xv = *reinterpret_cast<float4*>(xh + half * 32 + j);
+              float2 d0 = add2(make_float2(v[j], v[j + 1]), lo2(bb)), d1 = add2(make_float2(v[j + 2], v[j + 3]), hi2(bb));
+              if (relu) { d0 = max2(d0, 0.f); d1 = max2(d1, 0.f); }
+              if (resid) { d0 = add2(d0, lo2(xv)); d1 = add2(d1, hi2(xv)); }
+              *reinterpret_cast<float4*>(xh + half * 32 + j) = make_float4(d0.x, d0.y, d1.x, d1.y);
+              s1 = add2(s1, add2(d0, d1));
+              s2 = fma2(d0, d0, fma2(d1, d1, s2));
             }
           }
-          *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1, s2);
+          *reinterpret_cast<float2*>(xrow + 128 + 2 * h) = make_float2(s1.x + s1.y, s2.x + s2.y);
         }
         tc_fence_before();
         ENC_BAR();
@@ -347,18 +349,17 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 
       // ---- closing LayerNorm (in place; mask_logits for the max-pool), then coalesced store / column-wise max
       {
-        const float rsn = fin ? my_stat.x : 1.f, nmn = fin ? my_stat.y : 0.f;
-        const float off = (1.f - m_row) * STG_NEG;  // mask_logits: x*m + (1-m)*(-1e10)
+        const float2 rsn = dup2(fin ? my_stat.x : 1.f), nmn = dup2(fin ? my_stat.y : 0.f);
+        const float2 mm = dup2(m_row), off = dup2((1.f - m_row) * STG_NEG);  // mask_logits: x*m + (1-m)*(-1e10)
         const float* fg = FIN + h * 64;
         const float* fb = FIN + 128 + h * 64;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
           const float4 v = *reinterpret_cast<const float4*>(xh + j);
           const float4 g4 = *reinterpret_cast<const float4*>(fg + j), b4 = *reinterpret_cast<const float4*>(fb + j);
-          float4 o = make_float4(fmaf(fmaf(v.x, rsn, nmn), g4.x, b4.x), fmaf(fmaf(v.y, rsn, nmn), g4.y, b4.y),
-                                 fmaf(fmaf(v.z, rsn, nmn), g4.z, b4.z), fmaf(fmaf(v.w, rsn, nmn), g4.w, b4.w));
-          if (p.out_mode != 0) o = make_float4(o.x * m_row + off, o.y * m_row + off, o.z * m_row + off, o.w * m_row + off);
-          *reinterpret_cast<float4*>(xh + j) = o;
+          float2 o0 = fma2(fma2(lo2(v), rsn, nmn), lo2(g4), lo2(b4)), o1 = fma2(fma2(hi2(v), rsn, nmn), hi2(g4), hi2(b4));
+          if (p.out_mode != 0) { o0 = fma2(o0, mm, off); o1 = fma2(o1, mm, off); }
+          *reinterpret_cast<float4*>(xh + j) = make_float4(o0.x, o0.y, o1.x, o1.y);
         }
       }
       ENC_BAR();

@@ -209,6 +209,23 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Packed fp32 arithmetic (FFMA2 / FADD2, sm_100): one instruction for two lanes of a float2.  The 3-register FFMA issues
+// every other cycle per scheduler, so the element-wise phases of these kernels are bound by fma-pipe instruction count.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 max2(float2 a, float b) { return make_float2(fmaxf(a.x, b), fmaxf(a.y, b)); }
+// split of a float2: hi = fp16x2(v), lo = fp16x2(v - float(hi)) with the subtraction as one packed FMA
+__device__ __forceinline__ void split2p(float2 v, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __float22half2_rn(v);
+  const float2 f = __half22float2(h);
+  const __half2 l = __float22half2_rn(fma2(f, make_float2(-1.f, -1.f), v));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ HL8 split8(const float* v) {
   HL8 o;
   split2(v[0], v[1], o.hi.x, o.lo.x);
