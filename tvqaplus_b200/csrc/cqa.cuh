@@ -360,24 +360,32 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
               float* raw = vid ? raw_v : raw_s;
               float* nrm = vid ? nrm_v : nrm_s;
               const float shift = vid ? shift_v : shift_s;
-              float sum = 0.f;
+              float2 sum2 = make_float2(0.f, 0.f);
+              const float2 ia2 = dup2(ia), sc22 = dup2(sc2), nsh2 = dup2(-shift);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 c4 = ic4[j4];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = j4 * 4 + e;
+                for (int e = 0; e < 2; ++e) {
+                  const int j = j4 * 4 + e * 2;
                   // S - 1e10*(1 - S_mask) of the reference: |S| <= 1 is absorbed by -1e10 in fp32, so a select is exact.
                   // Padded columns (>= n_real) carry inverse norm 0 and behave like masked ones (weight exactly 0).
-                  const float w = ia * cc[e];
-                  const float v = (w != 0.f) ? sv[j] * w : -1e10f;
-                  if (raw != nullptr && ch * 16 + j < n_real) raw[ch * 16 + j] = v;
-                  const float ex = fast_exp2(fmaf(v, sc2, -shift));  // masked / padded: exp2(-1.4e11) = 0
-                  sum += ex;
-                  sv[j] = ex;
+                  const float2 w = mul2(ia2, e == 0 ? lo2(c4) : hi2(c4));
+                  float2 v = mul2(make_float2(sv[j], sv[j + 1]), w);
+                  v.x = (w.x != 0.f) ? v.x : -1e10f;
+                  v.y = (w.y != 0.f) ? v.y : -1e10f;
+                  if (raw != nullptr) {
+                    if (ch * 16 + j < n_real) raw[ch * 16 + j] = v.x;
+                    if (ch * 16 + j + 1 < n_real) raw[ch * 16 + j + 1] = v.y;
+                  }
+                  const float2 arg = fma2(v, sc22, nsh2);  // masked / padded: exp2(-1.4e11) = 0
+                  const float2 ex = make_float2(fast_exp2(arg.x), fast_exp2(arg.y));
+                  sum2 = add2(sum2, ex);
+                  sv[j] = ex.x;
+                  sv[j + 1] = ex.y;
                 }
               }
+              const float sum = sum2.x + sum2.y;
               if (nrm != nullptr) {  // optional output: normalised after the row sums are known (see below)
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -462,14 +470,21 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           const uint32_t tU = (g == 0 ? T2 : T3) + coff;
           const float isum = g == 0 ? is : iv;
           float* att = g == 0 ? p.att_sub : p.att_vid;
-          float s1 = 0.f, s2 = 0.f;
+          float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+          const float2 isum2 = dup2(isum);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float u[16];
             tmem_ld16(tU + h * 16, u);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { u[j] *= isum; s1 += u[j]; s2 = fmaf(u[j], u[j], s2); }
+            for (int j = 0; j < 16; j += 2) {
+              const float2 t = mul2(make_float2(u[j], u[j + 1]), isum2);
+              s1 = add2(s1, t);
+              s2 = fma2(t, t, s2);
+              u[j] = t.x;
+              u[j + 1] = t.y;
+            }
             if (att != nullptr && live) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
@@ -484,16 +499,18 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             tmem_ld16(tU + h * 16, u);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              u[j] *= isum * a_reg[h * 16 + j];
-              s1 += u[j];
-              s2 = fmaf(u[j], u[j], s2);
+            for (int j = 0; j < 16; j += 2) {
+              const float2 t = mul2(make_float2(u[j], u[j + 1]), mul2(isum2, make_float2(a_reg[h * 16 + j], a_reg[h * 16 + j + 1])));
+              s1 = add2(s1, t);
+              s2 = fma2(t, t, s2);
+              u[j] = t.x;
+              u[j + 1] = t.y;
             }
             CQA_SEG_PUT(h, u, 34)
           }
           CQA_SEG_DONE()
-          st_s1[g] = s1;
-          st_s2[g] = s2;
+          st_s1[g] = s1.x + s1.y;
+          st_s2[g] = s2.x + s2.y;
         }
         CQA_STAMP(0, 6);
         float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
@@ -524,11 +541,11 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         ++done_cnt;
         tc_fence_after();
         CQA_STAMP(0, 8);
-        float c1 = 0.f, c2 = 0.f;
+        float2 c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint32_t tC = (g == 0 ? T0 : T1) + coff;
-          const float rr = g == 0 ? r_s : r_v, nm = g == 0 ? nm_s : nm_v;
+          const float2 rr = dup2(g == 0 ? r_s : r_v), nm = dup2(g == 0 ? nm_s : nm_v);
           float* mixed = g == 0 ? p.mixed_sub : p.mixed_vid;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -540,13 +557,14 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 cs = cs4[j4], cb = cb4[j4];
-              const float csv[4] = {cs.x, cs.y, cs.z, cs.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = j4 * 4 + e;
-                m[j] = fmaxf(fmaf(rr, m[j], fmaf(nm, csv[e], cbv[e])), 0.f);
-                c1 += m[j];
-                c2 = fmaf(m[j], m[j], c2);
+              for (int e = 0; e < 2; ++e) {
+                const int j = j4 * 4 + e * 2;
+                const float2 t = max2(fma2(rr, make_float2(m[j], m[j + 1]), fma2(nm, e == 0 ? lo2(cs) : hi2(cs), e == 0 ? lo2(cb) : hi2(cb))), 0.f);
+                c1 = add2(c1, t);
+                c2 = fma2(t, t, c2);
+                m[j] = t.x;
+                m[j + 1] = t.y;
               }
             }
             tmem_st16(tC + h * 16, m);
@@ -567,17 +585,19 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           tmem_ld16(T1 + coff + h * 16, w);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            m[j] *= w[j];
-            c1 += m[j];
-            c2 = fmaf(m[j], m[j], c2);
+          for (int j = 0; j < 16; j += 2) {
+            const float2 t = mul2(make_float2(m[j], m[j + 1]), make_float2(w[j], w[j + 1]));
+            c1 = add2(c1, t);
+            c2 = fma2(t, t, c2);
+            m[j] = t.x;
+            m[j + 1] = t.y;
           }
           CQA_SEG_PUT(h, m, 38)
         }
         CQA_SEG_DONE()
         CQA_STAMP(0, 9);
-        xq[0][qd][row] = c1;
-        xq[1][qd][row] = c2;
+        xq[0][qd][row] = c1.x + c1.y;
+        xq[1][qd][row] = c2.x + c2.y;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const float mu_c = ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) * (1.f / 384.f);
         const float r_c = 1.f / sqrtf(fmaxf(((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
@@ -594,23 +614,25 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           tmem_ld16(T2 + coff, o);
           tmem_ld16(T2 + coff + 16, o + 16);
           tmem_wait_ld();
-          float o1 = 0.f, o2 = 0.f;
+          float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
+          const float2 r_c2 = dup2(r_c), nm_c2 = dup2(nm_c);
           const float4* cs4 = reinterpret_cast<const float4*>(&pvec[2][qd * 32]);
           const float4* cb4 = reinterpret_cast<const float4*>(&pvec[3][qd * 32]);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 cs = cs4[j4], cb = cb4[j4];
-            const float csv[4] = {cs.x, cs.y, cs.z, cs.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              o[j] = fmaxf(fmaf(r_c, o[j], fmaf(nm_c, csv[e], cbv[e])), 0.f);
-              o1 += o[j];
-              o2 = fmaf(o[j], o[j], o2);
+            for (int e = 0; e < 2; ++e) {
+              const int j = j4 * 4 + e * 2;
+              const float2 t = max2(fma2(r_c2, make_float2(o[j], o[j + 1]), fma2(nm_c2, e == 0 ? lo2(cs) : hi2(cs), e == 0 ? lo2(cb) : hi2(cb))), 0.f);
+              o1 = add2(o1, t);
+              o2 = fma2(t, t, o2);
+              o[j] = t.x;
+              o[j + 1] = t.y;
             }
           }
-          xq[2][qd][row] = o1;
-          xq[3][qd][row] = o2;
+          xq[2][qd][row] = o1.x + o1.y;
+          xq[3][qd][row] = o2.x + o2.y;
           asm volatile("bar.sync 1, 512;" ::: "memory");
           const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
           const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
@@ -628,11 +650,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
               dstep = p.stmt_stride;
             }
 #pragma unroll
+            const float2 rstd2 = dup2(rstd), nmr2 = dup2(nmr);
+#pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 g = g4p[j >> 2], b = b4p[j >> 2];
-              dst[(j >> 2) * dstep] =
-                  make_float4(fmaf(fmaf(o[j], rstd, nmr), g.x, b.x), fmaf(fmaf(o[j + 1], rstd, nmr), g.y, b.y),
-                              fmaf(fmaf(o[j + 2], rstd, nmr), g.z, b.z), fmaf(fmaf(o[j + 3], rstd, nmr), g.w, b.w));
+              const float2 y0 = fma2(fma2(make_float2(o[j], o[j + 1]), rstd2, nmr2), lo2(g), lo2(b));
+              const float2 y1 = fma2(fma2(make_float2(o[j + 2], o[j + 3]), rstd2, nmr2), hi2(g), hi2(b));
+              dst[(j >> 2) * dstep] = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
           }
           // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
