@@ -220,6 +220,8 @@ typedef struct {
   uint32_t a_mn, b_mn;
   uint32_t k_steps, n, use_bulk;
   float* d_out; /* [128,n] */
+  uint32_t repeat;      /* > 1: the k_steps MMAs are issued `repeat` times back to back (throughput measurement) */
+  long long* cycles_out; /* optional: SM cycles from the first MMA issue to the completion of the last */
 } StageProbeArgs;
 int stage_umma_probe(const StageProbeArgs* a, void* stream);
 

@@ -18,7 +18,7 @@ w = dict(wblob=ops.cqa_prepare_weights(torch.ones(384, device=dev), torch.zeros(
                                        torch.zeros(128, device=dev), torch.ones(384, device=dev), torch.zeros(384, device=dev),
                                        torch.randn(128, 384, device=dev) * 0.05, torch.zeros(128, device=dev)),
          cat_out_ln_g=torch.ones(128, device=dev), cat_out_ln_b=torch.zeros(128, device=dev))
-tl = torch.zeros(2, 64, 16, dtype=torch.int64, device=dev)
+tl = torch.zeros(4, 64, 16, dtype=torch.int64, device=dev)
 for _ in range(2):
     ops.cqa_fused_fwd(a, ones(N, 5, Lq), s, ones(N, T, Ls), v, ones(N, T, R), w, 10.0, timeline=tl)
 torch.cuda.synchronize()
@@ -35,3 +35,11 @@ d = (c[3:60, 1:12] - c[3:60, 0:11]).float().mean(0)
 print("compute mean phase cycles:", {names_c[i + 1]: int(d[i]) for i in range(11)}, "tile total", int((c[4:60, 0] - c[3:59, 0]).float().mean()))
 dm = (m[3:60, 1:9] - m[3:60, 0:8]).float().mean(0)
 print("mma mean phase cycles:", {names_m[i + 1]: int(dm[i]) for i in range(8)})
+
+# per-stage hand-off of the first 8 A stages (c2q): producer (thread 0) ready-to-store / arrived, MMA warp saw full / issued
+ps, ms = tl[2], tl[3]
+for tile in (4, 5):
+    base = int(c[tile][5])  # D2 seen by the compute thread
+    print("tile", tile, "stages (cycles after D2): " + "  ".join(
+        "s%d prod %d/%d mma %d/%d" % (k, int(ps[tile][2 * k]) - base, int(ps[tile][2 * k + 1]) - base, int(ms[tile][2 * k]) - base,
+                                      int(ms[tile][2 * k + 1]) - base) for k in range(8)))

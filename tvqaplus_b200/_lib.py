@@ -61,7 +61,8 @@ class ProbeArgs(C.Structure):
                 ("a_lbo", C.c_uint32), ("a_sbo", C.c_uint32), ("a_step", C.c_uint32),
                 ("b_lbo", C.c_uint32), ("b_sbo", C.c_uint32), ("b_step", C.c_uint32),
                 ("a_mn", C.c_uint32), ("b_mn", C.c_uint32),
-                ("k_steps", C.c_uint32), ("n", C.c_uint32), ("use_bulk", C.c_uint32), ("d_out", _f)]
+                ("k_steps", C.c_uint32), ("n", C.c_uint32), ("use_bulk", C.c_uint32), ("d_out", _f),
+                ("repeat", C.c_uint32), ("cycles_out", _f)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check the .so exports everything the header declares

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   {                                                                                          \
     const HL8 hl0 = split8((v)), hl1 = split8((v) + 8);                                      \
     uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2) * CqaCfg::LBO_A + row * 16;      \
+    if (st_seq < 8) CQA_STAMP(2, st_seq * 2);                                                \
     mbar_wait(&a_empty[h], (a_use & 1u) ^ 1u, code);                                         \
     *reinterpret_cast<uint4*>(dst) = hl0.hi;                                                 \
     *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl0.lo;                              \
@@ -271,6 +272,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     *reinterpret_cast<uint4*>(dst + CqaCfg::LBO_A + CqaCfg::AST_PART) = hl1.lo;              \
     fence_async_smem();                                                                      \
     mbar_arrive(&a_full[h]);                                                                 \
+    if (st_seq < 8) CQA_STAMP(2, st_seq * 2 + 1);                                            \
+    ++st_seq;                                                                                \
   }
 #define CQA_SEG_DONE() ++a_use;
 
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);  // output row
 #define orow (static_cast<size_t>(srow) * 128 + qd * 32) /* my 32 columns of the output row */
         CQA_STAMP(0, 0);
+        [[maybe_unused]] int st_seq = 0;  // A stage counter of this tile (timeline build)
         const float* rd = reinterpret_cast<const float*>(p.a_blob + nj * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row);
         if (a_i == 0) {
@@ -672,10 +676,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     }
 #undef CQA_SEG_PUT
 #undef CQA_SEG_DONE
-  } else if (warp == 16 && lane == 0) {
-    // =================================================================== MMA issue (one thread; never waits for a completion)
+  } else if (warp == 16) {
+    // =================================================================== MMA issue.  The whole warp runs the control flow
+    // (waits included) and ONE elected lane issues: only in converged code can the compiler keep descriptors in uniform
+    // registers; under a `lane == 0` branch every tcgen05 instruction sits in a lane-by-lane waterfall loop.  The issuer
+    // never waits for a completion.
     uint32_t ready_cnt = 0, seg_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
-    [[maybe_unused]] int tl_tile = 0;
+    [[maybe_unused]] int tl_tile = (lane == 0) ? 0 : 64;
     const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
     const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
     const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
@@ -687,41 +694,45 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         CQA_STAMP(1, 1);
         // ---- S = a . ctx^T for both streams
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_hi = make_smem_desc(aq + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t a_lo = make_smem_desc(aq + CqaCfg::AQ_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t s_hi = make_smem_desc(cs + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
-          const uint64_t s_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
-          umma_split3(T0, a_hi, a_lo, s_hi, s_lo, id_ssub, ks > 0 ? 1u : 0u);
-          const uint64_t v_hi = make_smem_desc(cv + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
-          const uint64_t v_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
-          umma_split3(T1, a_hi, a_lo, v_hi, v_lo, id_svid, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = make_smem_desc(aq + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t a_lo = make_smem_desc(aq + CqaCfg::AQ_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t s_hi = make_smem_desc(cs + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
+            const uint64_t s_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
+            umma_split3(T0, a_hi, a_lo, s_hi, s_lo, id_ssub, ks > 0 ? 1u : 0u);
+            const uint64_t v_hi = make_smem_desc(cv + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
+            const uint64_t v_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
+            umma_split3(T1, a_hi, a_lo, v_hi, v_lo, id_svid, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&mma_done);  // D1
         }
-        umma_commit(&mma_done);  // D1
         CQA_STAMP(1, 2);
         // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
         mbar_wait(&op_ready, ready_cnt & 1u, 42);  // E2
         ++ready_cnt;
         tc_fence_after();
         CQA_STAMP(1, 3);
-        for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(ps + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t a_lo = make_smem_desc(ps + CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t b_hi = make_smem_desc(cs + ks * 256, 128, CqaCfg::LBO_CS);
-          const uint64_t b_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 256, 128, CqaCfg::LBO_CS);
-          umma_split3(T2, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(ps + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t a_lo = make_smem_desc(ps + CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t b_hi = make_smem_desc(cs + ks * 256, 128, CqaCfg::LBO_CS);
+            const uint64_t b_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 256, 128, CqaCfg::LBO_CS);
+            umma_split3(T2, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
+          }
+          for (int ks = 0; ks < p.r_pad / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(pv + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t a_lo = make_smem_desc(pv + CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+            const uint64_t b_hi = make_smem_desc(cv + ks * 256, 128, CqaCfg::LBO_CV);
+            const uint64_t b_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 256, 128, CqaCfg::LBO_CV);
+            umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&mma_done);  // D2
+          umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
+          if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         }
-        for (int ks = 0; ks < p.r_pad / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(pv + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t a_lo = make_smem_desc(pv + CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-          const uint64_t b_hi = make_smem_desc(cv + ks * 256, 128, CqaCfg::LBO_CV);
-          const uint64_t b_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 256, 128, CqaCfg::LBO_CV);
-          umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(&mma_done);  // D2
-        umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
-        if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         CQA_STAMP(1, 4);
         // ---- GEMMs: 14 K=64 A stages (4 c2q sub, 4 c2q vid, 6 concat), each against two K=32 weight slots
         for (int hs = 0; hs < CqaCfg::HALF_SEGS; ++hs) {
@@ -731,30 +742,34 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           mbar_wait(&w_full[i0 % CqaCfg::W_SLOTS], (i0 / CqaCfg::W_SLOTS) & 1u, 46);
           mbar_wait(&w_full[(i0 + 1u) % CqaCfg::W_SLOTS], ((i0 + 1u) / CqaCfg::W_SLOTS) & 1u, 46);
           tc_fence_after();
+          if (hs < 8) CQA_STAMP(3, hs * 2);
           const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
           const uint32_t dcol = hs < 4 ? T0 : (hs < 8 ? T1 : T2);
           const bool first = (hs == 8);  // the c2q accumulators start from the stored a.Wa term, concat from zero
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t wsl = smem_u32(sB + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT);
-            const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
-            const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
-            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t wsl = ps + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
+              const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+              const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+              const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
+              const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
+              umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
+            }
+            umma_commit(&a_empty[h]);
+            umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
+            umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
+            if (hs == 7) umma_commit(&mma_done);  // D3
           }
-          umma_commit(&a_empty[h]);
-          umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
-          umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
+          if (hs < 8) CQA_STAMP(3, hs * 2 + 1);
           if (h == 1u) ++seg_cnt;
-          if (hs == 7) {
-            umma_commit(&mma_done);  // D3
-            CQA_STAMP(1, 6);
-          }
+          if (hs == 7) CQA_STAMP(1, 6);
           if (hs == 3) CQA_STAMP(1, 5);
         }
-        umma_commit(&mma_done);  // D4
-        umma_commit(&aq_free);   // the A stages (AQ region) may receive the next answer image
+        if (elect_one()) {
+          umma_commit(&mma_done);  // D4
+          umma_commit(&aq_free);   // the A stages (AQ region) may receive the next answer image
+        }
         CQA_STAMP(1, 7);
         q_cnt += CqaCfg::CHUNKS;
         CQA_STAMP(1, 8);

@@ -392,8 +392,10 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
       ENC_STAMP(14);
       ++tl_tile;
     }
-  } else if (warp == 8 && lane == 0) {
-    // =================================================================== MMA issue (one thread)
+  } else if (warp == 8) {
+    // =================================================================== MMA issue: the whole warp runs the control flow, one
+    // elected lane issues (converged code keeps the descriptors in uniform registers; under `lane == 0` every tcgen05.mma
+    // would sit in a lane-by-lane waterfall loop)
     const uint32_t idesc = make_idesc_f16(128);
     const uint32_t w0 = smem_u32(sW);
     uint32_t q = 0, ph = 0;
@@ -407,20 +409,22 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
           const uint32_t slot = q & 1u;
           mbar_wait(&w_full[slot], (q >> 1) & 1u, 23);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k2 = 0; k2 < 2; ++k2) {
-            const uint32_t ks = c * 2 + k2;
-            const uint32_t a_hi = tbase + 128 + ks * 8, a_lo = tbase + 192 + ks * 8;
-            const uint32_t wa = w0 + slot * EncCfg::W_SLOT + k2 * 2 * EncCfg::LBO_B;
-            const uint64_t b_hi = make_smem_desc(wa, EncCfg::LBO_B, 128);
-            const uint64_t b_lo = make_smem_desc(wa + EncCfg::W_HALF, EncCfg::LBO_B, 128);
-            umma_f16_ts(tbase, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
-            umma_f16_ts(tbase, a_hi, b_lo, idesc, 1u);
-            umma_f16_ts(tbase, a_hi, b_hi, idesc, 1u);
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const uint32_t ks = c * 2 + k2;
+              const uint32_t a_hi = tbase + 128 + ks * 8, a_lo = tbase + 192 + ks * 8;
+              const uint32_t wa = w0 + slot * EncCfg::W_SLOT + k2 * 2 * EncCfg::LBO_B;
+              const uint64_t b_hi = make_smem_desc(wa, EncCfg::LBO_B, 128);
+              const uint64_t b_lo = make_smem_desc(wa + EncCfg::W_HALF, EncCfg::LBO_B, 128);
+              umma_f16_ts(tbase, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+              umma_f16_ts(tbase, a_hi, b_lo, idesc, 1u);
+              umma_f16_ts(tbase, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit(&w_empty[slot]);
+            if (c == 3) umma_commit(&mma_done);
           }
-          umma_commit(&w_empty[slot]);
         }
-        umma_commit(&mma_done);
       }
     }
   } else if (warp == 9 && lane == 0) {

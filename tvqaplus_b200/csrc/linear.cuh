@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
     const long long total = my_tiles * p.n_chunks;  // flat (tile, chunk) sequence of this CTA
 
     float4 buf[PREF][NI][2];
+    const bool wide = (p.k & 7) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 31u) == 0;  // rows and slots are 32-byte aligned
     long long ptl = 0;  // (tile, chunk) of the next prefetch
     int pc = 0;
     auto issue = [&](float4 (&dst)[NI][2]) {
@@ -306,8 +307,16 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
         const long long gr = row0 + rbase + i * (256 / K8);
         const float4* src = reinterpret_cast<const float4*>(p.x + gr * p.k + k0);
         const bool ok = ptl < my_tiles && gr < p.m;
-        dst[i][0] = (ok && k0 + 4 <= p.k) ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dst[i][1] = (ok && k0 + 8 <= p.k) ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wide) {  // one 256-bit request per 8-column slot: every 32-byte sector is fetched once, by one instruction
+          if (ok && k0 + 8 <= p.k) {
+            ldg256(src, dst[i][0], dst[i][1]);
+          } else {
+            dst[i][0] = dst[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          dst[i][0] = (ok && k0 + 4 <= p.k) ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[i][1] = (ok && k0 + 8 <= p.k) ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       if (++pc == p.n_chunks) {
         pc = 0;
@@ -395,43 +404,48 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
         }
       }
     }
-  } else if (lane == 0) {
-    // -------------------------------------------------------------------- MMA issuer
+  } else {
+    // -------------------------------------------------------------------- MMA issuer: the whole warp runs the control flow
+    // (waits included), one elected lane issues -- in converged code the descriptors stay in uniform registers, under a
+    // `lane == 0` branch every tcgen05.mma sits in a lane-by-lane waterfall loop (~130 cycles per MMA measured)
     uint32_t it = 0, tile_it = 0;
     const uint32_t idesc0 = make_idesc_f16(Cfg::N0);
     const uint32_t idesc1 = make_idesc_f16(NPAD - Cfg::N0 > 0 ? NPAD - Cfg::N0 : 16);
+    const uint32_t smem0 = smem_u32(smem);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
       const uint32_t b = tile_it % Cfg::ACC_BUFS, ause = tile_it / Cfg::ACC_BUFS;
       mbar_wait(&acc_empty[b], (ause & 1u) ^ 1u, 12);
       tc_fence_after();
-      LIN_STAMP(tile_it, 2);
+      if (lane == 0) LIN_STAMP(tile_it, 2);
       const uint32_t dcol = tbase + b * Cfg::ACC_STRIDE;
       for (int c = 0; c < p.n_chunks; ++c, ++it) {
         const uint32_t s = it % STAGES, use = it / STAGES;
         mbar_wait(&full_bar[s], use & 1u, 13);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sA = smem0 + s * Cfg::STAGE_BYTES;
         const uint32_t sB = sA + Cfg::A_STAGE;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(sA + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128);
-          const uint64_t a_lo = make_smem_desc(sA + Cfg::A_PART + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128);
-          const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-          {
-            const uint64_t b_hi = make_smem_desc(sB + ks * 2 * Cfg::LBO_B, Cfg::LBO_B, 128);
-            const uint64_t b_lo = make_smem_desc(sB + Cfg::B_PART + ks * 2 * Cfg::LBO_B, Cfg::LBO_B, 128);
-            umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, idesc0, acc);
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(sA + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128);
+            const uint64_t a_lo = make_smem_desc(sA + Cfg::A_PART + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128);
+            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+            {
+              const uint64_t b_hi = make_smem_desc(sB + ks * 2 * Cfg::LBO_B, Cfg::LBO_B, 128);
+              const uint64_t b_lo = make_smem_desc(sB + Cfg::B_PART + ks * 2 * Cfg::LBO_B, Cfg::LBO_B, 128);
+              umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, idesc0, acc);
+            }
+            if (NPAD > Cfg::N0) {
+              const uint64_t b_hi = make_smem_desc(sB + ks * 2 * Cfg::LBO_B + Cfg::N0 * 16, Cfg::LBO_B, 128);
+              const uint64_t b_lo = make_smem_desc(sB + Cfg::B_PART + ks * 2 * Cfg::LBO_B + Cfg::N0 * 16, Cfg::LBO_B, 128);
+              umma_split3(dcol + Cfg::N0, a_hi, a_lo, b_hi, b_lo, idesc1, acc);
+            }
           }
-          if (NPAD > Cfg::N0) {
-            const uint64_t b_hi = make_smem_desc(sB + ks * 2 * Cfg::LBO_B + Cfg::N0 * 16, Cfg::LBO_B, 128);
-            const uint64_t b_lo = make_smem_desc(sB + Cfg::B_PART + ks * 2 * Cfg::LBO_B + Cfg::N0 * 16, Cfg::LBO_B, 128);
-            umma_split3(dcol + Cfg::N0, a_hi, a_lo, b_hi, b_lo, idesc1, acc);
-          }
+          umma_commit(&empty_bar[s]);
+          if (c == p.n_chunks - 1) umma_commit(&acc_full[b]);
         }
-        umma_commit(&empty_bar[s]);
       }
-      umma_commit(&acc_full[b]);
-      LIN_STAMP(tile_it, 3);
+      if (lane == 0) LIN_STAMP(tile_it, 3);
     }
   }
 

@@ -20,6 +20,8 @@ struct ProbeArgs {
   uint32_t a_tmem;     // 1: A comes from TENSOR MEMORY: a_img is row-major fp16 [128][16*k_steps]; thread r packs its row two
                        //    k values per 32-bit column and stores it with tcgen05.st at columns [256 + 8*ks, +8)
   float* d_out;        // [128][n]
+  uint32_t repeat;     // the k_steps MMAs are issued this many times (accumulating)
+  long long* cycles_out;
 };
 
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
@@ -68,13 +70,44 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs p) {
   if (tid == 0) {
     if (p.use_bulk) mbar_wait(&bar_tx, 0, 2);
     tc_fence_after();
-    for (uint32_t ks = 0; ks < p.k_steps; ++ks) {
-      uint64_t ad = make_smem_desc(smem_u32(sa) + ks * p.a_step, p.a_lbo, p.a_sbo);
-      uint64_t bd = make_smem_desc(smem_u32(sb) + ks * p.b_step, p.b_lbo, p.b_sbo);
-      if (p.a_tmem) umma_f16_ts(tbase, tbase + 256 + ks * 8, bd, p.idesc, ks > 0 ? 1u : 0u);
-      else umma_f16(tbase, ad, bd, p.idesc, ks > 0 ? 1u : 0u);
+    long long t_start = clock64();
+    if (p.repeat > 1 && p.k_steps == 8) {
+      // throughput mode: descriptors precomputed, 8 MMAs per unrolled loop body (what a lean issue loop can reach)
+      uint64_t ad[8], bd[8];
+#pragma unroll
+      for (uint32_t ks = 0; ks < 8; ++ks) {
+        ad[ks] = make_smem_desc(smem_u32(sa) + ks * p.a_step, p.a_lbo, p.a_sbo);
+        bd[ks] = make_smem_desc(smem_u32(sb) + ks * p.b_step, p.b_lbo, p.b_sbo);
+      }
+      const uint32_t ta = tbase + 256, idesc = p.idesc;
+      t_start = clock64();
+      if (p.a_tmem) {
+#pragma unroll 1
+        for (uint32_t rep = 0; rep < p.repeat; ++rep) {
+#pragma unroll
+          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16_ts(tbase, ta + ks * 8, bd[ks], idesc, 1u);
+        }
+      } else {
+#pragma unroll 1
+        for (uint32_t rep = 0; rep < p.repeat; ++rep) {
+#pragma unroll
+          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16(tbase, ad[ks], bd[ks], idesc, 1u);
+        }
+      }
+    } else {
+      for (uint32_t rep = 0; rep < p.repeat; ++rep) {
+        for (uint32_t ks = 0; ks < p.k_steps; ++ks) {
+          uint64_t ad = make_smem_desc(smem_u32(sa) + ks * p.a_step, p.a_lbo, p.a_sbo);
+          uint64_t bd = make_smem_desc(smem_u32(sb) + ks * p.b_step, p.b_lbo, p.b_sbo);
+          if (p.a_tmem) umma_f16_ts(tbase, tbase + 256 + ks * 8, bd, p.idesc, (ks > 0 || rep > 0) ? 1u : 0u);
+          else umma_f16(tbase, ad, bd, p.idesc, (ks > 0 || rep > 0) ? 1u : 0u);
+        }
+      }
     }
     umma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0, 3);
+    if (p.cycles_out != nullptr) *p.cycles_out = clock64() - t_start;
+
   }
   mbar_wait(&bar_mma, 0, 3);
   tc_fence_after();

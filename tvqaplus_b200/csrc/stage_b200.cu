@@ -72,6 +72,7 @@ int stage_umma_probe(const StageProbeArgs* a, void* stream) {
   p.a_tmem = (a->a_mn == 2u) ? 1u : 0u;  /* a_mn = 2: A operand from tensor memory (K-major by construction) */
   p.idesc = make_idesc_f16(a->n, p.a_tmem ? 0u : a->a_mn, a->b_mn);
   p.k_steps = a->k_steps; p.n = a->n; p.use_bulk = a->use_bulk; p.d_out = a->d_out;
+  p.repeat = a->repeat > 0 ? a->repeat : 1u; p.cycles_out = a->cycles_out;
   size_t smem = ((a->a_bytes + 1023u) & ~1023u) + a->b_bytes + 1024;
   STG_REQUIRE(smem <= 200 * 1024, STAGE_E_UNSUPPORTED, "probe: smem %zu", smem);
   int rc = set_smem(umma_probe_kernel, smem, "probe");

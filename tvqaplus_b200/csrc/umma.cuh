@@ -165,6 +165,19 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n, uint32_t
   return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// One lane of a CONVERGED warp (the role warps run their control flow with all 32 lanes and elect the issuer): under a
+// `lane == 0` branch the compiler cannot keep descriptors in uniform registers and wraps every tcgen05 instruction in a
+// lane-by-lane waterfall loop (~130 cycles per MMA measured, twice the tensor time of a 128x128x16 MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -247,6 +260,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 256-bit read-only global load (sm_100): 32 contiguous, 32-byte aligned bytes in one request
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
