@@ -12,9 +12,9 @@ from tvqaplus_b200 import _lib  # noqa: E402
 dev = torch.device("cuda:0")
 
 
-def rate(n, ksteps, a_tmem, repeat=400):
+def rate(n, ksteps, a_tmem, repeat=400, a_pad=0, b_pad=0):
     K = 16 * ksteps
-    a_lbo, b_lbo = 128 * 16, n * 16
+    a_lbo, b_lbo = 128 * 16 + a_pad, n * 16 + b_pad
     a = torch.zeros(128 * K * 2 if a_tmem else (K // 8) * a_lbo, dtype=torch.uint8, device=dev)
     b = torch.zeros((K // 8) * b_lbo, dtype=torch.uint8, device=dev)
     d = torch.zeros(128, n, device=dev)
@@ -31,3 +31,7 @@ def rate(n, ksteps, a_tmem, repeat=400):
 
 for n in (64, 128, 160, 256):
     print("N=%3d  SS %.1f cycles/MMA   TS %.1f cycles/MMA   (tensor floor %.0f)" % (n, rate(n, 8, False), rate(n, 8, True), 128 * n / 256))
+
+# padded LBO (the +16 / +32 bytes that spread the producers' stores over the banks): do the MMA operand reads pay for it?
+for a_pad, b_pad in ((16, 0), (32, 0), (0, 16), (16, 16), (128, 0)):
+    print("N=128  A LBO +%3d  B LBO +%3d:  SS %.1f cycles/MMA" % (a_pad, b_pad, rate(128, 8, False, a_pad=a_pad, b_pad=b_pad)))
