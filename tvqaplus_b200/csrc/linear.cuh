@@ -8,13 +8,14 @@
 // common offset costs neither GEMM nor variance precision.  mean / rstd come from sum(x - c) and sum((x - c)^2), which
 // the producers accumulate while they convert the row.
 //
-// Persistent CTAs, one 128-row tile at a time.  Warp roles (416 threads):
-//   warps 0-3   epilogue: TMEM -> registers (thread per row): folded LayerNorm / bias / ReLU / exact two-pass LN_out,
+// Persistent CTAs, one 128-row tile at a time.  Warp roles (416 threads; 544 with a single accumulator, see EPI_WARPS):
+//   warps 9-..  epilogue: TMEM -> registers (thread per row): folded LayerNorm / bias / ReLU / exact two-pass LN_out,
 //               then a 32x32 transpose through shared memory so that every global store covers whole 128-byte lines
-//   warps 4-11  producers: each thread owns the same (row, 8-column slot) pairs for every K chunk; its global loads run
+//   warps 0-7   producers: each thread owns the same (row, 8-column slot) pairs for every K chunk; its global loads run
 //               PREF chunks ahead in registers (HBM latency), values are split into fp16 (hi, lo) and stored as the
 //               A operand image; the first producer thread also launches the bulk copy of the matching weight chunk
-//   warp  12    MMA issuer (one lane): 3 tcgen05.mma per K=16 step (split-fp16); tcgen05.commit frees the stage
+//   warp  8     MMA issuer (converged warp, one elected lane): 3 tcgen05.mma per K=16 step (split-fp16); tcgen05.commit
+//               frees the stage
 // Pipelines: full[s]/empty[s] per smem stage, acc_full[b]/acc_empty[b] per TMEM accumulator buffer (two buffers when
 // 2*NPAD fits in 512 columns, so the epilogue of tile i overlaps the MMAs of tile i+1).
 //
@@ -43,7 +44,7 @@ struct LinearCfg {
   static constexpr uint32_t B_STAGE = 2u * B_PART;
   static constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE + 127u) & ~127u;
   static constexpr int TS = 36;                                  // fp32 row stride of a warp's 32x32 transpose buffer
-  static constexpr uint32_t TR_BYTES = 4u * 32u * TS * 4u;       // 18432: one buffer per epilogue warp
+  static constexpr uint32_t TR_BYTES = ((2 * NPAD <= 512 && NPAD <= 256) ? 4u : 8u) * 32u * TS * 4u;  // one 4.6 KB buffer per epilogue warp
   static constexpr uint32_t VEC_BYTES = 4u * NPAD * 4u;          // cs | cb (or bias) | ln_out gamma | ln_out beta
   static constexpr uint32_t OFF_TR = STAGES * STAGE_BYTES;
   static constexpr uint32_t OFF_VEC = OFF_TR + TR_BYTES;
@@ -52,9 +53,12 @@ struct LinearCfg {
   static constexpr uint32_t ACC_STRIDE = NPAD <= 128 ? 128u : 256u;
   static constexpr uint32_t TMEM_COLS = (ACC_BUFS == 2) ? 2u * ACC_STRIDE : 512u;
   static constexpr int N0 = NPAD <= 256 ? NPAD : ((NPAD / 2 + 15) / 16 * 16);  // first MMA N; second = NPAD - N0
-  static constexpr int THREADS = 416;
+  // With a single accumulator (N > 256) the epilogue cannot hide behind the next tile's MMAs, so it gets a second set of
+  // four warps (13-16) that takes the upper half of the 32-column blocks.
+  static constexpr int EPI_WARPS = (ACC_BUFS == 1) ? 8 : 4;
+  static constexpr int THREADS = (EPI_WARPS == 8) ? 544 : 416;
   static constexpr int ITEMS = 128 * K8 / 256;  // (row, 8-column slot) pairs per producer thread per chunk
-  static constexpr int PREF = (KC == 32) ? 4 : 2;  // chunks of global loads in flight per producer thread
+  static constexpr int PREF = (KC == 32) ? (EPI_WARPS == 8 ? 2 : 4) : 2;  // chunks of global loads in flight per producer thread
 };
 
 struct LinearDev {
@@ -75,7 +79,7 @@ struct LinearDev {
 };
 
 template <int NPAD, int KC, int STAGES>
-__global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
+__global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) linear_kernel(LinearDev p) {
   using Cfg = LinearCfg<NPAD, KC, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 128);
+      mbar_init(&acc_empty[b], Cfg::EPI_WARPS * 32);
     }
     mbar_fence_init();
   }
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
     vec[2 * NPAD + i] = (in && p.ln_out_g != nullptr) ? p.ln_out_g[i] : 1.f;
     vec[3 * NPAD + i] = (in && p.ln_out_b != nullptr) ? p.ln_out_b[i] : 0.f;
   }
-  if (warp == 12) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+  if (warp == 8) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -113,20 +117,25 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
   const long long n_tiles = (p.m + 127) / 128;
   const bool need_stats = (p.cs != nullptr) || p.l2norm_in;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ epilogue: thread per row
+  if (warp >= 9) {
+    // ------------------------------------------------------------------ epilogue: thread per row; with eight epilogue warps
+    // the second four (TMEM lane quadrant = warp % 4 like everyone) emit the upper half of the column blocks.  The
+    // epilogue warps carry the HIGHEST warp ids: the schedulers favour high ids, and with the low ids these warps took
+    // 18 k cycles to get through an EMPTY epilogue next to the producers (measured), which gates the next tile's MMAs.
+    const uint32_t ew = warp - 9;  // 0..7
+    const uint32_t qw = warp & 3u;                   // lane quadrant = the 32 rows this warp handles
     uint32_t tile_it = 0;
     const bool ln = (p.ln_out_g != nullptr);
-    float* tr = reinterpret_cast<float*>(smem + Cfg::OFF_TR) + warp * 32 * Cfg::TS;
+    float* tr = reinterpret_cast<float*>(smem + Cfg::OFF_TR) + ew * 32 * Cfg::TS;
     const float inv_k = 1.f / static_cast<float>(p.k), inv_n = 1.f / static_cast<float>(p.n);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
       const uint32_t b = tile_it % Cfg::ACC_BUFS, use = tile_it / Cfg::ACC_BUFS;
       mbar_wait(&acc_full[b], use & 1u, 11);
       tc_fence_after();
-      if (tid == 0) LIN_STAMP(tile_it, 4);
-      const int r = warp * 32 + lane;
-      const long long row0 = tile * 128 + warp * 32;  // first global row of this warp
-      const uint32_t trow = tbase + b * Cfg::ACC_STRIDE + ((warp * 32u) << 16);
+      if (ew == 0 && lane == 0) LIN_STAMP(tile_it, 4);
+      const int r = qw * 32 + lane;
+      const long long row0 = tile * 128 + qw * 32;  // first global row of this warp
+      const uint32_t trow = tbase + b * Cfg::ACC_STRIDE + ((qw * 32u) << 16);
       // input-side scalars of my row:  pre[c] = ga * acc[c] + gm * cs[c] + cb[c]   (acc is the GEMM of the SHIFTED row x - c)
       float ga = 1.f, gm = 0.f;
       if (need_stats) {
@@ -151,6 +160,10 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
       // (the block loops below are deliberately NOT unrolled: fully unrolled they are ~250 KB of code that is executed once
       //  per tile and streams through the instruction cache)
       constexpr int NBLK = (NPAD + 31) / 32;
+      // blocks this warp emits (the LayerNorm statistics pass always covers the whole row)
+      constexpr int HALF_BLK = (NBLK + 1) / 2;
+      const int blk_lo = (Cfg::EPI_WARPS == 8 && ew >= 4) ? HALF_BLK : 0;
+      const int blk_hi = (Cfg::EPI_WARPS == 8 && ew < 4) ? HALF_BLK : NBLK;
       auto load_blk = [&](int blk, float (&v)[32]) {
         tmem_ld16(trow + blk * 32, v);
         if (blk * 32 + 16 < NPAD) tmem_ld16(trow + blk * 32 + 16, v + 16);
@@ -194,16 +207,25 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
             }
           }
         };
-        load_blk(0, va);
+        if constexpr (Cfg::EPI_WARPS == 8) {  // two warps per scheduler hide the TMEM latency: one buffer, fewer registers
 #pragma unroll 1
-        for (int blk = 0; blk < NBLK; blk += 2) {
-          tmem_wait_ld();
-          if (blk + 1 < NBLK) load_blk(blk + 1, vb);
-          accumulate(blk, va);
-          if (blk + 1 < NBLK) {
+          for (int blk = 0; blk < NBLK; ++blk) {
+            load_blk(blk, va);
             tmem_wait_ld();
-            if (blk + 2 < NBLK) load_blk(blk + 2, va);
-            accumulate(blk + 1, vb);
+            accumulate(blk, va);
+          }
+        } else {
+          load_blk(0, va);
+#pragma unroll 1
+          for (int blk = 0; blk < NBLK; blk += 2) {
+            tmem_wait_ld();
+            if (blk + 1 < NBLK) load_blk(blk + 1, vb);
+            accumulate(blk, va);
+            if (blk + 1 < NBLK) {
+              tmem_wait_ld();
+              if (blk + 2 < NBLK) load_blk(blk + 2, va);
+              accumulate(blk + 1, vb);
+            }
           }
         }
         const float d = s * inv_n;
@@ -229,6 +251,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
         }
         const int cmul = p.out_blocked ? p.rows_per_block * 4 : 4;
         const float nm = -mean * rstd;
+        if (ew == 0 && lane == 0) LIN_STAMP(tile_it, 6);
         float va[32], vb[32];
         auto emit = [&](int blk, float (&v)[32]) {
           activate(blk, v);
@@ -269,26 +292,36 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
             }
           }
         };
-        load_blk(0, va);
+        if constexpr (Cfg::EPI_WARPS == 8) {
 #pragma unroll 1
-        for (int blk = 0; blk < NBLK; blk += 2) {
-          tmem_wait_ld();
-          if (blk + 1 < NBLK) load_blk(blk + 1, vb);
-          emit(blk, va);
-          if (blk + 1 < NBLK) {
+          for (int blk = blk_lo; blk < blk_hi; ++blk) {
+            load_blk(blk, va);
             tmem_wait_ld();
-            if (blk + 2 < NBLK) load_blk(blk + 2, va);
-            emit(blk + 1, vb);
+            emit(blk, va);
+          }
+        } else {
+          load_blk(blk_lo, va);
+#pragma unroll 1
+          for (int blk = blk_lo; blk < blk_hi; blk += 2) {
+            tmem_wait_ld();
+            if (blk + 1 < blk_hi) load_blk(blk + 1, vb);
+            emit(blk, va);
+            if (blk + 1 < blk_hi) {
+              tmem_wait_ld();
+              if (blk + 2 < blk_hi) load_blk(blk + 2, va);
+              emit(blk + 1, vb);
+            }
           }
         }
       }
+      if (ew == 0 && lane == 0) LIN_STAMP(tile_it, 7);
       tc_fence_before();
       mbar_arrive(&acc_empty[b]);
-      if (tid == 0) LIN_STAMP(tile_it, 5);
+      if (ew == 0 && lane == 0) LIN_STAMP(tile_it, 5);
     }
-  } else if (warp < 12) {
-    // ------------------------------------------------------------------ producers
-    const uint32_t ptid = tid - 128;
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ producers (warps 0-7)
+    const uint32_t ptid = tid;
     constexpr int K8 = Cfg::K8, NI = Cfg::ITEMS, PREF = Cfg::PREF;
     const int k8 = ptid % K8;
     const int rbase = ptid / K8;                 // my rows of a tile: rbase + i * (256 / K8)
@@ -405,7 +438,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
       }
     }
   } else {
-    // -------------------------------------------------------------------- MMA issuer: the whole warp runs the control flow
+    // -------------------------------------------------------------------- MMA issuer (warp 8): the whole warp runs the control flow
     // (waits included), one elected lane issues -- in converged code the descriptors stay in uniform registers, under a
     // `lane == 0` branch every tcgen05.mma sits in a lane-by-lane waterfall loop (~130 cycles per MMA measured)
     uint32_t it = 0, tile_it = 0;
@@ -451,7 +484,7 @@ __global__ void __launch_bounds__(416, 1) linear_kernel(LinearDev p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc<Cfg::TMEM_COLS>(tbase);
+  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tbase);
 }
 
 }  // namespace stg

@@ -60,7 +60,8 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 // Bounded wait (4 s of wall clock).  On timeout the error flag is raised and the caller carries on with garbage (the host
 // checks the flag) instead of hanging the GPU.  The %globaltimer read between two attempts doubles as a short back-off:
 // A/B on B200 (same box, configs[1]): this loop 14.16 ms/step, a bare attempt loop 14.67, __nanosleep(20..100) between
-// attempts 14.61; the value of the suspend hint (500 ns .. 1 ms) makes no difference, its presence does.
+// attempts 14.61; the value of the suspend hint (500 ns .. 1 ms) makes no difference, its presence does; an additional
+// exponential __nanosleep back-off (32 .. 2048 ns) changes nothing either.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned code = 1) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0, t1;
