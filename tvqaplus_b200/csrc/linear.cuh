@@ -44,7 +44,7 @@ struct LinearCfg {
   static constexpr uint32_t B_STAGE = 2u * B_PART;
   static constexpr uint32_t STAGE_BYTES = (A_STAGE + B_STAGE + 127u) & ~127u;
   static constexpr int TS = 36;                                  // fp32 row stride of a warp's 32x32 transpose buffer
-  static constexpr uint32_t TR_BYTES = ((2 * NPAD <= 512 && NPAD <= 256) ? 4u : 8u) * 32u * TS * 4u;  // one 4.6 KB buffer per epilogue warp
+  static constexpr uint32_t TR_BYTES = 8u * 32u * TS * 4u;       // 36864: one 4.6 KB buffer per epilogue warp
   static constexpr uint32_t VEC_BYTES = 4u * NPAD * 4u;          // cs | cb (or bias) | ln_out gamma | ln_out beta
   static constexpr uint32_t OFF_TR = STAGES * STAGE_BYTES;
   static constexpr uint32_t OFF_VEC = OFF_TR + TR_BYTES;
@@ -55,10 +55,10 @@ struct LinearCfg {
   static constexpr int N0 = NPAD <= 256 ? NPAD : ((NPAD / 2 + 15) / 16 * 16);  // first MMA N; second = NPAD - N0
   // With a single accumulator (N > 256) the epilogue cannot hide behind the next tile's MMAs, so it gets a second set of
   // four warps (13-16) that takes the upper half of the 32-column blocks.
-  static constexpr int EPI_WARPS = (ACC_BUFS == 1) ? 8 : 4;
+  static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = (EPI_WARPS == 8) ? 544 : 416;
   static constexpr int ITEMS = 128 * K8 / 256;  // (row, 8-column slot) pairs per producer thread per chunk
-  static constexpr int PREF = (KC == 32) ? (EPI_WARPS == 8 ? 2 : 4) : 2;  // chunks of global loads in flight per producer thread
+  static constexpr int PREF = (KC == 32) ? 2 : 1;  // chunks of global loads in flight per producer thread
 };
 
 struct LinearDev {
@@ -332,28 +332,38 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
     const bool wide = (p.k & 7) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 31u) == 0;  // rows and slots are 32-byte aligned
     long long ptl = 0;  // (tile, chunk) of the next prefetch
     int pc = 0;
-    auto issue = [&](float4 (&dst)[NI][2]) {
+    // my rows of the prefetch tile: slot-0 address of each (nullptr = row beyond m / tile beyond my last), set when the
+    // prefetch moves on to a new tile -- the per-chunk address is then one add
+    const float* rowp[NI];
+    auto set_rows = [&]() {
       const long long row0 = (blockIdx.x + ptl * gridDim.x) * 128;
-      const int k0 = pc * KC + k8 * 8;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const long long gr = row0 + rbase + i * (256 / K8);
-        const float4* src = reinterpret_cast<const float4*>(p.x + gr * p.k + k0);
-        const bool ok = ptl < my_tiles && gr < p.m;
-        if (wide) {  // one 256-bit request per 8-column slot: every 32-byte sector is fetched once, by one instruction
-          if (ok && k0 + 8 <= p.k) {
-            ldg256(src, dst[i][0], dst[i][1]);
+        rowp[i] = (ptl < my_tiles && gr < p.m) ? p.x + gr * p.k + k8 * 8 : nullptr;
+      }
+    };
+    set_rows();
+    auto issue = [&](float4 (&dst)[NI][2]) {
+      const int k0 = pc * KC + k8 * 8;
+      const bool in4 = k0 + 4 <= p.k, in8 = k0 + 8 <= p.k;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float4* src = reinterpret_cast<const float4*>(rowp[i] + pc * KC);
+        dst[i][0] = dst[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rowp[i] != nullptr) {
+          if (wide) {  // one 256-bit request per 8-column slot: every 32-byte sector is fetched once, by one instruction
+            if (in8) ldg256(src, dst[i][0], dst[i][1]);
           } else {
-            dst[i][0] = dst[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in4) dst[i][0] = __ldg(src);
+            if (in8) dst[i][1] = __ldg(src + 1);
           }
-        } else {
-          dst[i][0] = (ok && k0 + 4 <= p.k) ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[i][1] = (ok && k0 + 8 <= p.k) ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (++pc == p.n_chunks) {
         pc = 0;
         ++ptl;
+        set_rows();
       }
     };
 #pragma unroll
@@ -362,9 +372,13 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
     uint32_t it = 0;  // flat chunk counter (stage / phase tracking)
     long long tl = 0;
     int c = 0;
-    float cshift[NI], s1[NI], s2[NI];
+    float cshift[NI];
+    float2 s1[NI], s2[NI];  // packed partial sums (even, odd columns)
 #pragma unroll
-    for (int i = 0; i < NI; ++i) cshift[i] = s1[i] = s2[i] = 0.f;
+    for (int i = 0; i < NI; ++i) {
+      cshift[i] = 0.f;
+      s1[i] = s2[i] = make_float2(0.f, 0.f);
+    }
     for (long long g0 = 0; g0 < total; g0 += PREF) {
 #pragma unroll
       for (int d = 0; d < PREF; ++d) {
@@ -374,45 +388,64 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
           uint8_t* sB = sA + Cfg::A_STAGE;
           const int kleft = p.k - (c * KC + k8 * 8);  // valid columns of my 8-column slot in this chunk
           if (ptid == 0 && c == 0) LIN_STAMP(tl, 0);
-          HL8 hl[NI];
+          const bool full = (c + 1) * KC <= p.k;  // every slot of this chunk lies inside K: nothing to mask
+          // KC = 64 (four items per thread): wait for the stage first, then every item goes from registers straight to
+          // shared memory; KC = 32: convert first so that the conversion hides the wait (16 registers parked)
+          constexpr bool WAIT_FIRST = (NI > 2);
+          auto claim_stage = [&]() {
+            mbar_wait(&empty_bar[s], (use & 1u) ^ 1u, 10);
+            if (ptid == 0) {
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::B_STAGE);
+              bulk_g2s(sB, p.w + static_cast<size_t>(c) * Cfg::B_STAGE, Cfg::B_STAGE, &full_bar[s]);
+            }
+          };
+          if constexpr (WAIT_FIRST) claim_stage();
+          HL8 hl[WAIT_FIRST ? 1 : NI];
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
-            float v[8] = {buf[d][i][0].x, buf[d][i][0].y, buf[d][i][0].z, buf[d][i][0].w,
-                          buf[d][i][1].x, buf[d][i][1].y, buf[d][i][1].z, buf[d][i][1].w};
+            float2 v0 = lo2(buf[d][i][0]), v1 = hi2(buf[d][i][0]), v2 = lo2(buf[d][i][1]), v3 = hi2(buf[d][i][1]);
             if (need_stats) {
               if (c == 0) {
                 // with LN_in the row is shifted by its first element (held by the k8 == 0 lane) BEFORE it meets the tensor
                 // cores: a constant row then gives exactly beta and a large common offset costs no GEMM precision
-                const float first = __shfl_sync(0xffffffffu, v[0], lane & ~(K8 - 1));
+                const float first = __shfl_sync(0xffffffffu, v0.x, lane & ~(K8 - 1));
                 cshift[i] = (p.cs != nullptr) ? first : 0.f;
-                s1[i] = 0.f;
-                s2[i] = 0.f;
+                s1[i] = s2[i] = make_float2(0.f, 0.f);
               }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[j] = (j < kleft) ? v[j] - cshift[i] : 0.f;
-                s1[i] += v[j];
-                s2[i] = fmaf(v[j], v[j], s2[i]);
+              const float2 nc = dup2(-cshift[i]);
+              v0 = add2(v0, nc); v1 = add2(v1, nc); v2 = add2(v2, nc); v3 = add2(v3, nc);
+              if (!full) {  // the chunk that crosses K: columns >= K contribute nothing (the shift made them non-zero)
+                v0.x = 0 < kleft ? v0.x : 0.f; v0.y = 1 < kleft ? v0.y : 0.f; v1.x = 2 < kleft ? v1.x : 0.f; v1.y = 3 < kleft ? v1.y : 0.f;
+                v2.x = 4 < kleft ? v2.x : 0.f; v2.y = 5 < kleft ? v2.y : 0.f; v3.x = 6 < kleft ? v3.x : 0.f; v3.y = 7 < kleft ? v3.y : 0.f;
               }
+              s1[i] = add2(s1[i], add2(add2(v0, v1), add2(v2, v3)));
+              s2[i] = fma2(v0, v0, fma2(v1, v1, fma2(v2, v2, fma2(v3, v3, s2[i]))));
             }
-            hl[i] = split8(v);
+            HL8& h8 = hl[WAIT_FIRST ? 0 : i];
+            split2p(v0, h8.hi.x, h8.lo.x);
+            split2p(v1, h8.hi.y, h8.lo.y);
+            split2p(v2, h8.hi.z, h8.lo.z);
+            split2p(v3, h8.hi.w, h8.lo.w);
+            if constexpr (WAIT_FIRST) {
+              uint8_t* dst = sA + k8 * Cfg::LBO_A + (rbase + i * (256 / K8)) * 16;
+              *reinterpret_cast<uint4*>(dst) = h8.hi;
+              *reinterpret_cast<uint4*>(dst + Cfg::A_PART) = h8.lo;
+            }
           }
           issue(buf[d]);  // refill this register buffer: the loads fly while the next chunks are converted
-          mbar_wait(&empty_bar[s], (use & 1u) ^ 1u, 10);
-          if (ptid == 0) {
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_STAGE);
-            bulk_g2s(sB, p.w + static_cast<size_t>(c) * Cfg::B_STAGE, Cfg::B_STAGE, &full_bar[s]);
-          }
+          if constexpr (!WAIT_FIRST) {
+            claim_stage();
 #pragma unroll
-          for (int i = 0; i < NI; ++i) {
-            uint8_t* dst = sA + k8 * Cfg::LBO_A + (rbase + i * (256 / K8)) * 16;
-            *reinterpret_cast<uint4*>(dst) = hl[i].hi;
-            *reinterpret_cast<uint4*>(dst + Cfg::A_PART) = hl[i].lo;
+            for (int i = 0; i < NI; ++i) {
+              uint8_t* dst = sA + k8 * Cfg::LBO_A + (rbase + i * (256 / K8)) * 16;
+              *reinterpret_cast<uint4*>(dst) = hl[WAIT_FIRST ? 0 : i].hi;
+              *reinterpret_cast<uint4*>(dst + Cfg::A_PART) = hl[WAIT_FIRST ? 0 : i].lo;
+            }
           }
           if (need_stats && c == p.n_chunks - 1) {  // the row statistics travel with the last chunk of the tile
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
-              float a = s1[i], q = s2[i];
+              float a = s1[i].x + s1[i].y, q = s2[i].x + s2[i].y;
 #pragma unroll
               for (int o = 1; o < K8; o <<= 1) {
                 a += __shfl_xor_sync(0xffffffffu, a, o);

@@ -128,7 +128,7 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
   d.y = a->y; d.m = a->m; d.k = a->k; d.n = a->n; d.n_chunks = g.n_chunks; d.l2norm_in = a->l2norm_in; d.relu = a->relu;
   d.out_blocked = 0; d.rows_per_block = 1; d.timeline = a->timeline;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->n <= 128) return launch_linear<128, 64, 3>(d, s);
+  if (a->n <= 128) return launch_linear<128, 64, 2>(d, s);
   return launch_linear<304, 32, 3>(d, s);
 }
 
@@ -275,7 +275,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
     d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.cs = nullptr; d.cb = nullptr;
     d.ln_out_g = nullptr; d.ln_out_b = nullptr; d.y = za; d.m = static_cast<long long>(a->n) * 5 * a->lq;
     d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0; d.out_blocked = 1; d.rows_per_block = 5 * a->lq; d.timeline = nullptr;
-    int rc = launch_linear<128, 64, 3>(d, s);
+    int rc = launch_linear<128, 64, 2>(d, s);
     if (rc) return rc;
   }
   // 3. the fused kernel
