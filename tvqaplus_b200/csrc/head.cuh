@@ -45,11 +45,11 @@ __device__ __forceinline__ float4 ln128(float4 v, float4 g, float4 b) {
   return make_float4(a * rs * g.x + b.x, c * rs * g.y + b.y, d * rs * g.z + b.z, e * rs * g.w + b.w);
 }
 
-__global__ void __launch_bounds__(256, 1) head_kernel(HeadDev p) {
+__global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
   extern __shared__ __align__(16) float hs[];
   float* Wt = hs;                      // [128 k][128 c] transposed projection weight
-  float* lnv = Wt + 128 * 128;         // [8 warps][128] LN(x) staging
-  float* sc = lnv + 8 * 128;           // [t][2] masked scores, then probabilities
+  float* lnv = Wt + 128 * 128;         // [8 warps][2 frames][128] LN(x) staging
+  float* sc = lnv + 16 * 128;           // [t][2] masked scores, then probabilities
   float* fm = sc + 2 * p.t;            // [t] frame mask (max_statement_mask)
   float* feat = fm + p.t;              // [256] classifier input
   __shared__ float red[8];
@@ -63,11 +63,21 @@ __global__ void __launch_bounds__(256, 1) head_kernel(HeadDev p) {
     const int c = i >> 7, k = i & 127;
     Wt[k * 128 + c] = __ldg(p.proj_w + i);
   }
-  for (int t = tid; t < T; t += 256) {
-    const float* m = p.statement_mask + (static_cast<size_t>(row) * T + t) * p.lq;
-    float s = 0.f;
-    for (int l = 0; l < p.lq; ++l) s += __ldg(m + l);
-    fm[t] = (s != 0.f) ? 1.f : 0.f;
+  // frame mask = "any token of the statement is valid" (max_statement_mask, stage.py:505): the row's T*lq mask values are
+  // one contiguous block; every thread keeps eight independent loads in flight and raises the frame's flag
+  for (int t = tid; t < T; t += 256) fm[t] = 0.f;
+  __syncthreads();
+  {
+    const float* mrow = p.statement_mask + static_cast<size_t>(row) * T * p.lq;
+    const int total = T * p.lq;
+    for (int base = tid; base < total; base += 256 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (base + u * 256 < total) ? __ldg(mrow + base + u * 256) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (v[u] != 0.f) fm[(base + u * 256) / p.lq] = 1.f;  // benign race: every writer stores the same value
+    }
   }
   __syncthreads();
 
@@ -79,35 +89,59 @@ __global__ void __launch_bounds__(256, 1) head_kernel(HeadDev p) {
   const float4 ew = __ldg(reinterpret_cast<const float4*>(p.ed_w) + lane);
   const float st_bias = __ldg(p.st_bias), ed_bias = __ldg(p.ed_bias);
 
-  // ---- per frame: residual projection + st/ed logits (warp per frame, lane = 4 channels)
-  for (int t = warp; t < T; t += 8) {
-    const size_t off = (static_cast<size_t>(row) * T + t) * 128;
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p.max_statement + off) + lane);
-    const float4 l = ln128(x, pg, pb);
+  // ---- per frame: residual projection + st/ed logits (warp per PAIR of frames, lane = 4 channels: one weight row read
+  //      from shared memory serves both frames and the eight accumulator chains hide the FMA latency)
+  float4 gmax = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f);  // masked max over this warp's frames (global feature)
+  for (int t0 = warp * 2; t0 < T; t0 += 16) {
+    const bool two = t0 + 1 < T;
+    const size_t off0 = (static_cast<size_t>(row) * T + t0) * 128, off1 = off0 + 128;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.max_statement + off0) + lane);
+    const float4 x1 = two ? __ldg(reinterpret_cast<const float4*>(p.max_statement + off1) + lane) : x0;
+    const float4 l0 = ln128(x0, pg, pb), l1 = ln128(x1, pg, pb);
+    float* lv = lnv + warp * 256;
     __syncwarp();
-    *reinterpret_cast<float4*>(lnv + warp * 128 + lane * 4) = l;
+    *reinterpret_cast<float4*>(lv + lane * 4) = l0;
+    *reinterpret_cast<float4*>(lv + 128 + lane * 4) = l1;
     __syncwarp();
-    float4 acc = pbias;
-#pragma unroll 8
-    for (int k = 0; k < 128; ++k) {
-      const float a = lnv[warp * 128 + k];
-      const float4 w = *reinterpret_cast<const float4*>(Wt + k * 128 + lane * 4);
-      acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
+    float4 acc0 = pbias, acc1 = pbias;
+#pragma unroll 4
+    for (int k = 0; k < 128; k += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(lv + k), a1 = *reinterpret_cast<const float4*>(lv + 128 + k);
+      const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w = *reinterpret_cast<const float4*>(Wt + (k + e) * 128 + lane * 4);
+        acc0.x = fmaf(av0[e], w.x, acc0.x); acc0.y = fmaf(av0[e], w.y, acc0.y); acc0.z = fmaf(av0[e], w.z, acc0.z); acc0.w = fmaf(av0[e], w.w, acc0.w);
+        acc1.x = fmaf(av1[e], w.x, acc1.x); acc1.y = fmaf(av1[e], w.y, acc1.y); acc1.z = fmaf(av1[e], w.z, acc1.z); acc1.w = fmaf(av1[e], w.w, acc1.w);
+      }
     }
-    const float4 y = make_float4(x.x + fmaxf(acc.x, 0.f), x.y + fmaxf(acc.y, 0.f), x.z + fmaxf(acc.z, 0.f), x.w + fmaxf(acc.w, 0.f));
-    *reinterpret_cast<float4*>(p.enc + off + lane * 4) = y;
-    const float4 ls = ln128(y, sg, sb), le = ln128(y, eg, eb);
-    const float s_st = warp_sum((ls.x * sw.x + ls.y * sw.y) + (ls.z * sw.z + ls.w * sw.w)) + st_bias;
-    const float s_ed = warp_sum((le.x * ew.x + le.y * ew.y) + (le.z * ew.z + le.w * ew.w)) + ed_bias;
-    if (lane == 0) {
-      const float m = __ldg(p.ts_mask + static_cast<size_t>(n_i) * T + t);
-      const float off_m = (1.f - m) * STG_NEG;
-      const float a0 = s_st * m + off_m, a1 = s_ed * m + off_m;  // mask_logits
-      sc[2 * t] = a0; sc[2 * t + 1] = a1;
-      p.t_scores[(static_cast<size_t>(row) * T + t) * 2] = a0;
-      p.t_scores[(static_cast<size_t>(row) * T + t) * 2 + 1] = a1;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      if (f == 1 && !two) break;
+      const int t = t0 + f;
+      const float4 x = f == 0 ? x0 : x1, acc = f == 0 ? acc0 : acc1;
+      const size_t off = f == 0 ? off0 : off1;
+      const float4 y = make_float4(x.x + fmaxf(acc.x, 0.f), x.y + fmaxf(acc.y, 0.f), x.z + fmaxf(acc.z, 0.f), x.w + fmaxf(acc.w, 0.f));
+      *reinterpret_cast<float4*>(p.enc + off + lane * 4) = y;
+      {
+        const float m = fm[t], o = (1.f - m) * STG_NEG;  // mask_logits, then max over frames (stage.py:456-466)
+        gmax = make_float4(fmaxf(gmax.x, y.x * m + o), fmaxf(gmax.y, y.y * m + o), fmaxf(gmax.z, y.z * m + o), fmaxf(gmax.w, y.w * m + o));
+      }
+      const float4 ls = ln128(y, sg, sb), le = ln128(y, eg, eb);
+      const float s_st = warp_sum((ls.x * sw.x + ls.y * sw.y) + (ls.z * sw.z + ls.w * sw.w)) + st_bias;
+      const float s_ed = warp_sum((le.x * ew.x + le.y * ew.y) + (le.z * ew.z + le.w * ew.w)) + ed_bias;
+      if (lane == 0) {
+        const float m = __ldg(p.ts_mask + static_cast<size_t>(n_i) * T + t);
+        const float off_m = (1.f - m) * STG_NEG;
+        const float a0 = s_st * m + off_m, a1 = s_ed * m + off_m;  // mask_logits
+        sc[2 * t] = a0; sc[2 * t + 1] = a1;
+        p.t_scores[(static_cast<size_t>(row) * T + t) * 2] = a0;
+        p.t_scores[(static_cast<size_t>(row) * T + t) * 2 + 1] = a1;
+      }
     }
   }
+  __syncwarp();
+  *reinterpret_cast<float4*>(lnv + warp * 256 + lane * 4) = gmax;  // the staging rows are free now: [warp][128] partial maxima
   __syncthreads();
 
   // ---- softmax over frames for st (c=0) and ed (c=1)
@@ -146,21 +180,38 @@ __global__ void __launch_bounds__(256, 1) head_kernel(HeadDev p) {
   }
   __syncthreads();
 
-  // ---- span-local and global masked max over frames (thread = channel; threads 128.. do the global one)
+  // ---- global masked max: the eight per-warp partial maxima; span-local masked max: frames [st-E, ed+1+E) re-read from
+  //      the workspace this CTA wrote (L2), four loads in flight per thread
   {
     const int c = tid & 127;
-    int lo = 0, hi = T;
-    if (tid < 128) {
-      lo = span_sh[0] - p.extra; if (lo < 0) lo = 0;
-      hi = span_sh[1] + 1 + p.extra; if (hi > T) hi = T;
+    if (tid >= 128) {
+      float mx = lnv[c];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, lnv[w * 256 + c]);
+      feat[p.add_local ? tid : c] = mx;
+    } else if (p.add_local) {
+      int lo = span_sh[0] - p.extra, hi = span_sh[1] + 1 + p.extra;
+      if (lo < 0) lo = 0;
+      if (hi > T) hi = T;
+      const float* e = p.enc + static_cast<size_t>(row) * T * 128 + c;
+      float mx = -3.0e38f;
+      int t = lo;
+      for (; t + 4 <= hi; t += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcg(e + static_cast<size_t>(t + u) * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float m = fm[t + u];
+          mx = fmaxf(mx, v[u] * m + (1.f - m) * STG_NEG);
+        }
+      }
+      for (; t < hi; ++t) {
+        const float m = fm[t];
+        mx = fmaxf(mx, __ldcg(e + static_cast<size_t>(t) * 128) * m + (1.f - m) * STG_NEG);
+      }
+      feat[tid] = mx;
     }
-    float mx = -3.0e38f;
-    for (int t = lo; t < hi; ++t) {
-      const float m = fm[t];
-      const float v = p.enc[(static_cast<size_t>(row) * T + t) * 128 + c] * m + (1.f - m) * STG_NEG;
-      mx = fmaxf(mx, v);
-    }
-    if (p.add_local) feat[tid] = mx; else if (tid >= 128) feat[c] = mx;
   }
   __syncthreads();
 

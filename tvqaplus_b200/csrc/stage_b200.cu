@@ -321,7 +321,7 @@ int stage_span_head_fwd(const StageHeadArgs* a, void* stream) {
   d.cls_g = a->cls_ln_g; d.cls_b = a->cls_ln_b; d.cls_w = a->cls_w; d.cls_bias = a->cls_b;
   d.t_scores = a->t_scores; d.t_probs = a->t_probs; d.spans = a->spans; d.span_conf = a->span_conf; d.answer = a->answer;
   d.enc = a->workspace;
-  const size_t smem = (128 * 128 + 8 * 128 + 3 * static_cast<size_t>(a->t) + 256) * sizeof(float);
+  const size_t smem = (128 * 128 + 16 * 128 + 3 * static_cast<size_t>(a->t) + 256) * sizeof(float);
   int rc = set_smem(head_kernel, smem, "span_head");
   if (rc) return rc;
   head_kernel<<<a->n * 5, 256, smem, static_cast<cudaStream_t>(stream)>>>(d);
