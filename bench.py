@@ -273,17 +273,26 @@ def main():
     T, R, Lq, Ls = SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"]
     with torch.no_grad():
         a_embed = model.base_encoder(dbatch.qas_bert.view(N * 5, Lq, 768), dbatch.qas_mask.view(N * 5, Lq), model._text_fc, None, model.input_encoder).view(N, 5, Lq, H)
-        sub_embed = model.base_encoder(dbatch.sub_bert.view(N * T, Ls, 768), dbatch.sub_mask.view(N * T, Ls), model._text_fc, None, model.input_encoder).view(N, T, Ls, H)
         vid_embed = model.base_encoder(dbatch.vid.view(N * T, R, 300), dbatch.vid_mask.view(N * T, R), model._vid_fc, None, model.input_encoder).view(N, T, R, H)
+        # like STAGE.forward: the sub-title encoder writes its output into the context blobs of the CQA workspace, so the
+        # timed launch is what the forward runs (preparation of answers + regions, a.Wa, the fused kernel)
+        ws = ops.CqaWorkspace(N, T, Lq, dev)
+        sub_embed = None
+        if model.input_encoder.can_write_cqa_workspace(Ls):
+            model.input_encoder(model._text_fc(dbatch.sub_bert.view(N * T, Ls, 768)), dbatch.sub_mask.view(N * T, Ls), cqa_workspace=ws)
+        else:
+            sub_embed = model.base_encoder(dbatch.sub_bert.view(N * T, Ls, 768), dbatch.sub_mask.view(N * T, Ls), model._text_fc, None, model.input_encoder).view(N, T, Ls, H)
         w = model._cqa_weights()
         blk = ops.blocked_fits(Lq)  # the same statement layout STAGE.forward uses
-        ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale, blocked=blk)
+        run_cqa = lambda: ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale,
+                                            blocked=blk, workspace=ws)
+        run_cqa()
         torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
         k0.record()
         for _ in range(reps):
-            ops.cqa_fused_fwd(a_embed, dbatch.qas_mask, sub_embed, dbatch.sub_mask, vid_embed, dbatch.vid_mask, w, opt.scale, blocked=blk)
+            run_cqa()
         k1.record()
         torch.cuda.synchronize()
     cqa_ms = k0.elapsed_time(k1) / reps

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define STAGE_ABI_VERSION 1
+#define STAGE_ABI_VERSION 2
 #define STAGE_HSZ 128          /* opt.hsz the kernels are specialised for (config.py:103) */
 #define STAGE_MAX_SEQ 128      /* longest token/region axis one encoder tile holds */
 #define STAGE_MAX_CONV 4       /* n_conv per encoder block (config.py:108,114 default 2) */
@@ -81,6 +81,10 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream);
  * x + pe -> n_conv x [LN -> depthwise conv(k, zero pad k/2) -> pointwise 128x128 -> ReLU -> + residual] -> LN.
  * With self-attention (n_heads > 0) the caller passes STAGE_ENC_NO_FINAL_LN here and finishes the block with
  * stage_mha_fwd (LN -> MHA -> + residual -> LN).
+ * out_mode 2 (STAGE_ENC_OUT_CQA_SUB): the closing LayerNorm output of sequence i goes straight into the sub-title part of
+ * context blob i of a stage_cqa_fused_fwd workspace (split-fp16 operand image, inverse L2 norms, masks; y = the blob
+ * base stage_cqa_ctx_blobs(workspace, ..)), so that stage_cqa_fused_fwd(sub_prepared = 1) needs neither the fp32 sub-title
+ * embeddings nor a conversion pass over them.  Needs a mask and 64 < L <= 112 (one sequence per tile).
  * out_mode 0: y[n_seq,L,128].  out_mode 1: masked max-pool over L (mask_logits + max, model/stage.py:503):
  * y[n_seq,128].  L <= 128. */
 #define STAGE_ENC_NO_PE 1        /* skip the position-encoding add */
@@ -177,9 +181,15 @@ typedef struct {
   float* att_sub;              /* optional */
   float* mixed_vid;            /* optional [n,5,t,lq,128] c2q output */
   float* mixed_sub;            /* optional */
-  long long* timeline;         /* optional debug: [2][64][16] SM clock stamps of CTA 0 (see tools/cqa_timeline.py) */
+  long long* timeline;         /* optional debug: [4][64][16] SM clock stamps of CTA 0 (see tools/cqa_timeline.py) */
+  int sub_prepared;            /* 1: the sub-title parts of the context blobs were written by stage_encoder_block_fwd(out_mode 2);
+                                  sub_embed may then be NULL */
 } StageCqaArgs;
 int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream);
+/* first context blob (one per (example, frame), stage_cqa_ctx_blob_bytes() apart) inside a workspace of
+ * stage_cqa_workspace_bytes(n, t, lq) bytes: the y argument of stage_encoder_block_fwd(out_mode 2) */
+void* stage_cqa_ctx_blobs(void* workspace, int n, int t, int lq);
+size_t stage_cqa_ctx_blob_bytes(void);
 
 /* ---- span + answer heads -------------------------------------------------------------------------------------------
  * residual_temporal_predictor, mask, softmax over frames, best (st<=ed) span, span-local / global masked max,

@@ -90,3 +90,48 @@ def test_cqa_fused(N, T, Lq, Ls, R, dense):
     # statement written without the optional outputs must be identical
     got2 = run_gpu(*case, scale=10.0, want=())
     assert torch.equal(got2["statement"], got["statement"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,Lq,Ls,R,k", [(2, 5, 40, 100, 20, 7), (1, 3, 100, 70, 9, 7), (2, 4, 24, 112, 30, 5)])
+def test_encoder_writes_cqa_context_blobs(N, T, Lq, Ls, R, k):
+    """Internal fast path of STAGE.forward: the sub-title input encoder writes its closing-LayerNorm output straight into
+    the context blobs of the CQA workspace (stage_encoder_block_fwd out_mode 2 + stage_cqa_fused_fwd sub_prepared).  The
+    result must match the two-step path (encoder -> fp32 -> preparation pass) to rounding of the inverse norms."""
+    from tests.test_encoder_gpu import random_block
+    dev = torch.device("cuda:0")
+    a, am, s_raw, sm, v, vm, sd = make_case(N, T, Lq, Ls, R, seed=N * 100 + Ls)
+    g = torch.Generator().manual_seed(5)
+    esd = {kk: vv.to(dev) for kk, vv in random_block("enc", 2, k, g).items()}
+    convs = [dict(ln_g=esd["enc.layer_norm.%d.weight" % i], ln_b=esd["enc.layer_norm.%d.bias" % i],
+                  dw_w=esd["enc.conv.%d.depthwise_conv.weight" % i], dw_b=esd["enc.conv.%d.depthwise_conv.bias" % i],
+                  pw_packed=ops.pack_weight(esd["enc.conv.%d.pointwise_conv.weight" % i], 64),
+                  pw_b=esd["enc.conv.%d.pointwise_conv.bias" % i]) for i in range(2)]
+    fin = (esd["enc.final_layer_norm.weight"], esd["enc.final_layer_norm.bias"])
+    pe = esd["enc.position_encoding.pe"]
+    d = {kk: vv.to(dev) for kk, vv in sd.items()}
+    w = dict(wblob=ops.cqa_prepare_weights(d["c2q_down_projection.0.weight"], d["c2q_down_projection.0.bias"],
+                                           d["c2q_down_projection.2.weight"], d["c2q_down_projection.2.bias"],
+                                           d["concat_fc.0.weight"], d["concat_fc.0.bias"], d["concat_fc.2.weight"],
+                                           d["concat_fc.2.bias"]),
+             cat_out_ln_g=d["concat_fc.4.weight"], cat_out_ln_b=d["concat_fc.4.bias"])
+    x = (s_raw * sm[..., None]).view(N * T, Ls, 128).to(dev)
+    smd = sm.to(dev)
+    want_keys = ("sub_raw_s", "att_sub")
+    # two-step path
+    sub = ops.encoder_block_fwd(x, smd.view(N * T, Ls), pe, convs, fin, k).view(N, T, Ls, 128)
+    ref = ops.cqa_fused_fwd(a.to(dev), am.to(dev), sub, smd, v.to(dev), vm.to(dev), w, 10.0, want=want_keys)
+    # fused path
+    ws = ops.CqaWorkspace(N, T, Lq, dev)
+    assert ops.encoder_block_fwd(x, smd.view(N * T, Ls), pe, convs, fin, k, cqa_workspace=ws) is None
+    assert ws.sub_prepared and ws.sub_len == Ls
+    got = ops.cqa_fused_fwd(a.to(dev), am.to(dev), None, smd, v.to(dev), vm.to(dev), w, 10.0, want=want_keys, workspace=ws)
+    torch.cuda.synchronize()
+    _lib.check_device_error()
+    assert torch.equal(got["statement_mask"], ref["statement_mask"])
+    for key in ("statement",) + want_keys:
+        r_, g_ = ref[key], got[key]
+        live = r_ > -1e9  # raw scores carry exact -1e10 entries at masked pairs
+        assert torch.equal(live, g_ > -1e9)
+        err = (g_[live] - r_[live]).abs().max().item() / max(r_[live].abs().max().item(), 1e-9)
+        assert err < 1e-5, (key, err)

@@ -43,7 +43,7 @@ class CqaArgs(C.Structure):
                 ("wblob", _f), ("cat_out_ln_g", _f), ("cat_out_ln_b", _f), ("workspace", _f),
                 ("statement_blocked", C.c_int), ("statement", _f), ("statement_mask", _f), ("vid_raw_s", _f), ("sub_raw_s", _f),
                 ("vid_norm_s", _f), ("sub_norm_s", _f), ("att_vid", _f), ("att_sub", _f),
-                ("mixed_vid", _f), ("mixed_sub", _f), ("timeline", _f)]
+                ("mixed_vid", _f), ("mixed_sub", _f), ("timeline", _f), ("sub_prepared", C.c_int)]
 
 
 class HeadArgs(C.Structure):
@@ -80,6 +80,8 @@ SYMBOLS = {
     "stage_cqa_weight_blob_bytes": (C.c_size_t, []),
     "stage_cqa_prepare_weights": (C.c_int, [C.c_void_p] * 10),
     "stage_cqa_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "stage_cqa_ctx_blobs": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "stage_cqa_ctx_blob_bytes": (C.c_size_t, []),
     "stage_cqa_fused_fwd": (C.c_int, [C.POINTER(CqaArgs), C.c_void_p]),
     "stage_span_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
     "stage_find_max_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -102,7 +104,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.stage_abi_version() != 1:
+        if l.stage_abi_version() != 2:
             raise RuntimeError("tvqaplus_b200: ABI version mismatch in %s" % LIB_PATH)
         _lib = l
     return _lib

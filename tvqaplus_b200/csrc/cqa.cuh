@@ -103,13 +103,14 @@ struct CqaPrepDev {
   const float* vid_embed; const float* vid_mask;
   uint8_t* a_blob; uint8_t* ctx_blob;
   float* a_blk;  // fp32 copy of a_embed in the blocked layout [example][4-column group (32)][packed row (5*lq)] float4
+  int sub_prepared;  // the sub-title parts of the ctx blobs already exist (written by the input encoder): skip them
 };
 
 __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long n_a = static_cast<long long>(p.n) * p.n_pt * 128;
-  const long long n_s = static_cast<long long>(p.n) * p.t * p.ls_pad;
+  const long long n_s = p.sub_prepared ? 0 : static_cast<long long>(p.n) * p.t * p.ls_pad;
   const long long n_v = static_cast<long long>(p.n) * p.t * p.r_pad;
   if (warp >= n_a + n_s + n_v) return;
   const float* src = nullptr;

@@ -66,6 +66,8 @@ struct EncDev {
   int L, n_conv, out_mode, flags;
   int S;  // row stride of the blocked input layout (STAGE_ENC_IN_BLOCKED)
   long long* timeline;  // optional debug: [32 tiles][16] SM clock stamps of thread 0 of CTA 0 (tools/encoder_timeline.py)
+  // out_mode 2: geometry of the CQA context blob the sequence is written into (filled from CqaCfg by the host code)
+  uint32_t blob_bytes, blob_lbo, blob_part, blob_inv_off, blob_mask_off;
 };
 
 #define STG_NEG (-1e10f)
@@ -358,13 +360,48 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
           const float4 v = *reinterpret_cast<const float4*>(xh + j);
           const float4 g4 = *reinterpret_cast<const float4*>(fg + j), b4 = *reinterpret_cast<const float4*>(fb + j);
           float2 o0 = fma2(fma2(lo2(v), rsn, nmn), lo2(g4), lo2(b4)), o1 = fma2(fma2(hi2(v), rsn, nmn), hi2(g4), hi2(b4));
-          if (p.out_mode != 0) { o0 = fma2(o0, mm, off); o1 = fma2(o1, mm, off); }
+          if (p.out_mode == 1) { o0 = fma2(o0, mm, off); o1 = fma2(o1, mm, off); }
           *reinterpret_cast<float4*>(xh + j) = make_float4(o0.x, o0.y, o1.x, o1.y);
         }
       }
       ENC_BAR();
       ENC_STAMP(12);
-      if (p.out_mode == 0) {
+      if (p.out_mode == 2) {
+        // one sequence per tile (host-checked): row r = token r of frame `tile`.  The closing LayerNorm output (sitting in
+        // X now) becomes the split-fp16 image of the CQA context blob: 16 bytes per (row, 8-column group), lanes = rows, so
+        // a warp writes 512-byte runs; rows [L, round_up(L, 16)) are the zero padding of the image.
+        const int ls_pad = (L + 15) & ~15;
+        uint8_t* blob = reinterpret_cast<uint8_t*>(p.y) + static_cast<size_t>(tile) * p.blob_bytes;
+        float2 ss = make_float2(0.f, 0.f);
+        if (r < ls_pad) {
+#pragma unroll
+          for (int kg = 0; kg < 8; ++kg) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (live) {
+              a = *reinterpret_cast<const float4*>(xh + kg * 8);
+              b = *reinterpret_cast<const float4*>(xh + kg * 8 + 4);
+            }
+            ss = fma2(lo2(a), lo2(a), fma2(hi2(a), hi2(a), fma2(lo2(b), lo2(b), fma2(hi2(b), hi2(b), ss))));
+            uint4 hi, lo;
+            split2p(lo2(a), hi.x, lo.x);
+            split2p(hi2(a), hi.y, lo.y);
+            split2p(lo2(b), hi.z, lo.z);
+            split2p(hi2(b), hi.w, lo.w);
+            uint8_t* dst = blob + (h * 8 + kg) * p.blob_lbo + r * 16;
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + p.blob_part) = lo;
+          }
+        }
+        // the two half-row sums of squares meet in the row's padding (free again: the statistics were consumed above)
+        reinterpret_cast<float*>(xrow + 128)[h] = ss.x + ss.y;
+        ENC_BAR();
+        if (h == 0 && r < ls_pad) {
+          const float tot = xrow[128] + xrow[129];
+          // F.normalize: x / max(||x||, eps); a masked row stores 0 so that the CQA kernel needs one load, not two
+          reinterpret_cast<float*>(blob + p.blob_inv_off)[r] = (live && m_row != 0.f) ? 1.f / fmaxf(sqrtf(tot), 1e-12f) : 0.f;
+          reinterpret_cast<float*>(blob + p.blob_mask_off)[r] = live ? m_row : 0.f;
+        }
+      } else if (p.out_mode == 0) {
         for (int rr = warp; rr < n_valid; rr += 8)
           *reinterpret_cast<float4*>(p.y + (seq0 * L + rr) * 128 + lane * 4) = *reinterpret_cast<const float4*>(X + rr * XS + lane * 4);
       } else {

@@ -141,13 +141,17 @@ int stage_encoder_block_fwd(const StageEncoderArgs* a, void* stream) {
   STG_REQUIRE(a->n_seq > 0 && a->L > 0, STAGE_E_BADARG, "encoder: n_seq=%lld L=%d", (long long)a->n_seq, a->L);
   STG_REQUIRE(a->L <= STAGE_MAX_SEQ, STAGE_E_UNSUPPORTED, "encoder: L=%d > %d", a->L, STAGE_MAX_SEQ);
   STG_REQUIRE(a->n_conv >= 1 && a->n_conv <= STAGE_MAX_CONV, STAGE_E_UNSUPPORTED, "encoder: n_conv=%d", a->n_conv);
-  STG_REQUIRE(a->out_mode == 0 || (a->out_mode == 1 && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
+  STG_REQUIRE(a->out_mode == 0 || ((a->out_mode == 1 || a->out_mode == 2) && a->mask), STAGE_E_BADARG, "encoder: out_mode=%d needs a mask", a->out_mode);
+  STG_REQUIRE(a->out_mode != 2 || (a->L > 64 && a->L <= CqaCfg::LS_MAX && !(a->flags & STAGE_ENC_NO_FINAL_LN)), STAGE_E_UNSUPPORTED,
+              "encoder: out_mode 2 needs 64 < L <= %d (one sequence per tile) and the closing LayerNorm", CqaCfg::LS_MAX);
   STG_REQUIRE(aligned16(a->x) && aligned16(a->y) && (!a->pe || aligned16(a->pe)), STAGE_E_BADARG, "encoder: pointers must be 16-byte aligned");
   const int S = stage_blocked_stride(a->L);
   EncDev d;
   d.S = S;
   d.x = a->x; d.mask = a->mask; d.pe = a->pe; d.fin_g = a->final_ln_g; d.fin_b = a->final_ln_b; d.y = a->y;
   d.n_seq = a->n_seq; d.L = a->L; d.n_conv = a->n_conv; d.out_mode = a->out_mode; d.flags = a->flags; d.timeline = a->timeline;
+  d.blob_bytes = CqaCfg::CTX_BYTES; d.blob_lbo = CqaCfg::LBO_CS; d.blob_part = CqaCfg::CS_PART;
+  d.blob_inv_off = CqaCfg::CTX_CS_INV; d.blob_mask_off = CqaCfg::CTX_CS_MASK;
   for (int i = 0; i < STAGE_MAX_CONV; ++i) {
     const bool on = i < a->n_conv;
     if (on) STG_REQUIRE((a->ln_g[i] == nullptr) == (a->ln_b[i] == nullptr) && a->dw_w[i] && a->dw_b[i] && a->pw_packed[i] && a->pw_b[i], STAGE_E_BADARG,
@@ -237,15 +241,22 @@ size_t stage_cqa_workspace_bytes(int n, int t, int lq) {
          2 * align128(static_cast<size_t>(n) * 5 * lq * 128 * sizeof(float));  // a.Wa and the blocked fp32 answers
 }
 
+void* stage_cqa_ctx_blobs(void* workspace, int n, int t, int lq) {
+  if (!workspace || n <= 0 || t <= 0 || lq <= 0) return nullptr;
+  const size_t n_pt = (5 * static_cast<size_t>(lq) + 127) / 128;
+  return static_cast<uint8_t*>(workspace) + align128(static_cast<size_t>(n) * n_pt * CqaCfg::ABLOB_BYTES);
+}
+size_t stage_cqa_ctx_blob_bytes(void) { return CqaCfg::CTX_BYTES; }
+
 int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
-  STG_REQUIRE(a && a->a_embed && a->a_mask && a->sub_embed && a->sub_mask && a->vid_embed && a->vid_mask, STAGE_E_BADARG,
+  STG_REQUIRE(a && a->a_embed && a->a_mask && (a->sub_embed || a->sub_prepared) && a->sub_mask && a->vid_embed && a->vid_mask, STAGE_E_BADARG,
               "cqa: null input (single-stream models are not built yet)");
   STG_REQUIRE(a->wblob && a->cat_out_ln_g && a->cat_out_ln_b && a->workspace, STAGE_E_BADARG, "cqa: null weight blob / workspace");
   STG_REQUIRE(a->statement && a->statement_mask, STAGE_E_BADARG, "cqa: null output");
   STG_REQUIRE(a->n > 0 && a->t > 0 && a->lq > 0 && a->ls > 0 && a->r > 0, STAGE_E_BADARG, "cqa: non-positive size");
   STG_REQUIRE(a->lq <= 128 && a->ls <= CqaCfg::LS_MAX && a->r <= CqaCfg::R_MAX, STAGE_E_UNSUPPORTED,
               "cqa: lq=%d ls=%d r=%d exceed the tile (128, %d, %d)", a->lq, a->ls, a->r, CqaCfg::LS_MAX, CqaCfg::R_MAX);
-  STG_REQUIRE(aligned16(a->a_embed) && aligned16(a->sub_embed) && aligned16(a->vid_embed) && aligned16(a->statement) &&
+  STG_REQUIRE(aligned16(a->a_embed) && (!a->sub_embed || aligned16(a->sub_embed)) && aligned16(a->vid_embed) && aligned16(a->statement) &&
                   aligned16(a->wblob) && (reinterpret_cast<uintptr_t>(a->workspace) & 127u) == 0, STAGE_E_BADARG,
               "cqa: pointers must be 16-byte (workspace 128-byte) aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -264,7 +275,8 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
     d.n = a->n; d.t = a->t; d.lq = a->lq; d.ls = a->ls; d.r = a->r; d.ls_pad = ls_pad; d.r_pad = r_pad; d.n_pt = n_pt;
     d.a_embed = a->a_embed; d.a_mask = a->a_mask; d.sub_embed = a->sub_embed; d.sub_mask = a->sub_mask;
     d.vid_embed = a->vid_embed; d.vid_mask = a->vid_mask; d.a_blob = a_blob; d.ctx_blob = ctx_blob; d.a_blk = a_blk;
-    const long long warps = static_cast<long long>(a->n) * n_pt * 128 + static_cast<long long>(a->n) * a->t * (ls_pad + r_pad);
+    d.sub_prepared = a->sub_prepared;
+    const long long warps = static_cast<long long>(a->n) * n_pt * 128 + static_cast<long long>(a->n) * a->t * ((a->sub_prepared ? 0 : ls_pad) + r_pad);
     cqa_prep_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(d);
     int rc = check_launch("cqa_prep");
     if (rc) return rc;

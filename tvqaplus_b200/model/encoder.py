@@ -44,17 +44,20 @@ class EncoderBlock(nn.Module):
             self._pe_blk, self._pe_blk_tag = ops.blocked_pe(pe, L), tag
         return self._pe_blk
 
-    def forward(self, x, mask, pool: bool = False, blocked_in=None):
+    def forward(self, x, mask, pool: bool = False, blocked_in=None, cqa_workspace=None):
         """x (N, L, D), mask (N, L) -> (N, L, D); ``pool=True`` returns max_l mask_logits(out, mask) (N, D) instead
         (the fused tail of STAGE.classfier_head_multi_proposal).  ``blocked_in=(N, L)``: x is the flat blocked tile buffer
-        ``ops.cqa_fused_fwd(blocked=True)`` produced (internal fast path of STAGE.forward)."""
+        ``ops.cqa_fused_fwd(blocked=True)`` produced (internal fast path of STAGE.forward).  ``cqa_workspace``: write the
+        output as the sub-title operand images of that ``ops.CqaWorkspace`` and return None (internal fast path, too)."""
         _no_train_dropout(self, self.dropout)
         convs = [c.conv_args(ln) for c, ln in zip(self.conv, self.layer_norm)]
         fin = (self.final_layer_norm.weight, self.final_layer_norm.bias)
         pe = self.position_encoding.pe if blocked_in is None else self._blocked_pe(blocked_in[1])
         if self.num_heads == 0:
             return ops.encoder_block_fwd(x, mask, pe, convs, fin, self.kernel_size, out_mode=1 if pool else 0,
-                                         blocked_in=blocked_in)
+                                         blocked_in=blocked_in, cqa_workspace=cqa_workspace)
+        if cqa_workspace is not None:
+            raise RuntimeError("tvqaplus_b200: the CQA-workspace output needs an attention-free encoder block")
         # convs (no closing LN) -> LN + MHA + residual -> closing LN (+ pool)
         y = ops.encoder_block_fwd(x, mask, pe, convs, None, self.kernel_size, skip_final_ln=True, blocked_in=blocked_in)
         return ops.mha_fwd(y, mask, self.multi_head_attn.attn_args(self.attn_layer_norm), self.num_heads, residual=True,
@@ -69,7 +72,13 @@ class StackedEncoder(nn.Module):
             EncoderBlock(n_conv=n_conv, kernel_size=kernel_size, n_filters=hidden_size, dropout=dropout,
                          num_heads=num_heads) for _ in range(n_blocks)])
 
-    def forward(self, x, mask, pool: bool = False, blocked_in=None):
+    def forward(self, x, mask, pool: bool = False, blocked_in=None, cqa_workspace=None):
         for i, blk in enumerate(self.stacked_encoderBlocks):
-            x = blk(x, mask, pool=pool and i == self.n_blocks - 1, blocked_in=blocked_in if i == 0 else None)
+            last = i == self.n_blocks - 1
+            x = blk(x, mask, pool=pool and last, blocked_in=blocked_in if i == 0 else None,
+                    cqa_workspace=cqa_workspace if last else None)
         return x
+
+    def can_write_cqa_workspace(self, L: int) -> bool:
+        """The last block is attention-free and L sits in the range ``ops.CqaWorkspace`` takes directly."""
+        return self.n_blocks > 0 and self.stacked_encoderBlocks[-1].num_heads == 0 and ops.CqaWorkspace.takes_sub(L)

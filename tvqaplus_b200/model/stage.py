@@ -217,8 +217,15 @@ class STAGE(nn.Module):
 
         T, Ls = batch.sub_bert.shape[1:3]
         sub_mask = batch.sub_mask.float()
-        sub_embed = self.base_encoder(batch.sub_bert.view(bsz * T, Ls, -1), sub_mask.view(bsz * T, Ls),
-                                      self._text_fc, None, self.input_encoder).view(bsz, T, Ls, hsz)
+        # the sub-title encoder writes its output straight into the operand images of the fused CQA kernel's workspace
+        # (no fp32 round trip, no conversion pass) whenever the sequence length allows it
+        cqa_ws = ops.CqaWorkspace(bsz, T, Lq, a_embed.device)
+        if self.input_encoder.can_write_cqa_workspace(Ls):
+            self.input_encoder(self._text_fc(batch.sub_bert.view(bsz * T, Ls, -1)), sub_mask.view(bsz * T, Ls), cqa_workspace=cqa_ws)
+            sub_embed = None
+        else:
+            sub_embed = self.base_encoder(batch.sub_bert.view(bsz * T, Ls, -1), sub_mask.view(bsz * T, Ls),
+                                          self._text_fc, None, self.input_encoder).view(bsz, T, Ls, hsz)
         R = batch.vid.shape[2]
         vid_mask = batch.vid_mask.float()
         vid_embed = self.base_encoder(batch.vid.view(bsz * T, R, -1), vid_mask.view(bsz * T, R),
@@ -227,7 +234,8 @@ class STAGE(nn.Module):
         need_raw = self.inference_mode
         blocked = ops.blocked_fits(Lq)  # the statement goes to the cls encoder in the blocked tile layout (never seen outside)
         cq = ops.cqa_fused_fwd(a_embed, qas_mask.view(bsz, num_a, Lq), sub_embed, sub_mask, vid_embed, vid_mask,
-                               self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else (), blocked=blocked)
+                               self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else (), blocked=blocked,
+                               workspace=cqa_ws)
         other_outputs = {"vid_raw_s": cq.get("vid_raw_s")}
         out, target, t_scores, t_probs = self.classfier_head_multi_proposal(
             cq["statement"], cq["statement_mask"], batch.target, batch.ts_label, batch.ts_label_mask,

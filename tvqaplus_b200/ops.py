@@ -100,7 +100,7 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
                       final_ln, ksize: int, *, out_mode: int = 0, timeline: Optional[torch.Tensor] = None,
                       blocked_in: Optional[tuple] = None,
                       conv_only: bool = False, pre_ln_only: bool = False, relu: bool = True,
-                      skip_final_ln: bool = False) -> torch.Tensor:
+                      skip_final_ln: bool = False, cqa_workspace: Optional["CqaWorkspace"] = None) -> torch.Tensor:
     """One EncoderBlock (stage_encoder_block_fwd).  x (n_seq, L, 128); convs[i] = dict(ln_g, ln_b, dw_w, dw_b,
     pw_packed, pw_b); final_ln = (g, b).  out_mode 1 returns the masked max-pool (n_seq, 128).
 
@@ -125,7 +125,14 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
         flags |= _lib.ENC_NO_FINAL_LN
     if not (flags & _lib.ENC_NO_PE) and blocked_in is None and pe.shape[0] < L:
         raise RuntimeError("tvqaplus_b200: sequence length %d exceeds the position-encoding table (%d)" % (L, pe.shape[0]))
-    y = torch.empty((n_seq, L, D) if out_mode == 0 else (n_seq, D), dtype=torch.float32, device=x.device)
+    if cqa_workspace is not None:
+        # out_mode 2: the closing LayerNorm output is written as the sub-title operand image (+ inverse norms, masks) of the
+        # CQA context blobs inside ``cqa_workspace``; nothing else is returned
+        if n_seq != cqa_workspace.n * cqa_workspace.t or not cqa_workspace.takes_sub(L):
+            raise RuntimeError("tvqaplus_b200: encoder output (n_seq=%d, L=%d) does not match the CQA workspace" % (n_seq, L))
+        out_mode, y = 2, None
+    else:
+        y = torch.empty((n_seq, L, D) if out_mode == 0 else (n_seq, D), dtype=torch.float32, device=x.device)
     names = ("ln_g", "ln_b", "dw_w", "dw_b", "pw_b")
     keep = [[_f32(c[k]) if c.get(k) is not None else None for k in names] for c in convs]  # keep contiguous copies alive
     cols = {k: [ptr(row[i]) for row in keep] for i, k in enumerate(names)}
@@ -136,11 +143,35 @@ def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optiona
                          flags=flags, x=ptr(x), mask=ptr(mask_c), pe=ptr(pe_c),
                          ln_g=_arr(cols["ln_g"]), ln_b=_arr(cols["ln_b"]), dw_w=_arr(cols["dw_w"]),
                          dw_b=_arr(cols["dw_b"]), pw_packed=_arr([ptr(c["pw_packed"]) for c in convs]),
-                         pw_b=_arr(cols["pw_b"]), final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]), y=ptr(y),
-                         timeline=ptr(timeline))
+                         pw_b=_arr(cols["pw_b"]), final_ln_g=ptr(fin[0]), final_ln_b=ptr(fin[1]),
+                         y=ptr(y) if cqa_workspace is None else cqa_workspace.ctx_blobs, timeline=ptr(timeline))
     check(lib().stage_encoder_block_fwd(C.byref(a), current_stream()), "stage_encoder_block_fwd")
     _count()
+    if cqa_workspace is not None:
+        cqa_workspace.sub_prepared = True
+        cqa_workspace.sub_len = L
+        return None
     return y
+
+
+class CqaWorkspace:
+    """Caller-owned scratch of one ``cqa_fused_fwd`` call (stage_cqa_workspace_bytes).  Allocated BEFORE the sub-title
+    input encoder runs, that encoder can write its output straight into the context blobs (``encoder_block_fwd(...,
+    cqa_workspace=ws)``) and the fused kernel's preparation pass then skips the sub-title stream."""
+
+    def __init__(self, n: int, t: int, lq: int, device):
+        self.n, self.t, self.lq = int(n), int(t), int(lq)
+        nbytes = lib().stage_cqa_workspace_bytes(self.n, self.t, self.lq)
+        self.buf = torch.empty(nbytes + 128, dtype=torch.uint8, device=device)
+        self.ptr = (self.buf.data_ptr() + 127) // 128 * 128
+        self.ctx_blobs = lib().stage_cqa_ctx_blobs(self.ptr, self.n, self.t, self.lq)
+        self.sub_prepared = False
+        self.sub_len = 0
+
+    @staticmethod
+    def takes_sub(L: int) -> bool:
+        """Sequence lengths the encoder can write directly (one sequence per tile, within the CQA sub-title tile)."""
+        return 64 < L <= 112
 
 
 def cqa_prepare_weights(c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, cat_w, cat_b) -> torch.Tensor:
@@ -171,7 +202,8 @@ def blocked_pe(pe: torch.Tensor, L: int) -> torch.Tensor:
 
 
 def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
-                  want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None, blocked: bool = False) -> dict:
+                  want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None, blocked: bool = False,
+                  workspace: Optional[CqaWorkspace] = None) -> dict:
     """Fused StructuredAttention x2 + c2q_down_projection x2 + concat_fc (stage_cqa_fused_fwd).
 
     a_embed (N,5,Lq,128), a_mask (N,5,Lq), sub_embed (N,T,Ls,128), sub_mask (N,T,Ls), vid_embed (N,T,R,128),
@@ -180,9 +212,11 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
     Returns dict with ``statement`` (N,5,T,Lq,128), ``statement_mask`` (N,5,T,Lq).
     """
     a_embed, a_mask = _f32(a_embed), _f32(a_mask)
-    sub_embed, sub_mask, vid_embed, vid_mask = _f32(sub_embed), _f32(sub_mask), _f32(vid_embed), _f32(vid_mask)
+    sub_mask, vid_embed, vid_mask = _f32(sub_mask), _f32(vid_embed), _f32(vid_mask)
     N, A, Lq, D = a_embed.shape
-    T, Ls = sub_embed.shape[1:3]
+    prepared = workspace is not None and workspace.sub_prepared  # ``sub_embed`` may be None: its images are in the workspace
+    sub_embed = None if prepared else _f32(sub_embed)
+    T, Ls = sub_mask.shape[1:3]
     R = vid_embed.shape[2]
     if A != 5 or D != HSZ:
         raise RuntimeError("tvqaplus_b200: a_embed must be (N,5,Lq,128)")
@@ -197,16 +231,17 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
               "mixed_vid": (N, 5, T, Lq, D), "mixed_sub": (N, 5, T, Lq, D)}
     for k in want:
         out[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
-    ws_bytes = lib().stage_cqa_workspace_bytes(N, T, Lq)
-    ws = torch.empty(ws_bytes + 128, dtype=torch.uint8, device=dev)
-    ws_ptr = (ws.data_ptr() + 127) // 128 * 128
+    ws = workspace if workspace is not None else CqaWorkspace(N, T, Lq, dev)
+    if (ws.n, ws.t, ws.lq) != (N, T, Lq) or (prepared and ws.sub_len != Ls):
+        raise RuntimeError("tvqaplus_b200: CQA workspace was sized for another problem")
+    ws_ptr = ws.ptr
     a = _lib.CqaArgs(n=N, t=T, lq=Lq, ls=Ls, r=R, scale=float(scale),
                      a_embed=ptr(a_embed), a_mask=ptr(a_mask), sub_embed=ptr(sub_embed), sub_mask=ptr(sub_mask),
                      vid_embed=ptr(vid_embed), vid_mask=ptr(vid_mask), wblob=ptr(w["wblob"]),
                      cat_out_ln_g=ptr(_f32(w["cat_out_ln_g"])), cat_out_ln_b=ptr(_f32(w["cat_out_ln_b"])),
                      workspace=ws_ptr, statement_blocked=int(blocked), statement=ptr(out["statement"]),
                      statement_mask=ptr(out["statement_mask"]),
-                     timeline=ptr(timeline), **{k: ptr(out.get(k)) for k in shapes})
+                     timeline=ptr(timeline), sub_prepared=int(prepared), **{k: ptr(out.get(k)) for k in shapes})
     check(lib().stage_cqa_fused_fwd(C.byref(a), current_stream()), "stage_cqa_fused_fwd")
     _count(3)
     return out
