@@ -198,7 +198,11 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
 template <bool TIMELINE>
 __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t op_ready, mma_done, ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
+  // mma_done[k]: the k-th completion event of a tile (D1 S, D2 U, D3 c2q, D4 concat) has its OWN barrier.  With one shared
+  // barrier a compute thread that wakes up late from a suspended wait can find the barrier two phases further on (D4 of
+  // tile i and D1 of tile i+1 both complete), read its parity as 'not yet' and wait for an event that needs the thread
+  // itself: a deadlock, seen as sporadic wait time-outs once the waits got a long suspend hint.
+  __shared__ uint64_t op_ready, mma_done[4], ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
       w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
   __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
 
   if (tid == 0) {
     mbar_init(&op_ready, 512);
-    mbar_init(&mma_done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&mma_done[i], 1);
     mbar_init(&ctx_full, 1);
     mbar_init(&aq_full, 1);
     mbar_init(&ctx_free, 1);
@@ -308,8 +312,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      The 7 sub + 3 vid score chunks (16 columns each) are dealt to the quarters as
         //      q0: sub 0,1,2   q1: sub 3,4,5   q2: sub 6, vid 0   q3: vid 1, 2
         CQA_STAMP(0, 1);
-        mbar_wait(&mma_done, done_cnt & 1u, 31);  // D1: S ready
-        ++done_cnt;
+        mbar_wait(&mma_done[0], done_cnt & 1u, 31);  // D1: S ready
         tc_fence_after();
         CQA_STAMP(0, 2);
         {
@@ -442,8 +445,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         // ---- c2q A operands for both streams: the raw U segment, then the raw a*U segment; statistics on the fly.
         //      Everything is produced 16 columns (one stage contribution) at a time to stay inside the register budget
         //      (shared memory takes the whole L1 carve-out here, so a spill would cost an L2 round trip).
-        mbar_wait(&mma_done, done_cnt & 1u, 32);  // D2: U ready
-        ++done_cnt;
+        mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2: U ready
         tc_fence_after();
         CQA_STAMP(0, 5);
         tmem_st16(T0 + coff, za);
@@ -542,8 +544,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      re-reads them instead of holding 64 registers.
         tc_fence_before();
         CQA_STAMP(0, 7);
-        mbar_wait(&mma_done, done_cnt & 1u, 35);  // D3: both c2q accumulators complete
-        ++done_cnt;
+        mbar_wait(&mma_done[2], done_cnt & 1u, 35);  // D3: both c2q accumulators complete
         tc_fence_after();
         CQA_STAMP(0, 8);
         float2 c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
@@ -610,8 +611,8 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
 
         // ---- relu(rstd*(acc - mean*cs) + cb) -> LN128 -> statement
         tc_fence_before();
-        mbar_wait(&mma_done, done_cnt & 1u, 39);  // D4: concat accumulator complete
-        ++done_cnt;
+        mbar_wait(&mma_done[3], done_cnt & 1u, 39);  // D4: concat accumulator complete
+        ++done_cnt;  // one phase of every mma_done barrier per tile
         tc_fence_after();
         CQA_STAMP(0, 10);
         {
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             const uint64_t v_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
             umma_split3(T1, a_hi, a_lo, v_hi, v_lo, id_svid, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&mma_done);  // D1
+          umma_commit(&mma_done[0]);  // D1
         }
         CQA_STAMP(1, 2);
         // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             const uint64_t b_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 256, 128, CqaCfg::LBO_CV);
             umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&mma_done);  // D2
+          umma_commit(&mma_done[1]);  // D2
           umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
           if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         }
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             umma_commit(&a_empty[h]);
             umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
             umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
-            if (hs == 7) umma_commit(&mma_done);  // D3
+            if (hs == 7) umma_commit(&mma_done[2]);  // D3
           }
           if (hs < 8) CQA_STAMP(3, hs * 2 + 1);
           if (h == 1u) ++seg_cnt;
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           if (hs == 3) CQA_STAMP(1, 5);
         }
         if (elect_one()) {
-          umma_commit(&mma_done);  // D4
+          umma_commit(&mma_done[3]);  // D4
           umma_commit(&aq_free);   // the A stages (AQ region) may receive the next answer image
         }
         CQA_STAMP(1, 7);
