@@ -5,7 +5,7 @@ so ``main.py`` / ``inference.py`` can import this class instead of ``model.stage
 eight kernel launches (csrc/*.cuh):
 
     linear x2 (text)  ->  encoder        a_embed   (5N, Lq, 128)
-    linear x2 (text)  ->  encoder        sub_embed (N*T, Ls, 128)
+    linear x2 (text)  ->  encoder        sub_embed (N*T, Ls, 128)        [written straight into the CQA operand images]
     linear x2 (vid)   ->  encoder        vid_embed (N*T, R, 128)
     cqa_fused                            statement (N, 5, T, Lq, 128)   [S, P, U, both mixed tensors never leave the SM]
     encoder (cls, masked max-pool)       max_statement (5N*T, 128)
