@@ -2,7 +2,7 @@
 
 Same constructor (``STAGE(opt)``), ``forward(batch)`` contract, sub-module names and ``state_dict`` keys as the reference,
 so ``main.py`` / ``inference.py`` can import this class instead of ``model.stage.STAGE``.  The eval / inference forward is
-eight kernel launches (csrc/*.cuh):
+fourteen kernel launches (csrc/*.cuh):
 
     linear x2 (text)  ->  encoder        a_embed   (5N, Lq, 128)
     linear x2 (text)  ->  encoder        sub_embed (N*T, Ls, 128)        [written straight into the CQA operand images]
