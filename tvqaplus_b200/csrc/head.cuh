@@ -45,6 +45,19 @@ __device__ __forceinline__ float4 ln128(float4 v, float4 g, float4 b) {
   return make_float4(a * rs * g.x + b.x, c * rs * g.y + b.y, d * rs * g.z + b.z, e * rs * g.w + b.w);
 }
 
+// the same LayerNorm split into its statistics (two-pass: a constant -1e10 row must give exactly beta) and its affine part,
+// for rows that feed two LayerNorms with different gamma / beta
+__device__ __forceinline__ float4 ln128_center(float4 v, float& rs) {
+  const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+  const float a = v.x - mean, c = v.y - mean, d = v.z - mean, e = v.w - mean;
+  const float var = warp_sum((a * a + c * c) + (d * d + e * e)) * (1.f / 128.f);
+  rs = 1.f / sqrtf(var + 1e-5f);
+  return make_float4(a, c, d, e);
+}
+__device__ __forceinline__ float4 ln128_affine(float4 c, float rs, float4 g, float4 b) {
+  return make_float4(c.x * rs * g.x + b.x, c.y * rs * g.y + b.y, c.z * rs * g.z + b.z, c.w * rs * g.w + b.w);
+}
+
 __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
   extern __shared__ __align__(16) float hs[];
   float* Wt = hs;                      // [128 k][128 c] transposed projection weight
@@ -127,7 +140,9 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
         const float m = fm[t], o = (1.f - m) * STG_NEG;  // mask_logits, then max over frames (stage.py:456-466)
         gmax = make_float4(fmaxf(gmax.x, y.x * m + o), fmaxf(gmax.y, y.y * m + o), fmaxf(gmax.z, y.z * m + o), fmaxf(gmax.w, y.w * m + o));
       }
-      const float4 ls = ln128(y, sg, sb), le = ln128(y, eg, eb);
+      float rs_y;
+      const float4 yc = ln128_center(y, rs_y);  // one set of statistics serves the start and the end scorer
+      const float4 ls = ln128_affine(yc, rs_y, sg, sb), le = ln128_affine(yc, rs_y, eg, eb);
       const float s_st = warp_sum((ls.x * sw.x + ls.y * sw.y) + (ls.z * sw.z + ls.w * sw.w)) + st_bias;
       const float s_ed = warp_sum((le.x * ew.x + le.y * ew.y) + (le.z * ew.z + le.w * ew.w)) + ed_bias;
       if (lane == 0) {
