@@ -93,3 +93,32 @@ def test_host_helpers():
     assert compute_temporal_iou([0, 4], [2, 6]) == O.compute_temporal_iou([0, 4], [2, 6]) == 2 / 6
     assert compute_temporal_iou([1, 1], [1, 1]) == 0
     assert get_high_iou_sapns([(0, 4)], [[[0, 3, 0.9], [8, 9, 0.5]]]) == [[(0, 4), [0, 3]]]
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / field offsets of every argument struct as gcc sees include/stage_b200.h against the ctypes mirrors."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("StageLinearArgs", _lib.LinearArgs), ("StageEncoderArgs", _lib.EncoderArgs), ("StageMhaArgs", _lib.MhaArgs),
+             ("StageCqaArgs", _lib.CqaArgs), ("StageHeadArgs", _lib.HeadArgs), ("StageProbeArgs", _lib.ProbeArgs)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "stage_b200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for (cname, ct), line in zip(pairs, out):
+        toks = line.split()
+        assert toks[0] == cname
+        assert int(toks[1]) == ctypes.sizeof(ct), "%s: sizeof %s (C) vs %d (ctypes)" % (cname, toks[1], ctypes.sizeof(ct))
+        for (fname, _), off in zip(ct._fields_, toks[2:]):
+            assert int(off) == getattr(ct, fname).offset, "%s.%s: offset %s (C) vs %d (ctypes)" % (cname, fname, off, getattr(ct, fname).offset)
