@@ -32,6 +32,10 @@ import torch  # noqa: E402
 
 METRIC = "QA-examples/sec forward (synthetic T=300,R=20,L=100,H=128)"
 SHAPE = dict(T=300, R=20, Lq=100, Ls=100)
+# BASELINE.json configs: cfg2 = configs[1] (the headline line), cfg5 = configs[4] (long-context stress)
+CONFIGS = {"cfg2": dict(T=300, R=20, Lq=100, Ls=100, batch=32, name="configs[1]"),
+           "cfg5": dict(T=600, R=40, Lq=100, Ls=100, batch=8, name="configs[4] long-context"),
+           "cfg1": dict(T=40, R=25, Lq=40, Ls=50, batch=2, name="configs[0] debug shapes")}
 H = 128
 
 
@@ -41,12 +45,14 @@ def alg_flops_cqa(n_ex, T, R, Lq, Ls):
     return n_ex * (4 * H * n_st * (Ls + R) + 3 * (2 * 3 * H * H) * n_st)
 
 
-def alg_flops_total(n_ex, T, R, Lq, Ls, k_in=7, k_cls=5, n_conv=2):
+def alg_flops_total(n_ex, T, R, Lq, Ls, k_in=7, k_cls=5, n_conv=2, heads=0):
     n_qa, n_sub, n_vid, n_st = 5 * Lq, T * Ls, T * R, 5 * T * Lq
     f = 2 * 768 * 300 * (n_qa + n_sub) + 2 * 300 * 300 * n_vid + 2 * 300 * H * (n_qa + n_sub + n_vid)
     f += n_conv * (2 * k_in * H + 2 * H * H) * (n_qa + n_sub + n_vid)
     f += 4 * H * n_st * (Ls + R) + 3 * (2 * 3 * H * H) * n_st + n_conv * (2 * k_cls * H + 2 * H * H) * n_st
     f += (2 * H * H + 4 * H) * 5 * T
+    if heads:  # 8H^2 per token + 4H*L per token (QK^T and PV) for each encoder
+        f += 8 * H * H * (n_qa + n_sub + n_vid + n_st) + 4 * H * (n_qa * Lq + n_sub * Ls + n_vid * R + n_st * Lq)
     return n_ex * f
 
 
@@ -99,10 +105,10 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def make_host_batch(N, pin):
-    """Dense synthetic batch of configs[1] on the host (pinned for the e2e leg)."""
+def make_host_batch(N, pin, shape):
+    """Dense synthetic batch of the chosen BASELINE config on the host (pinned for the e2e leg)."""
     from tvqaplus_b200 import host
-    return host.synthetic_batch(N, SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"], seed=2018, pin=pin)
+    return host.synthetic_batch(N, shape["T"], shape["R"], shape["Lq"], shape["Ls"], seed=2018, pin=pin)
 
 
 TENSOR_KEYS = ("qas_bert", "sub_bert", "vid", "qas_mask", "sub_mask", "vid_mask", "ts_label_mask", "target")
@@ -121,22 +127,36 @@ def to_device(b, dev, non_blocking=False, into=None):
     return out
 
 
-def cpu_port(n_ex, steps, warmup, threads):
-    """Times the CPU oracle port (torch fp32 ops in the reference's order) — the reference's own CPU path restated."""
+def take_examples(b, idx):
+    """Examples ``idx`` of a host batch as a batch of their own (the CPU legs run on a bounded sample of the timed batch)."""
+    from tvqaplus_b200 import host
+    out = host.Batch(b)
+    n = len(b["qid"])
+    for k, v in b.items():
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n:
+            out[k] = v[idx].contiguous()
+        elif isinstance(v, list) and len(v) == n:
+            out[k] = [v[i] for i in idx]
+    out["ts_label"] = {k: v[idx] for k, v in b["ts_label"].items()}
+    return out
+
+
+def cpu_port(batch, opt, sd, steps, warmup, threads, device="cpu"):
+    """Times the oracle port (torch fp32 ops in the reference's order: the reference's own path restated) on ``device``.
+    Returns (times, last outputs)."""
     from oracle import stage_oracle as O
-    from tvqaplus_b200.model import STAGE
     torch.set_num_threads(threads)
-    opt = O.default_opt()
-    torch.manual_seed(2018)
-    sd = STAGE(opt).state_dict()
-    batch = O.make_synthetic_batch(n_ex, SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"], seed=2018, dense=True)
-    times = []
+    times, out = [], None
     for i in range(warmup + steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        O.stage_forward(sd, opt, batch)
+        out = O.stage_forward(sd, opt, batch, keep=True)
+        if device != "cpu":
+            torch.cuda.synchronize()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times
+    return times, out
 
 
 def main():
@@ -145,28 +165,45 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="examples per GPU per step (configs[1]: 32)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json config (cfg2 = configs[1], the headline)")
+    ap.add_argument("--heads", type=int, default=0, choices=[0, 4], help="self-attention heads in both encoders (config.py:110,116)")
+    ap.add_argument("--batch", type=int, default=0, help="examples per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    config = dict(workload="configs[1]: eval forward, add_local, sub+vfeat, batch=%d/GPU, T=300, R=20, Lq=Ls=100, H=128, dense masks"
-                  % args.batch, global_batch=args.batch * world, per_gpu_batch=args.batch, parallelism="dp%d (replicas, no collective)" % world,
-                  l2="inputs (3.3 GB/batch) exceed the 126 MB L2; no flush needed")
+    cfg = CONFIGS[args.config]
+    shape = {k: cfg[k] for k in ("T", "R", "Lq", "Ls")}
+    T, R, Lq, Ls = shape["T"], shape["R"], shape["Lq"], shape["Ls"]
+    N = args.batch or cfg["batch"]
+    in_gb = N * 4 * (5 * Lq * 768 + T * Ls * 768 + T * R * 300) / 1e9
+    config = dict(workload="%s: eval forward, add_local, sub+vfeat, heads=%d, batch=%d/GPU, T=%d, R=%d, Lq=%d, Ls=%d, H=128, dense masks"
+                  % (cfg["name"], args.heads, N, T, R, Lq, Ls), global_batch=N * world, per_gpu_batch=N,
+                  parallelism="dp%d (replicas, no collective)" % world,
+                  l2="inputs (%.2f GB/batch) %s the 126 MB L2%s" % (in_gb, "exceed" if in_gb > 0.2 else "FIT in", "; no flush needed" if in_gb > 0.2 else " (numerics-gate shape, not a timing shape)"))
+    metric = METRIC if args.config == "cfg2" else "QA-examples/sec forward (synthetic T=%d,R=%d,L=%d,H=128)" % (T, R, Lq)
+
+    from tvqaplus_b200 import host
+    from tvqaplus_b200.model import STAGE
+    opt = host.default_opt(input_encoder_n_heads=args.heads, cls_encoder_n_heads=args.heads)
 
     if args.impl == "reference":
         if rank != 0:
             return
         W = max(1, min(args.warmup, 2))
-        times = cpu_port(1, args.steps, W, cores)
+        torch.manual_seed(2018)
+        sd = STAGE(opt).state_dict()
+        one = take_examples(make_host_batch(2, False, shape), [0])
+        times, _ = cpu_port(one, opt, sd, args.steps, W, cores)
         v = 1.0 / statistics.mean(times)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "examples/s", "n_gpus": args.gpus,
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "examples/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": W, "ms_per_step": 1e3 * statistics.mean(times),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": dict(config, sample="1 example of the configs[1] shape per step"),
+                          "data": "synthetic", "config": dict(config, sample="1 example of the %s shape per step" % cfg["name"]),
                           "cpu_baseline": {"value": v, "unit": "examples/s", "cores": cores, "kind": "port",
                                            "sample": "CPU oracle port (torch fp32, reference op order), 1 example/step, %d steps" % args.steps},
                           "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,8 +211,7 @@ def main():
         return
 
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
-    from tvqaplus_b200 import _lib, host, ops
-    from tvqaplus_b200.model import STAGE
+    from tvqaplus_b200 import _lib, ops
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the STAGE kernels)")
     if world > 1:
@@ -184,11 +220,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.lib()
-    opt = host.default_opt()
     torch.manual_seed(2018)
     model = STAGE(opt).to(dev).eval()
-    N = args.batch
-    hbatch = make_host_batch(N, pin=not args.no_e2e)
+    hbatch = make_host_batch(N, pin=not args.no_e2e, shape=shape)
     dbatch = to_device(hbatch, dev)
     torch.cuda.synchronize()
 
@@ -221,6 +255,7 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     _lib.check_device_error()
     value = N * world * args.steps / (ms_total * 1e-3)
+    dev_answer, dev_probs, dev_spans = out[0].cpu(), out[4].cpu(), model._last_spans.cpu().long().view(N, 5, 2)
 
     # ---------------------------------------------------------------- end-to-end (host buffers, copies inside)
     e2e = None
@@ -230,7 +265,7 @@ def main():
         bufs = [{k: torch.empty_like(dbatch[k]) for k in TENSOR_KEYS} for _ in range(2)]
         for b in bufs:
             b["ts_label"] = dbatch["ts_label"]
-        res_host = [dict(a=torch.empty(N, 5).pin_memory(), p=torch.empty(N, 5, SHAPE["T"], 2).pin_memory()) for _ in range(2)]
+        res_host = [dict(a=torch.empty(N, 5).pin_memory(), p=torch.empty(N, 5, T, 2).pin_memory()) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         h2d = sum(hbatch[k].numel() * hbatch[k].element_size() for k in TENSOR_KEYS)
@@ -267,10 +302,11 @@ def main():
         barrier()
         e2e = {"value": N * world * args.steps / (ms_e2e * 1e-3), "unit": "examples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "h2d_gb_per_s_per_rank": h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
                "note": "pinned host inputs, double-buffered H2D on a copy stream, answer + span probs read back every step"}
+        del bufs
 
     # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0 timing, own stream)
-    T, R, Lq, Ls = SHAPE["T"], SHAPE["R"], SHAPE["Lq"], SHAPE["Ls"]
     with torch.no_grad():
         a_embed = model.base_encoder(dbatch.qas_bert.view(N * 5, Lq, 768), dbatch.qas_mask.view(N * 5, Lq), model._text_fc, None, model.input_encoder).view(N, 5, Lq, H)
         vid_embed = model.base_encoder(dbatch.vid.view(N * T, R, 300), dbatch.vid_mask.view(N * T, R), model._vid_fc, None, model.input_encoder).view(N, T, R, H)
@@ -295,33 +331,65 @@ def main():
             run_cqa()
         k1.record()
         torch.cuda.synchronize()
+        del ws, a_embed, vid_embed, sub_embed
     cqa_ms = k0.elapsed_time(k1) / reps
     pk = peaks()
     achieved = alg_flops_cqa(N, T, R, Lq, Ls) / (cqa_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "cqa_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    if os.path.exists(tp) and args.config == "cfg2" and N == 32:
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     roofline = {"bound": "tensor", "kernel": "cqa_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": traffic, "ms_per_launch": cqa_ms, "peak_source": pk["src"] + " bf16 sustained",
+                "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src, "ms_per_launch": cqa_ms,
+                "peak_source": pk["src"] + " bf16 sustained",
                 "note": "algorithmic FLOPs (a7+a8+a9, %.1f GFLOP/example); executed tensor FLOPs are 3x (split-fp16) on 128-row tiles"
                         % (alg_flops_cqa(1, T, R, Lq, Ls) / 1e9),
                 "step_share": cqa_ms / (ms_total / args.steps)}
 
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
-    cpu = None
+    # ---------------------------------------------------------------- CPU baseline + parity at the benchmarked configuration
+    # (rank 0, N=1 only): the oracle port runs on two examples OF THE TIMED BATCH (the first and the last), which times the
+    # reference's CPU path and checks the outputs the timed forward produced for exactly those rows.
+    cpu = parity = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times = cpu_port(2, 3, 1, cores)
-        cpu = {"value": 2.0 / statistics.mean(times), "unit": "examples/s", "cores": cores, "kind": "port",
-               "sample": "CPU oracle port (torch fp32, reference op order), batch of 2 configs[1] examples, 1 warm-up + 3 timed"}
+        idx = [0, N - 1] if N > 1 else [0]
+        sample = take_examples(hbatch, idx)
+        sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        times, want = cpu_port(sample, opt, sd_cpu, 3, 1, cores)
+        cpu = {"value": len(idx) / statistics.mean(times), "unit": "examples/s", "cores": cores, "kind": "port",
+               "sample": "CPU oracle port (torch fp32, reference op order) on examples %s of the timed batch, 1 warm-up + 3 timed" % idx}
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+        parity = {"examples": idx, "of_batch": N,
+                  "answer_max_rel": rel(dev_answer[idx], want["answer"]), "t_probs_max_rel": rel(dev_probs[idx], want["t_probs"]),
+                  "answer_argmax_equal": bool(torch.equal(dev_answer[idx].argmax(1), want["answer"].argmax(1))),
+                  "spans_equal": bool(torch.equal(dev_spans[idx].reshape(-1, 2), want["spans"])),
+                  "tolerance": 1e-3, "checker": "oracle/stage_oracle.py on the host, fp32"}
+    # ---------------------------------------------------------------- the honest competitor: the reference's eager path on this GPU
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            sd_dev = {k: v.detach() for k, v in model.state_dict().items()}
+            torch.cuda.empty_cache()
+            times, _ = cpu_port(dbatch, opt, sd_dev, 3, 1, cores, device="cuda")
+            eager = {"value": N / statistics.mean(times), "unit": "examples/s", "ms_per_step": 1e3 * statistics.mean(times),
+                     "batch": N, "kind": "port",
+                     "note": "the oracle port = the reference's torch ops in the reference's order, eager on this GPU, fp32 with "
+                             "allow_tf32=False, same batch, wall clock with synchronize (includes the reference's host-side numpy "
+                             "span search, model/model_utils.py:102-121); 1 warm-up + 3 timed"}
+        except Exception as e:  # e.g. out of memory at a large config: report, never fail the bench line
+            eager = {"unavailable": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 (split-fp16 x3 tensor-core GEMMs, fp32 accumulate)", "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu,
-                "alg_tflops_whole_path": alg_flops_total(N * world, T, R, Lq, Ls) * args.steps / (ms_total * 1e-3) / 1e12}
+                "cpu_baseline": cpu, "parity_at_bench_config": parity, "eager_cuda_baseline": eager,
+                "alg_tflops_whole_path": alg_flops_total(N * world, T, R, Lq, Ls, heads=args.heads) * args.steps / (ms_total * 1e-3) / 1e12}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -39,6 +39,11 @@ int stage_abi_version(void);
 const char* stage_last_error(void);
 /* Reads and clears the device-side error flag (synchronises the stream). 0 = clean. */
 int stage_check_device_error(void* stream);
+/* Asynchronous form for callers that must not synchronise: enqueues a copy of the error flag into `host_flag` (one
+ * uint32 of PINNED host memory owned by the caller) behind everything already on `stream`.  The caller reads it once an
+ * event recorded after this call has completed; non-zero = a bounded wait timed out in an earlier kernel and its outputs
+ * are garbage.  The flag is not cleared. */
+int stage_post_device_error(unsigned int* host_flag, void* stream);
 
 /* ---- weight packing ------------------------------------------------------------------------------------------
  * nn.Linear / 1x1 Conv1d weights W[N,K] (row-major fp32, as stored in the reference state_dict, e.g.
@@ -181,7 +186,7 @@ typedef struct {
   float* att_sub;              /* optional */
   float* mixed_vid;            /* optional [n,5,t,lq,128] c2q output */
   float* mixed_sub;            /* optional */
-  long long* timeline;         /* optional debug: [4][64][16] SM clock stamps of CTA 0 (see tools/cqa_timeline.py) */
+  long long* timeline;         /* optional debug: [8][64][16] SM clock stamps of CTA 0 (see tools/cqa_timeline.py) */
   int sub_prepared;            /* 1: the sub-title parts of the context blobs were written by stage_encoder_block_fwd(out_mode 2);
                                   sub_embed may then be NULL */
 } StageCqaArgs;
@@ -218,6 +223,14 @@ int stage_span_head_fwd(const StageHeadArgs* a, void* stream);
 /* ---- best span search on its own (find_max_triples topN=1, model/model_utils.py:92-121) -------------------------- */
 int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, int32_t* spans, float* conf,
                         void* stream);
+
+/* ---- span of the predicted answer at inference time (find_max_pair, inference.py:13-35) ---------------------------
+ * p1 / p2: start / end probabilities, element (row, i) at p[row*row_stride + i*elem_stride] (so the (N,T,2) slice of
+ * t_scores for the predicted answers is passed as p1 = base, p2 = base + 1, row_stride = 2T, elem_stride = 2).
+ * spans[rows,2] = (st, ed) with st <= ed, val[rows] = p1[st]*p2[ed] in double, exactly the reference's Python-float loop
+ * (first maximum wins; (0, 1) / 0.0 when every product is 0). */
+int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64_t row_stride, int elem_stride,
+                        int32_t* spans, double* val, void* stream);
 
 /* ---- mask_logits (model/model_utils.py:14-15): y = x*m + (1-m)*(-1e10), m broadcast over the last `inner` elems ---- */
 int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream);

@@ -458,3 +458,48 @@ def stage_forward(sd: Dict[str, torch.Tensor], opt, batch, training: bool = Fals
     if keep:
         out.update(a_embed=a_embed, statement=statement, statement_mask=statement_mask, **inter, **head_inter)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# inference post-processing — model/stage.py:748-806, inference.py:13-35
+# ----------------------------------------------------------------------------------------------
+def get_att_prediction(scores, object_vocab, words, vid_names, qids, img_indices, boxes, start_indices,
+                       score_thd: float = 0.2, num_a: int = 5):
+    """Per (question, answer, annotated frame, object word): regions with raw cosine >= ``score_thd``, ascending by
+    score — model/stage.py:775-805 (same loop order, same numpy calls, so ties sort the same way)."""
+    out = []
+    for b in range(len(scores)):
+        start_idx = start_indices[b]
+        per_q = {}
+        for a in range(num_a):
+            per_q[a] = []
+            for local_i in range(len(boxes[b])):
+                gi = local_i + start_idx
+                cur = scores[b, a, gi]
+                cur_words = words[b, a].tolist()
+                cur_boxes = boxes[b][local_i]
+                for wi, w in enumerate(cur_words):
+                    if w in object_vocab:
+                        row = cur[wi].detach().cpu().numpy()
+                        ids = np.nonzero(row >= score_thd)[0].tolist()
+                        sc = [float(row[i]) for i in ids]
+                        bx = [cur_boxes[i] for i in ids]
+                        order = np.argsort(sc)
+                        per_q[a].append({"pred": [sc[i] for i in order], "bbox": [bx[i] for i in order],
+                                         "word": int(words[b, a, wi]), "qid": int(qids[b]), "vid_name": vid_names[b],
+                                         "img_idx": img_indices[b][gi]})
+        out.append(per_q)
+    return out
+
+
+def find_max_pair(p1, p2):
+    """inference.py:13-35: running first-argmax of p1, best p1[k1]*p2[k2] with k1 <= k2 under strict '>' (Python floats,
+    i.e. double products of the fp32 probabilities); starts from span (0, 1), value 0."""
+    max_val, best, k1 = 0, (0, 1), 0
+    for i in range(len(p1)):
+        v1 = p1[k1]
+        if v1 < p1[i]:
+            k1, v1 = i, p1[i]
+        if v1 * p2[i] > max_val:
+            best, max_val = (k1, i), v1 * p2[i]
+    return best, float(max_val)

@@ -18,7 +18,7 @@ w = dict(wblob=ops.cqa_prepare_weights(torch.ones(384, device=dev), torch.zeros(
                                        torch.zeros(128, device=dev), torch.ones(384, device=dev), torch.zeros(384, device=dev),
                                        torch.randn(128, 384, device=dev) * 0.05, torch.zeros(128, device=dev)),
          cat_out_ln_g=torch.ones(128, device=dev), cat_out_ln_b=torch.zeros(128, device=dev))
-tl = torch.zeros(4, 64, 16, dtype=torch.int64, device=dev)
+tl = torch.zeros(8, 64, 16, dtype=torch.int64, device=dev)
 for _ in range(2):
     ops.cqa_fused_fwd(a, ones(N, 5, Lq), s, ones(N, T, Ls), v, ones(N, T, R), w, 10.0, timeline=tl)
 torch.cuda.synchronize()
@@ -43,3 +43,18 @@ for tile in (4, 5):
     print("tile", tile, "stages (cycles after D2): " + "  ".join(
         "s%d prod %d/%d mma %d/%d" % (k, int(ps[tile][2 * k]) - base, int(ps[tile][2 * k + 1]) - base, int(ms[tile][2 * k]) - base,
                                       int(ms[tile][2 * k + 1]) - base) for k in range(8)))
+
+# skew between compute warps: the same phase stamps taken by warp 15 (row 4) and warp 5 (row 7), relative to warp 0's
+c15, c5 = tl[4], tl[7]
+for tile in (4, 5):
+    print("tile", tile, "warp 15 minus warp 0 per phase:", "  ".join("%s %+d" % (names_c[i], int(c15[tile][i]) - int(c[tile][i])) for i in range(12)))
+    print("tile", tile, "warp 5 minus warp 0 per phase: ", "  ".join("%s %+d" % (names_c[i], int(c5[tile][i]) - int(c[tile][i])) for i in range(12)))
+    base = int(c[tile][5])
+    p15 = tl[6]
+    print("tile", tile, "warp 15 stages (cycles after warp 0's D2): " + "  ".join(
+        "s%d %d/%d" % (k, int(p15[tile][2 * k]) - base, int(p15[tile][2 * k + 1]) - base) for k in range(8)))
+# epilogue detail of thread 0 (row 5): accumulator read, statistics done, barrier passed, stores issued — cycles after D4
+ep = tl[5]
+d4 = c[3:60, 10]
+print("epilogue (mean cycles after D4): acc read %d  stats %d  barrier %d  stored %d  end %d" % tuple(
+    int((x - d4).float().mean()) for x in (ep[3:60, 0], ep[3:60, 1], ep[3:60, 2], ep[3:60, 3], c[3:60, 11])))

@@ -70,6 +70,7 @@ SYMBOLS = {
     "stage_abi_version": (C.c_int, []),
     "stage_last_error": (C.c_char_p, []),
     "stage_check_device_error": (C.c_int, [C.c_void_p]),
+    "stage_post_device_error": (C.c_int, [C.c_void_p, C.c_void_p]),
     "stage_packed_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "stage_pack_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_pack_weight_ln": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
@@ -85,6 +86,8 @@ SYMBOLS = {
     "stage_cqa_fused_fwd": (C.c_int, [C.POINTER(CqaArgs), C.c_void_p]),
     "stage_span_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
     "stage_find_max_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_find_max_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "stage_mask_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_umma_probe": (C.c_int, [C.POINTER(ProbeArgs), C.c_void_p]),
 }
@@ -134,3 +137,61 @@ def current_stream() -> int:
 
 def check_device_error() -> None:
     check(lib().stage_check_device_error(current_stream()), "stage_check_device_error")
+
+
+class on_device:
+    """Context manager: make the device of ``t`` current for the launches inside (the library launches on the current
+    device's stream; ``model.to('cuda:1')`` without ``torch.cuda.set_device`` must still work, as it does with PyTorch ops).
+    Tensors on different devices raise."""
+
+    def __init__(self, *tensors):
+        import torch
+        devs = {t.device for t in tensors if torch.is_tensor(t) and t.is_cuda}
+        if len(devs) > 1:
+            raise RuntimeError("tvqaplus_b200: tensors of one call live on different devices: %s" % sorted(map(str, devs)))
+        cpu = [t for t in tensors if torch.is_tensor(t) and not t.is_cuda]
+        if cpu:
+            raise RuntimeError("tvqaplus_b200: expected a CUDA tensor (no CPU path exists)")
+        self.guard = torch.cuda.device(next(iter(devs))) if devs else None
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
+
+
+class DeviceErrorMonitor:
+    """Non-blocking watch on the device error flag (a bounded mbarrier wait that timed out sets it and the kernel carries
+    on with garbage).  ``post()`` enqueues a copy of the flag into pinned host memory behind the work already on the
+    stream; ``poll()`` raises as soon as a posted copy has landed non-zero — without ever synchronising.  STAGE.forward
+    posts at the end of every call and polls at the start of the next one and after every host read it does anyway, so a
+    timed-out wait surfaces within one step instead of silently returning wrong answers."""
+
+    def __init__(self, device):
+        import torch
+        self.device = torch.device(device)
+        self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    def post(self) -> None:
+        import torch
+        with torch.cuda.device(self.device):
+            check(lib().stage_post_device_error(self.flag.data_ptr(), current_stream()), "stage_post_device_error")
+            self.event = torch.cuda.Event()
+            self.event.record()
+
+    def poll(self, wait: bool = False) -> None:
+        if self.event is None:
+            return
+        if wait:
+            self.event.synchronize()
+        if self.event.query():
+            v = int(self.flag.item()) & 0xFFFFFFFF
+            if v != 0:
+                raise RuntimeError("tvqaplus_b200: device error flag 0x%x — a bounded mbarrier wait timed out in an earlier "
+                                   "kernel; the outputs of that forward are invalid" % v)

@@ -40,15 +40,17 @@ inline int set_smem(K kernel, size_t bytes, const char* what) {
   return STAGE_OK;
 }
 
-inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+inline int num_sms() {  // of the CURRENT device (a process may drive several)
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 }  // namespace stg

@@ -190,7 +190,7 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
 #define CQA_STAMP(who, idx)                                                                         \
   do {                                                                                              \
     if constexpr (TIMELINE) {                                                                       \
-      if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64)                                 \
+      if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64 && (who) < 8)                    \
         p.timeline[((who) * 64 + tl_tile) * 16 + (idx)] = clock64();                                \
     }                                                                                               \
   } while (0)
@@ -254,7 +254,11 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
     const uint32_t coff = lane_off + qd * 32;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
-    [[maybe_unused]] int tl_tile = (tid == 0) ? 0 : 64;
+    // timeline build: thread 0 stamps rows 0 (phases), 2 (A stages), 5 (epilogue detail); thread 480 (warp 15) rows 4 / 6;
+    // thread 160 (warp 5) row 7 (phases only)
+    [[maybe_unused]] int tl_tile = (tid == 0 || tid == 160 || tid == 480) ? 0 : 64;
+    [[maybe_unused]] const int tl_ph = tid == 0 ? 0 : (tid == 480 ? 4 : 7), tl_st = tid == 0 ? 2 : (tid == 480 ? 6 : 8);
+    [[maybe_unused]] const int tl_ep = tid == 0 ? 5 : 8;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
     for (int i = tid; i < 128; i += 512) {  // per-column vectors of the folded GEMM epilogues
       pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   {                                                                                          \
     const HL8 hl0 = split8((v)), hl1 = split8((v) + 8);                                      \
     uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2) * CqaCfg::LBO_A + row * 16;      \
-    if (st_seq < 8) CQA_STAMP(2, st_seq * 2);                                                \
+    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2);                                                \
     mbar_wait(&a_empty[h], (a_use & 1u) ^ 1u, code);                                         \
     *reinterpret_cast<uint4*>(dst) = hl0.hi;                                                 \
     *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl0.lo;                              \
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     *reinterpret_cast<uint4*>(dst + CqaCfg::LBO_A + CqaCfg::AST_PART) = hl1.lo;              \
     fence_async_smem();                                                                      \
     mbar_arrive(&a_full[h]);                                                                 \
-    if (st_seq < 8) CQA_STAMP(2, st_seq * 2 + 1);                                            \
+    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2 + 1);                                            \
     ++st_seq;                                                                                \
   }
 #define CQA_SEG_DONE() ++a_use;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         const uint32_t arow = (static_cast<uint32_t>(n_i) * 32u + qd * 8u) * (5u * p.lq) + (live ? prow : 0);
         const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);  // output row
 #define orow (static_cast<size_t>(srow) * 128 + qd * 32) /* my 32 columns of the output row */
-        CQA_STAMP(0, 0);
+        CQA_STAMP(tl_ph, 0);
         [[maybe_unused]] int st_seq = 0;  // A stage counter of this tile (timeline build)
         const float* rd = reinterpret_cast<const float*>(p.a_blob + nj * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row);
@@ -311,10 +315,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      quarters meet in shared memory under the U MMAs, so this phase has no block barrier at all).
         //      The 7 sub + 3 vid score chunks (16 columns each) are dealt to the quarters as
         //      q0: sub 0,1,2   q1: sub 3,4,5   q2: sub 6, vid 0   q3: vid 1, 2
-        CQA_STAMP(0, 1);
+        CQA_STAMP(tl_ph, 1);
         mbar_wait(&mma_done[0], done_cnt & 1u, 31);  // D1: S ready
         tc_fence_after();
-        CQA_STAMP(0, 2);
+        CQA_STAMP(tl_ph, 2);
         {
           float* raw_s = (p.sub_raw_s && live) ? p.sub_raw_s + static_cast<size_t>(srow) * p.ls : nullptr;
           float* raw_v = (p.vid_raw_s && live) ? p.vid_raw_s + static_cast<size_t>(srow) * p.r : nullptr;
@@ -326,10 +330,12 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   const int n_real = vid ? p.r : p.ls;                                                 \
   const bool on = (qd < 2 || (k) < 2) && ch * 16 < (vid ? p.r_pad : p.ls_pad);
           // |cos| <= 1, so sc2 = scale*log2(e) bounds every live score: shifting by sc2 - 15 keeps P' inside fp16 range
-          // ((0, 2^15]) without knowing the row maximum.  Very large scales take the exact-maximum path instead.
+          // ((0, 2^15]) without knowing the row maximum as long as sc2 <= 15 (a row whose best cosine is c peaks at
+          // 2^(15 - sc2*(1-c)) >= 2^-15).  Larger scales (the reference's docstring suggests 100) take the exact-maximum
+          // path: the row peaks at exactly 2^15 and whatever underflows fp16 is < 2^-29 of the row sum.
           const float sc2 = p.scale * 1.4426950408889634f;
           float shift_s = sc2 - 15.f, shift_v = sc2 - 15.f;
-          if (sc2 > 50.f) {
+          if (sc2 > 15.f) {
             float mxs = -3.0e38f, mxv = -3.0e38f;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -352,8 +358,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             xq[0][qd][row] = mxs;
             xq[1][qd][row] = mxv;
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            shift_s = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row])) - 15.f;
-            shift_v = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row])) - 15.f;
+            // a row without a live column (padded answer token, frame without sub-title / regions) keeps the static shift:
+            // its arguments stay at -1e10*sc2, exp2 gives exactly 0 and U = 0 (with the -3e38 sentinel the shift would turn
+            // them into +3e38 -> inf -> NaN in the split)
+            const float ms_ = fmaxf(fmaxf(xq[0][0][row], xq[0][1][row]), fmaxf(xq[0][2][row], xq[0][3][row]));
+            const float mv_ = fmaxf(fmaxf(xq[1][0][row], xq[1][1][row]), fmaxf(xq[1][2][row], xq[1][3][row]));
+            shift_s = (ms_ > -1e30f ? ms_ : sc2) - 15.f;
+            shift_v = (mv_ > -1e30f ? mv_ : sc2) - 15.f;
             asm volatile("bar.sync 1, 512;" ::: "memory");
           }
           float sms = 0.f, smv = 0.f;
@@ -414,11 +425,11 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           xq[0][qd][row] = sms;  // (xq[0..1] were last read before this tile's predecessor passed its final barrier)
           xq[1][qd][row] = smv;
         }
-        CQA_STAMP(0, 3);
+        CQA_STAMP(tl_ph, 3);
         tc_fence_before();
         fence_async_smem();
         mbar_arrive(&op_ready);  // E2: P' images and the partial row sums are in place, S has been consumed
-        CQA_STAMP(0, 4);
+        CQA_STAMP(tl_ph, 4);
         // ---- my 32 answer values (columns [32*quarter, +32) of the row); the loads fly while U = P.ctx runs
         float a_reg[32];
         {
@@ -447,7 +458,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      (shared memory takes the whole L1 carve-out here, so a spill would cost an L2 round trip).
         mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2: U ready
         tc_fence_after();
-        CQA_STAMP(0, 5);
+        CQA_STAMP(tl_ph, 5);
         tmem_st16(T0 + coff, za);
         tmem_st16(T0 + coff + 16, za + 16);
         tmem_st16(T1 + coff, za);
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           st_s1[g] = s1.x + s1.y;
           st_s2[g] = s2.x + s2.y;
         }
-        CQA_STAMP(0, 6);
+        CQA_STAMP(tl_ph, 6);
         float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
         {
           const float asum = __ldg(rd + 256 + row), asq = __ldg(rd + 384 + row);  // sum(a), sum(a^2) of my row
@@ -543,10 +554,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         //      activated values are written back over their accumulators (my own TMEM cells), so the product segment
         //      re-reads them instead of holding 64 registers.
         tc_fence_before();
-        CQA_STAMP(0, 7);
+        CQA_STAMP(tl_ph, 7);
         mbar_wait(&mma_done[2], done_cnt & 1u, 35);  // D3: both c2q accumulators complete
         tc_fence_after();
-        CQA_STAMP(0, 8);
+        CQA_STAMP(tl_ph, 8);
         float2 c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -601,7 +612,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           CQA_SEG_PUT(h, m, 38)
         }
         CQA_SEG_DONE()
-        CQA_STAMP(0, 9);
+        CQA_STAMP(tl_ph, 9);
         xq[0][qd][row] = c1.x + c1.y;
         xq[1][qd][row] = c2.x + c2.y;
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -614,12 +625,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         mbar_wait(&mma_done[3], done_cnt & 1u, 39);  // D4: concat accumulator complete
         ++done_cnt;  // one phase of every mma_done barrier per tile
         tc_fence_after();
-        CQA_STAMP(0, 10);
+        CQA_STAMP(tl_ph, 10);
         {
           float o[32];
           tmem_ld16(T2 + coff, o);
           tmem_ld16(T2 + coff + 16, o + 16);
           tmem_wait_ld();
+          CQA_STAMP(tl_ep, 0);
           float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
           const float2 r_c2 = dup2(r_c), nm_c2 = dup2(nm_c);
           const float4* cs4 = reinterpret_cast<const float4*>(&pvec[2][qd * 32]);
@@ -639,7 +651,9 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           }
           xq[2][qd][row] = o1.x + o1.y;
           xq[3][qd][row] = o2.x + o2.y;
+          CQA_STAMP(tl_ep, 1);
           asm volatile("bar.sync 1, 512;" ::: "memory");
+          CQA_STAMP(tl_ep, 2);
           const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
           const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
           const float nmr = -mean * rstd;
@@ -665,13 +679,14 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
               dst[(j >> 2) * dstep] = make_float4(y0.x, y0.y, y1.x, y1.y);
             }
           }
+          CQA_STAMP(tl_ep, 3);
           // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
           if (live && qd == 0) p.statement_mask[srow] = (ma * any_v != 0.f) ? 1.f : 0.f;
         }
         tc_fence_before();
         // no barrier here: the next tile first writes xq[0..1] (softmax sums), which every thread finished reading before the
         // barrier above; xq[2..3] are rewritten only after the next tile's c2q production, which needs all 512 threads
-        CQA_STAMP(0, 11);
+        CQA_STAMP(tl_ph, 11);
         if constexpr (TIMELINE) ++tl_tile;
 #undef orow
       }

@@ -260,6 +260,29 @@ __global__ void find_max_span_kernel(const float* __restrict__ p_st, const float
   conf[r] = best;
 }
 
+// inference.py:13-35 find_max_pair: running FIRST argmax of p1 (strict '<'), best p1[k1]*p2[i] under strict '>' starting
+// from value 0 / span (0, 1).  The reference multiplies Python floats, i.e. the exact double products of the fp32
+// probabilities, so the comparison runs in double here as well (an fp32 x fp32 product is exact in fp64).
+__global__ void find_max_pair_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int rows, int T,
+                                     long long row_stride, int elem_stride, int* __restrict__ spans,
+                                     double* __restrict__ val) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* a = p1 + static_cast<size_t>(r) * row_stride;
+  const float* b = p2 + static_cast<size_t>(r) * row_stride;
+  double best = 0.0;
+  int k1 = 0, bs = 0, be = 1;
+  float v1 = T > 0 ? a[0] : 0.f;
+  for (int i = 0; i < T; ++i) {
+    const float ai = a[static_cast<size_t>(i) * elem_stride];
+    if (v1 < ai) { k1 = i; v1 = ai; }
+    const double v = static_cast<double>(v1) * static_cast<double>(b[static_cast<size_t>(i) * elem_stride]);
+    if (v > best) { best = v; bs = k1; be = i; }
+  }
+  spans[2 * r] = bs; spans[2 * r + 1] = be;
+  val[r] = best;
+}
+
 __global__ void mask_logits_kernel(const float* __restrict__ x, const float* __restrict__ m, long long outer, int inner,
                                    float* __restrict__ y) {
   const long long total = outer * inner;

@@ -62,6 +62,14 @@ int stage_check_device_error(void* stream) {
   return STAGE_OK;
 }
 
+int stage_post_device_error(unsigned int* host_flag, void* stream) {
+  STG_REQUIRE(host_flag, STAGE_E_BADARG, "post_device_error: null pointer");
+  cudaError_t e = cudaMemcpyFromSymbolAsync(host_flag, g_dev_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost,
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(STAGE_E_LAUNCH, "post error flag: %s", cudaGetErrorString(e));
+  return STAGE_OK;
+}
+
 int stage_umma_probe(const StageProbeArgs* a, void* stream) {
   STG_REQUIRE(a && a->a_img && a->b_img && a->d_out, STAGE_E_BADARG, "probe: null pointer");
   STG_REQUIRE(a->n % 16 == 0 && a->n >= 16 && a->n <= 256, STAGE_E_UNSUPPORTED, "probe: n=%u", a->n);
@@ -345,6 +353,14 @@ int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, i
   STG_REQUIRE(rows > 0 && t > 0, STAGE_E_BADARG, "find_max_span: rows=%d t=%d", rows, t);
   find_max_span_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p_st, p_ed, rows, t, spans, conf);
   return check_launch("find_max_span");
+}
+
+int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64_t row_stride, int elem_stride,
+                        int32_t* spans, double* val, void* stream) {
+  STG_REQUIRE(p1 && p2 && spans && val, STAGE_E_BADARG, "find_max_pair: null pointer");
+  STG_REQUIRE(rows > 0 && t > 0 && row_stride > 0 && elem_stride > 0, STAGE_E_BADARG, "find_max_pair: rows=%d t=%d", rows, t);
+  find_max_pair_kernel<<<(rows + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(p1, p2, rows, t, row_stride, elem_stride, spans, val);
+  return check_launch("find_max_pair");
 }
 
 int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream) {

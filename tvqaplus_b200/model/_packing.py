@@ -1,5 +1,9 @@
 """Cache of split-fp16 weight images, keyed on the parameter's storage and version counter so an optimizer step (or
-``load_state_dict``) invalidates it; kernels otherwise read parameter storage in place."""
+``load_state_dict``) invalidates it; kernels otherwise read parameter storage in place.
+
+The version counter does NOT move for in-place edits through ``.data`` (``p.data.copy_()``, EMA swaps, manual weight
+surgery): after such an edit call ``invalidate_weight_cache()`` (or ``STAGE.invalidate_weight_cache()``), otherwise the
+kernels keep using the images packed from the old values."""
 from __future__ import annotations
 
 import weakref
@@ -10,6 +14,19 @@ import torch
 from .. import ops
 
 _cache: Dict[int, Tuple[tuple, torch.Tensor, "weakref.ref"]] = {}
+_epoch = 0  # bumped by invalidate_weight_cache(); part of every tag (module-level tags such as STAGE._cqa_tag read it too)
+
+
+def epoch() -> int:
+    return _epoch
+
+
+def invalidate_weight_cache() -> None:
+    """Drop every packed weight image; the next forward re-packs from the current parameter values."""
+    global _epoch
+    _epoch += 1
+    _cache.clear()
+    _cache_ln.clear()
 
 
 def packed(param: torch.Tensor, kc: int) -> torch.Tensor:

@@ -7,6 +7,7 @@ the attention sub-layer runs between the conv rounds and the closing LayerNorm.
 import torch.nn as nn
 
 from .. import ops
+from . import _packing
 from .cnn import DepthwiseSeparableConv
 from .position_encoding import PositionEncoding
 from .self_attention import MultiHeadedAttention
@@ -39,7 +40,7 @@ class EncoderBlock(nn.Module):
 
     def _blocked_pe(self, L):
         pe = self.position_encoding.pe
-        tag = (L, pe.data_ptr(), pe._version)
+        tag = (L, pe.data_ptr(), pe._version, _packing.epoch())
         if getattr(self, "_pe_blk_tag", None) != tag:
             self._pe_blk, self._pe_blk_tag = ops.blocked_pe(pe, L), tag
         return self._pe_blk

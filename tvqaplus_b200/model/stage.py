@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from . import _packing
 from ._packing import packed, packed_ln
 from .cnn import DepthwiseSeparableConv
 from .context_query_attention import StructuredAttention
@@ -79,6 +80,7 @@ class STAGE(nn.Module):
         super().__init__()
         self.opt = opt
         self.inference_mode = False
+        self.error_checks = True  # watch the device error flag (no synchronisation; see _forward_eval)
         self.sub_flag = opt.sub_flag
         self.vfeat_flag = opt.vfeat_flag
         self.vfeat_size = opt.vfeat_size
@@ -193,7 +195,7 @@ class STAGE(nn.Module):
     def _cqa_weights(self):
         c2q, cat = self.c2q_down_projection, self.concat_fc
         params = (c2q[0].weight, c2q[0].bias, c2q[2].weight, c2q[2].bias, cat[0].weight, cat[0].bias, cat[2].weight, cat[2].bias)
-        tag = tuple((t.data_ptr(), t._version) for t in params)
+        tag = tuple((t.data_ptr(), t._version) for t in params) + (_packing.epoch(),)
         if getattr(self, "_cqa_tag", None) != tag:  # re-fold after an optimizer step / load_state_dict / .to()
             self._cqa_blob, self._cqa_tag = ops.cqa_prepare_weights(*params), tag
         return dict(wblob=self._cqa_blob, cat_out_ln_g=cat[4].weight, cat_out_ln_b=cat[4].bias)
@@ -206,7 +208,39 @@ class STAGE(nn.Module):
             w[key + "_w"], w[key + "_b"] = mod.conv[2].weight, mod.conv[2].bias
         return w
 
+    @staticmethod
+    def invalidate_weight_cache():
+        """Re-pack every weight image at the next forward.  Needed only after in-place edits through ``.data`` (they do not
+        move the parameter's version counter, which is what the caches are keyed on)."""
+        _packing.invalidate_weight_cache()
+
+    def _monitor(self, device):
+        mon = getattr(self, "_err_monitor", None)
+        if mon is None or mon.device != device:
+            from .._lib import DeviceErrorMonitor
+            mon = self._err_monitor = DeviceErrorMonitor(device)
+        return mon
+
+    def check_device_errors(self):
+        """Wait for the last forward and raise if one of its kernels reported a timed-out barrier wait."""
+        mon = getattr(self, "_err_monitor", None)
+        if mon is not None:
+            mon.poll(wait=True)
+
     def _forward_eval(self, batch):
+        # Device error flag (bounded mbarrier waits): polled without synchronising — a time-out in forward k raises at the
+        # latest at the start of forward k+1 (or right here when this call reads results back to the host anyway).
+        mon = self._monitor(batch.qas_bert.device) if self.error_checks else None
+        if mon is not None:
+            mon.poll()
+        out = self._forward_eval_impl(batch)
+        if mon is not None:
+            mon.post()
+            if self.inference_mode:
+                mon.poll(wait=True)  # get_att_prediction has synchronised already
+        return out
+
+    def _forward_eval_impl(self, batch):
         self.bsz = bsz = len(batch.qid)
         num_a, hsz = self.num_a, self.hsz
         qas_mask = batch.qas_mask.float()

@@ -22,6 +22,27 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
+def _tensors(objs):
+    for o in objs:
+        if torch.is_tensor(o):
+            yield o
+        elif isinstance(o, dict):
+            yield from _tensors(o.values())
+        elif isinstance(o, (list, tuple)):
+            yield from _tensors(o)
+
+
+def _guarded(fn):
+    """Run ``fn`` with the device of its tensor arguments current (see ``_lib.on_device``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        with _lib.on_device(*_tensors(args), *_tensors(kw.values())):
+            return fn(*args, **kw)
+    return wrapper
+
+
 def _f32(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError("tvqaplus_b200: expected float32, got %s" % t.dtype)
@@ -33,6 +54,7 @@ def kc_for(n: int) -> int:
     return 64 if n <= 128 else 32
 
 
+@_guarded
 def pack_weight(w: torch.Tensor, kc: Optional[int] = None) -> torch.Tensor:
     """Split W[N,K] (or a 1x1 conv weight [N,K,1]) into the fp16 hi/lo operand image (stage_pack_weight)."""
     w = _f32(w.detach())
@@ -50,6 +72,7 @@ def pack_weight(w: torch.Tensor, kc: Optional[int] = None) -> torch.Tensor:
     return out
 
 
+@_guarded
 def pack_weight_ln(w: torch.Tensor, bias: torch.Tensor, ln_g: torch.Tensor, ln_b: torch.Tensor, kc: Optional[int] = None):
     """Weight of a Linear that follows a LayerNorm: the image of W*gamma plus the two epilogue vectors cs / cb
     (stage_pack_weight_ln).  Returns (image, cs, cb)."""
@@ -68,6 +91,7 @@ def pack_weight_ln(w: torch.Tensor, bias: torch.Tensor, ln_g: torch.Tensor, ln_b
     return img, cs, cb
 
 
+@_guarded
 def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n: int, *, kc: Optional[int] = None,
                ln_in=None, ln_out=None, l2norm_in: bool = False, relu: bool = False,
                timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -96,6 +120,7 @@ def _arr(vals: Sequence[Optional[int]], n: int = _lib.MAX_CONV):
     return a
 
 
+@_guarded
 def encoder_block_fwd(x: torch.Tensor, mask: Optional[torch.Tensor], pe: Optional[torch.Tensor], convs: Sequence[dict],
                       final_ln, ksize: int, *, out_mode: int = 0, timeline: Optional[torch.Tensor] = None,
                       blocked_in: Optional[tuple] = None,
@@ -174,6 +199,7 @@ class CqaWorkspace:
         return 64 < L <= 112
 
 
+@_guarded
 def cqa_prepare_weights(c2q_ln_g, c2q_ln_b, c2q_w, c2q_b, cat_ln_g, cat_ln_b, cat_w, cat_b) -> torch.Tensor:
     """Fold LayerNorm(384) into c2q_down_projection / concat_fc and build their split-fp16 images
     (stage_cqa_prepare_weights).  Re-run whenever one of the eight parameters changes."""
@@ -201,6 +227,7 @@ def blocked_pe(pe: torch.Tensor, L: int) -> torch.Tensor:
     return _f32(pe[:L]).view(L, 32, 4).permute(1, 0, 2).contiguous()
 
 
+@_guarded
 def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: dict, scale: float, *,
                   want: Sequence[str] = (), timeline: Optional[torch.Tensor] = None, blocked: bool = False,
                   workspace: Optional[CqaWorkspace] = None) -> dict:
@@ -247,6 +274,7 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
     return out
 
 
+@_guarded
 def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local: bool, extra_span_length: int) -> dict:
     """Span + answer heads, eval branch (stage_span_head_fwd).
 
@@ -274,6 +302,7 @@ def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local:
     return o
 
 
+@_guarded
 def find_max_span(p_st: torch.Tensor, p_ed: torch.Tensor):
     """Best (st <= ed) pair maximising p_st[st]*p_ed[ed] per row (stage_find_max_span)."""
     p_st, p_ed = _f32(p_st), _f32(p_ed)
@@ -286,6 +315,23 @@ def find_max_span(p_st: torch.Tensor, p_ed: torch.Tensor):
     return spans, conf
 
 
+@_guarded
+def find_max_pairs(probs: torch.Tensor):
+    """Batched ``find_max_pair`` of inference.py:13-35 on the device: probs (rows, T, 2) = start / end probabilities
+    -> spans (rows, 2) int32 [st, ed], values (rows,) float64 (stage_find_max_pair)."""
+    probs = _f32(probs)
+    rows, T, two = probs.shape
+    if two != 2:
+        raise RuntimeError("tvqaplus_b200: probs must be (rows, T, 2)")
+    spans = torch.empty(rows, 2, dtype=torch.int32, device=probs.device)
+    val = torch.empty(rows, dtype=torch.float64, device=probs.device)
+    check(lib().stage_find_max_pair(ptr(probs), ptr(probs) + 4, rows, T, 2 * T, 2, ptr(spans), ptr(val), current_stream()),
+          "stage_find_max_pair")
+    _count()
+    return spans, val
+
+
+@_guarded
 def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """x*m + (1-m)*(-1e10) with m broadcast over the trailing axes of x it lacks (stage_mask_logits)."""
     x = _f32(x)
@@ -306,6 +352,7 @@ def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 _zero_cqa_blobs: dict = {}
 
 
+@_guarded
 def attention_only_fwd(c_embed, c_mask, q_embed, q_mask, scale: float) -> dict:
     """StructuredAttention alone for one stream: C (N,5,Lq,128), Q (N,T,Lr,128) -> att (N,5,T,Lq,128),
     raw_s / norm_s (N,5,T,Lq,Lr).  Runs the fused kernel with the query tensor in its subtitle slot (Lr <= 112), a
@@ -326,6 +373,7 @@ def attention_only_fwd(c_embed, c_mask, q_embed, q_mask, scale: float) -> dict:
     return dict(att=out["att_sub"], raw_s=out["sub_raw_s"], norm_s=out["sub_norm_s"])
 
 
+@_guarded
 def mha_fwd(x, mask, attn: dict, n_heads: int, *, residual: bool = False, final_ln=None, pool: bool = False):
     """Multi-head self-attention (stage_mha_fwd): y = LN_fin?((x +)? MHA(LN_in?(x))); ``attn`` = dict(ln_g, ln_b,
     w_packed[4], b[4]) as ``MultiHeadedAttention.attn_args`` builds it.  ``pool=True`` returns the masked max over L."""
