@@ -25,7 +25,7 @@ def _model(heads=0, seed=2018, **over):
 
 
 def _check(model, opt, batch, tag):
-    want = O.stage_forward({k: v.clone() for k, v in model.state_dict().items()}, opt, batch, keep=True)
+    want = O.stage_forward({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, opt, batch, keep=True)
     model, (answer, _, _, t_loss, t_probs) = run_product(model, batch)
     errs = dict(answer=H.max_rel(answer.cpu(), want["answer"]), t_probs=H.max_rel(t_probs.cpu(), want["t_probs"]),
                 t_loss=abs(t_loss.item() - want["temporal_loss"].item()) / abs(want["temporal_loss"].item()))

@@ -20,7 +20,7 @@ w = dict(wblob=ops.cqa_prepare_weights(torch.ones(384, device=dev), torch.zeros(
          cat_out_ln_g=torch.ones(128, device=dev), cat_out_ln_b=torch.zeros(128, device=dev))
 tl = torch.zeros(8, 64, 16, dtype=torch.int64, device=dev)
 for _ in range(2):
-    ops.cqa_fused_fwd(a, ones(N, 5, Lq), s, ones(N, T, Ls), v, ones(N, T, R), w, 10.0, timeline=tl)
+    ops.cqa_fused_fwd(a, ones(N, 5, Lq), s, ones(N, T, Ls), v, ones(N, T, R), w, 10.0, timeline=tl, blocked=True)  # the statement layout STAGE.forward uses
 torch.cuda.synchronize()
 tl = tl.cpu()
 c, m = tl[0], tl[1]
