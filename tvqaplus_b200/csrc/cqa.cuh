@@ -14,15 +14,33 @@
 // are still quoted in full).  The softmax is normalised late: P' = exp2(scale*log2e*S - shift) goes to the tensor cores
 // un-normalised and U = P'.ctx is divided by the row sum when it is read back, so the softmax phase needs no barrier.
 //
+// v4 (round 2).  What paced v3 (measured, profiles/r2a/cqa_tl.txt): with both operands in shared memory an M=128, N=128
+// MMA reads 128 B per clock — all the shared-memory bandwidth an SM has — so the producers' stores, the weight fills and
+// the MMAs starved one another (12 MMAs of a K=64 stage took 1.15 k cycles instead of 768), and the issuing warp then
+// waited another ~0.6 k per stage for a weight slot that could only be refilled after its previous MMAs had completed.
+// The tile was also one strictly serial chain (softmax -> U -> c2q -> concat -> epilogue).  Now:
+//   * A operands are converted IN PLACE in tensor memory: a thread reads its 16 fp32 accumulator cells (U, or the c2q
+//     accumulator after activation), splits them into fp16 (hi, lo) pairs and writes the 8 + 8 packed columns back over
+//     the very cells it read (tcgen05.st).  The next GEMM takes them as a TS-form A operand (A from tensor memory), so
+//     10 of the 14 K=64 stages of a tile never touch shared memory on the A side, need no ring, no a_empty wait and no
+//     async-proxy fence.  Only the a*U segments of c2q (no free TMEM columns while U and both accumulators are live)
+//     still go through the two shared-memory stages.
+//   * The concat product segment ms*mv is rebuilt from the packed (hi + lo) cells of T0 / T1 and written to T3.
+//   * Four epilogue warps (thread = row) own LN128 + the statement store; the compute warps hand over two scalars per
+//     row and go straight to the next tile, whose S MMAs are issued right behind the concat MMAs (the answer image has
+//     been able to land since the last shared-memory A stage was consumed, i.e. half a tile earlier).
+//   * c2q(sub) and c2q(vid) complete on separate barriers, so the ms segment is produced while c2q(vid) drains.
+//
 // Everything between the fp32 encoder outputs and the statement tile stays on chip:
 //   shared memory: split-fp16 images of the frame's ctx tiles (one cp.async.bulk per frame; read K-major for S and
-//                  MN-major for U), the answer image (one bulk copy per tile), P', two K=64 A stages and a 4-slot ring of
-//                  K=32 weight chunks for the three 384->128 GEMMs
-//   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator -> activated ms,  T1 = S_vid -> c2q(vid) -> activated mv,
-//                  T2 = U_sub -> concat accumulator,  T3 = U_vid
-// Warp roles (576 threads): warps 0-15 compute (thread = row x column quarter; everything is produced 16 columns at a
-// time so that the 96-register budget of an 18-warp CTA is never exceeded: shared memory takes the whole L1 carve-out, a
-// spill would be an L2 round trip), warp 16 = MMA issue (never waits for a completion), warp 17 = all bulk copies.
+//                  MN-major for U), the answer image (one bulk copy per tile), P', two K=64 A stages (a*U) and a 4-slot
+//                  ring of K=32 weight chunks for the three 384->128 GEMMs
+//   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator -> ms operand,  T1 = S_vid -> c2q(vid) -> mv operand,
+//                  T2 = U_sub -> U_sub operand -> concat accumulator,  T3 = U_vid -> U_vid operand -> ms*mv operand
+// Warp roles (768 threads, register budgets set per role with setmaxnreg): warps 0-15 compute (thread = row x column
+// quarter, 96 registers: everything is produced 16 columns at a time; shared memory takes the whole L1 carve-out, a
+// spill would be an L2 round trip), warp 16 = MMA issue (never waits for a completion), warp 17 = weight ring copies,
+// warp 18 = ctx / answer image copies, warp 19 idle, warps 20-23 = epilogue.
 // The 5 x Lq answer rows of an example are packed into 128-row tiles (4 tiles instead of 5 at Lq = 100); per-thread
 // global accesses (fp32 answers, Za, and optionally the statement) use a blocked [4-column group][row] layout so that a
 // warp's 32 rows touch whole lines.
@@ -65,9 +83,8 @@ struct CqaCfg {
   static constexpr uint32_t OFF_B = (OFF_AQ + AQ_BYTES + 127u) & ~127u;  // P_sub; later the weight ring
   static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                  // 65536 >= 2*PS_PART (57792)
   static constexpr uint32_t SMEM_BYTES = OFF_B + B_BYTES + 1024u;
-  static constexpr int THREADS = 576;        // 16 compute warps + MMA warp + copy warp
+  static constexpr int THREADS = 768;        // 16 compute warps | MMA, weight copies, ctx/answer copies, idle | 4 epilogue warps
   static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 weight chunks per tile: c2q(sub), c2q(vid), concat
-  static constexpr int HALF_SEGS = CHUNKS / 2;  // K=64 A stages per tile
   static_assert(2u * AST_BYTES <= AQ_BYTES, "the two A stages overlay the answer image");
   static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
   static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
@@ -90,7 +107,7 @@ struct CqaDev {
   int stmt_stride;            // 0: row-major statement; else S of the blocked tile layout
   float* vid_raw_s; float* sub_raw_s; float* vid_norm_s; float* sub_norm_s;
   float* att_vid; float* att_sub; float* mixed_vid; float* mixed_sub;
-  long long* timeline;  // optional [2][64][16] clock64 stamps of block 0 (compute thread 0 / MMA thread), first 64 tiles
+  long long* timeline;  // optional [8][64][16] clock64 stamps of block 0, first 64 tiles (tools/cqa_timeline.py)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -173,17 +190,32 @@ __global__ void __launch_bounds__(256) cqa_prep_kernel(CqaPrepDev p) {
 // ------------------------------------------------------------------------------------------------------------------
 // compute-side helpers
 // ------------------------------------------------------------------------------------------------------------------
-// store one K=32 A chunk (32 fp32 values of this thread's row) into an A stage, then publish it
-__device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int row, uint64_t* full) {
+__device__ __forceinline__ void reg_alloc_compute() { asm volatile("setmaxnreg.inc.sync.aligned.u32 96;"); }
+__device__ __forceinline__ void reg_release_issue() { asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); }
+__device__ __forceinline__ void reg_release_epilogue() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); }
+
+// 16 fp32 values of this thread's row -> fp16 (hi, lo) pairs written over the 16 TMEM cells they came from: columns
+// [c, c+8) hold the 16 hi halves (two per 32-bit column, k ascending), [c+8, c+16) the lo halves.  A TS-form MMA reads
+// them as one K=16 step of the A operand (hi at c, lo at c + 8).
+__device__ __forceinline__ void put_operand16(uint32_t taddr, const float* v) {
+  const HL8 h0 = split8(v), h1 = split8(v + 8);
+  tmem_st8(taddr, h0.hi, h1.hi);
+  tmem_st8(taddr + 8, h0.lo, h1.lo);
+}
+// the inverse: 16 packed cells -> 16 floats (hi + lo reproduces the value the split saw to 2^-22)
+__device__ __forceinline__ void get_operand16(uint32_t taddr, float* v) {
+  float raw[16];
+  tmem_ld16(taddr, raw);
+  tmem_wait_ld();
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(raw);
 #pragma unroll
-  for (int s8 = 0; s8 < 4; ++s8) {
-    HL8 hl = split8(v + s8 * 8);
-    uint8_t* dst = stage + s8 * CqaCfg::LBO_A + row * 16;
-    *reinterpret_cast<uint4*>(dst) = hl.hi;
-    *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl.lo;
+  for (int j = 0; j < 8; ++j) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&r[j]));
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&r[8 + j]));
+    const float2 s = add2(h, l);
+    v[2 * j] = s.x;
+    v[2 * j + 1] = s.y;
   }
-  fence_async_smem();
-  mbar_arrive(full);
 }
 
 // phase stamps exist only in the TIMELINE instantiation (tools/cqa_timeline.py); the production kernel carries none
@@ -196,16 +228,15 @@ __device__ __forceinline__ void put_chunk(const float* v, uint8_t* stage, int ro
   } while (0)
 
 template <bool TIMELINE>
-__global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
+__global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // mma_done[k]: the k-th completion event of a tile (D1 S, D2 U, D3 c2q, D4 concat) has its OWN barrier.  With one shared
-  // barrier a compute thread that wakes up late from a suspended wait can find the barrier two phases further on (D4 of
-  // tile i and D1 of tile i+1 both complete), read its parity as 'not yet' and wait for an event that needs the thread
-  // itself: a deadlock, seen as sporadic wait time-outs once the waits got a long suspend hint.
-  __shared__ uint64_t op_ready, mma_done[4], ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
-      w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
+  // Completion events of a tile, each with its OWN barrier (a thread that wakes up late from a suspended wait must never
+  // find its barrier two phases further on): D1 S, D2 U, D3a c2q(sub), D3b c2q(vid), D4 concat.
+  __shared__ uint64_t op_ready, mma_done[5], ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
+      useg_full[2], cat_full[3], ep_ready, t2_free, w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
   __shared__ uint32_t tmem_slot;
   __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
+  __shared__ float2 ep_stat[128];  // (rstd, -rstd*mean) of the concat LayerNorm(384) row, compute -> epilogue warps
   __shared__ __align__(16) float pvec[6][128];  // c2q cs, c2q cb, cat cs, cat cb, out gamma, out beta
 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space visible
@@ -216,13 +247,13 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   const float* mask_cs = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CS_MASK);
   const float* inv_cv = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CV_INV);
   const float* mask_cv = reinterpret_cast<const float*>(sCTX + CqaCfg::CTX_CV_MASK);
-  uint8_t* sAQ = smem + CqaCfg::OFF_AQ;  // a image -> P_vid -> A stages
+  uint8_t* sAQ = smem + CqaCfg::OFF_AQ;  // a image -> P_vid -> the two a*U stages
   uint8_t* sB = smem + CqaCfg::OFF_B;    // P_sub -> weight ring
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&op_ready, 512);
-    for (int i = 0; i < 4; ++i) mbar_init(&mma_done[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&mma_done[i], 1);
     mbar_init(&ctx_full, 1);
     mbar_init(&aq_full, 1);
     mbar_init(&ctx_free, 1);
@@ -231,12 +262,20 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 512);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&useg_full[i], 512);
     }
+    for (int i = 0; i < 3; ++i) mbar_init(&cat_full[i], 512);
+    mbar_init(&ep_ready, 512);
+    mbar_init(&t2_free, 128);
     for (int i = 0; i < CqaCfg::W_SLOTS; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
     mbar_fence_init();
+  }
+  for (int i = tid; i < 128; i += CqaCfg::THREADS) {  // per-column vectors of the folded GEMM epilogues
+    pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
+    pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
   }
   if (warp == 16) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
@@ -245,8 +284,11 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
   const uint32_t tbase = tmem_slot;
   const uint32_t T0 = tbase, T1 = tbase + 128, T2 = tbase + 256, T3 = tbase + 384;
   const int n_frames = p.n * p.t;
+  const int my_frames = static_cast<int>(blockIdx.x) < n_frames ? (n_frames - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  const int my_tiles = my_frames * p.n_pt;
 
   if (warp < 16) {
+    reg_alloc_compute();
     // =================================================================== compute warps
     // thread = (row, quarter): row = 32*(warp & 3) + lane (the TMEM lane quadrant a warp may touch is warp % 4),
     // quarter = warp / 4 owns columns [32*quarter, +32) of every 128-wide segment = exactly one K=32 chunk per segment
@@ -254,26 +296,20 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
     const uint32_t coff = lane_off + qd * 32;
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
-    // timeline build: thread 0 stamps rows 0 (phases), 2 (A stages), 5 (epilogue detail); thread 480 (warp 15) rows 4 / 6;
-    // thread 160 (warp 5) row 7 (phases only)
+    // timeline build: thread 0 stamps rows 0 (phases) and 2 (a*U stages); thread 480 (warp 15) rows 4 / 6; thread 160
+    // (warp 5) row 7 (phases only)
     [[maybe_unused]] int tl_tile = (tid == 0 || tid == 160 || tid == 480) ? 0 : 64;
     [[maybe_unused]] const int tl_ph = tid == 0 ? 0 : (tid == 480 ? 4 : 7), tl_st = tid == 0 ? 2 : (tid == 480 ? 6 : 8);
-    [[maybe_unused]] const int tl_ep = tid == 0 ? 5 : 8;
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
-    for (int i = tid; i < 128; i += 512) {  // per-column vectors of the folded GEMM epilogues
-      pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
-      pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
-    }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
 
-    // One 128-column segment of a GEMM's A operand = two K=64 stages; stage h holds columns [32*quarter + 16*h, +16) of
-    // every quarter (the weight columns are packed in the same order).  CQA_SEG_PUT publishes my 16 columns of stage h:
-    // wait until the MMAs of the previous segment have drained the stage, split, store, fence, arrive.
+    // The a*U segment of a c2q GEMM = two K=64 stages in shared memory; stage h holds columns [32*quarter + 16*h, +16) of
+    // every quarter (the weight columns of that segment are packed in the same order).  CQA_SEG_PUT publishes my 16 columns
+    // of stage h: wait until the MMAs of the previous segment have drained the stage, split, store, fence, arrive.
 #define CQA_SEG_PUT(h, v, code)                                                              \
   {                                                                                          \
     const HL8 hl0 = split8((v)), hl1 = split8((v) + 8);                                      \
     uint8_t* dst = sAQ + (h) * CqaCfg::AST_BYTES + (qd * 2) * CqaCfg::LBO_A + row * 16;      \
-    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2);                                                \
+    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2);                                            \
     mbar_wait(&a_empty[h], (a_use & 1u) ^ 1u, code);                                         \
     *reinterpret_cast<uint4*>(dst) = hl0.hi;                                                 \
     *reinterpret_cast<uint4*>(dst + CqaCfg::AST_PART) = hl0.lo;                              \
@@ -281,10 +317,9 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
     *reinterpret_cast<uint4*>(dst + CqaCfg::LBO_A + CqaCfg::AST_PART) = hl1.lo;              \
     fence_async_smem();                                                                      \
     mbar_arrive(&a_full[h]);                                                                 \
-    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2 + 1);                                            \
+    if (st_seq < 8) CQA_STAMP(tl_st, st_seq * 2 + 1);                                        \
     ++st_seq;                                                                                \
   }
-#define CQA_SEG_DONE() ++a_use;
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
       const int n_i = frame / p.t, t_i = frame - n_i * p.t;
@@ -299,7 +334,7 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
         const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);  // output row
 #define orow (static_cast<size_t>(srow) * 128 + qd * 32) /* my 32 columns of the output row */
         CQA_STAMP(tl_ph, 0);
-        [[maybe_unused]] int st_seq = 0;  // A stage counter of this tile (timeline build)
+        [[maybe_unused]] int st_seq = 0;  // a*U stage counter of this tile (timeline build)
         const float* rd = reinterpret_cast<const float*>(p.a_blob + nj * CqaCfg::ABLOB_BYTES + CqaCfg::ABLOB_ROWDATA);
         const float ia = __ldg(rd + row), ma = __ldg(rd + 128 + row);
         if (a_i == 0) {
@@ -440,32 +475,26 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             a_reg[j * 4] = v.x; a_reg[j * 4 + 1] = v.y; a_reg[j * 4 + 2] = v.z; a_reg[j * 4 + 3] = v.w;
           }
         }
-
         // ---- the frame-invariant a.Wa term of c2q (same for both streams): its loads fly under the U MMAs, then it is
         //      written into both c2q accumulators (my own cells of T0 / T1; S there is dead once U has completed) and the
         //      c2q MMAs accumulate on top of it
-        float za[32];
         {
+          float za[32];
           const float4* zsrc = reinterpret_cast<const float4*>(p.za) + arow;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 v = live ? __ldg(zsrc + j * (5 * p.lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
             za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
           }
+          mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2: U ready
+          tc_fence_after();
+          CQA_STAMP(tl_ph, 5);
+          tmem_st16(T0 + coff, za);
+          tmem_st16(T0 + coff + 16, za + 16);
+          tmem_st16(T1 + coff, za);
+          tmem_st16(T1 + coff + 16, za + 16);
         }
-        // ---- c2q A operands for both streams: the raw U segment, then the raw a*U segment; statistics on the fly.
-        //      Everything is produced 16 columns (one stage contribution) at a time to stay inside the register budget
-        //      (shared memory takes the whole L1 carve-out here, so a spill would cost an L2 round trip).
-        mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2: U ready
-        tc_fence_after();
-        CQA_STAMP(tl_ph, 5);
-        tmem_st16(T0 + coff, za);
-        tmem_st16(T0 + coff + 16, za + 16);
-        tmem_st16(T1 + coff, za);
-        tmem_st16(T1 + coff + 16, za + 16);
-        tmem_wait_st();
-        tc_fence_before();  // orders the stores before my a_full arrivals, i.e. before the first c2q MMA
-        // U completed => every thread has passed E2 => all partial row sums are in xq[2..3].  Masked entries of a live row
+        // U completed => every thread has passed E2 => all partial row sums are in xq[0..1].  Masked entries of a live row
         // are exactly 0; a fully masked row must become 0 after the "* S_mask" of the reference -> its 1/sum is replaced by 0
         const float is = (ma != 0.f && any_s != 0.f) ? 1.f / ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) : 0.f;
         const float iv = (ma != 0.f && any_v != 0.f) ? 1.f / ((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) : 0.f;
@@ -482,6 +511,10 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           }
         }
 #undef CQA_SLOT
+        // ---- c2q A operands of both streams, 16 columns at a time: the U segment goes back IN PLACE over the cells it came
+        //      from (TS-form operand, natural K order), the a*U segment through the two shared-memory stages; LayerNorm(384)
+        //      statistics on the fly.  (The stores of Za above are ordered before the first c2q MMA by the fence that
+        //      precedes my first arrival below.)
         float st_s1[2], st_s2[2];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -508,25 +541,21 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(att + orow + h * 16 + j) = make_float4(u[j], u[j + 1], u[j + 2], u[j + 3]);
             }
-            CQA_SEG_PUT(h, u, 33)
-          }
-          CQA_SEG_DONE()
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float u[16];
-            tmem_ld16(tU + h * 16, u);
-            tmem_wait_ld();
+            put_operand16(tU + h * 16, u);
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float2 t = mul2(make_float2(u[j], u[j + 1]), mul2(isum2, make_float2(a_reg[h * 16 + j], a_reg[h * 16 + j + 1])));
+              const float2 t = mul2(make_float2(u[j], u[j + 1]), make_float2(a_reg[h * 16 + j], a_reg[h * 16 + j + 1]));
               s1 = add2(s1, t);
               s2 = fma2(t, t, s2);
               u[j] = t.x;
               u[j + 1] = t.y;
             }
-            CQA_SEG_PUT(h, u, 34)
+            tmem_wait_st();
+            tc_fence_before();  // Za (first pass) and my operand cells are in tensor memory before I arrive anywhere
+            CQA_SEG_PUT(h, u, 33)
           }
-          CQA_SEG_DONE()
+          ++a_use;
+          mbar_arrive(&useg_full[g]);  // my 32 cells of the U operand are in place
           st_s1[g] = s1.x + s1.y;
           st_s2[g] = s2.x + s2.y;
         }
@@ -549,21 +578,20 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           nm_v = -r_v * mu_v;
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");  // everyone has read xq before it is reused below
-
-        // ---- concat_fc A operands: ms, mv, ms*mv segments with ms/mv = relu(rstd*(acc + za - mean*cs) + cb).  The
-        //      activated values are written back over their accumulators (my own TMEM cells), so the product segment
-        //      re-reads them instead of holding 64 registers.
-        tc_fence_before();
         CQA_STAMP(tl_ph, 7);
-        mbar_wait(&mma_done[2], done_cnt & 1u, 35);  // D3: both c2q accumulators complete
-        tc_fence_after();
-        CQA_STAMP(tl_ph, 8);
+
+        // ---- concat_fc A operands: ms, mv = relu(rstd*(acc - mean*cs) + cb) go back in place over their accumulators
+        //      (T0 / T1) as TS-form operands; the product segment is rebuilt from those packed cells and written to T3
+        //      (U_vid's operand there is dead once c2q(vid) has completed).
         float2 c1 = make_float2(0.f, 0.f), c2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint32_t tC = (g == 0 ? T0 : T1) + coff;
           const float2 rr = dup2(g == 0 ? r_s : r_v), nm = dup2(g == 0 ? nm_s : nm_v);
           float* mixed = g == 0 ? p.mixed_sub : p.mixed_vid;
+          mbar_wait(&mma_done[2 + g], done_cnt & 1u, 35);  // D3a / D3b: this stream's c2q accumulator is complete
+          tc_fence_after();
+          CQA_STAMP(tl_ph, 8 + 2 * g);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float m[16];
@@ -584,23 +612,23 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
                 m[j + 1] = t.y;
               }
             }
-            tmem_st16(tC + h * 16, m);
             if (live && mixed != nullptr) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(mixed + orow + h * 16 + j) = make_float4(m[j], m[j + 1], m[j + 2], m[j + 3]);
             }
-            CQA_SEG_PUT(h, m, 36)
+            put_operand16(tC + h * 16, m);
           }
-          CQA_SEG_DONE()
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&cat_full[g]);
+          CQA_STAMP(tl_ph, 9 + 2 * g);
         }
-        tmem_wait_st();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float m[16], w[16];
-          tmem_ld16(T0 + coff + h * 16, m);
-          tmem_ld16(T1 + coff + h * 16, w);
-          tmem_wait_ld();
+          get_operand16(T0 + coff + h * 16, m);
+          get_operand16(T1 + coff + h * 16, w);
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
             const float2 t = mul2(make_float2(m[j], m[j + 1]), make_float2(w[j], w[j + 1]));
@@ -609,108 +637,99 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             m[j] = t.x;
             m[j + 1] = t.y;
           }
-          CQA_SEG_PUT(h, m, 38)
+          put_operand16(T3 + coff + h * 16, m);
         }
-        CQA_SEG_DONE()
-        CQA_STAMP(tl_ph, 9);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&cat_full[2]);
+        CQA_STAMP(tl_ph, 12);
+        // ---- LayerNorm(384) statistics of the concat row; then, while the MMA warp issues the next tile's S behind the
+        //      concat MMAs, the first half of the epilogue: relu(rstd*(acc - mean*cs) + cb) goes back in place over the
+        //      accumulator together with the LayerNorm(128) statistics; the epilogue warps normalise and store.
         xq[0][qd][row] = c1.x + c1.y;
         xq[1][qd][row] = c2.x + c2.y;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         const float mu_c = ((xq[0][0][row] + xq[0][1][row]) + (xq[0][2][row] + xq[0][3][row])) * (1.f / 384.f);
         const float r_c = 1.f / sqrtf(fmaxf(((xq[1][0][row] + xq[1][1][row]) + (xq[1][2][row] + xq[1][3][row])) * (1.f / 384.f) - mu_c * mu_c, 0.f) + 1e-5f);
         const float nm_c = -r_c * mu_c;
-
-        // ---- relu(rstd*(acc - mean*cs) + cb) -> LN128 -> statement
-        tc_fence_before();
-        mbar_wait(&mma_done[3], done_cnt & 1u, 39);  // D4: concat accumulator complete
+        mbar_wait(&mma_done[4], done_cnt & 1u, 39);  // D4: concat accumulator complete
         ++done_cnt;  // one phase of every mma_done barrier per tile
         tc_fence_after();
-        CQA_STAMP(tl_ph, 10);
+        CQA_STAMP(tl_ph, 13);
         {
-          float o[32];
-          tmem_ld16(T2 + coff, o);
-          tmem_ld16(T2 + coff + 16, o + 16);
-          tmem_wait_ld();
-          CQA_STAMP(tl_ep, 0);
           float2 o1 = make_float2(0.f, 0.f), o2 = make_float2(0.f, 0.f);
           const float2 r_c2 = dup2(r_c), nm_c2 = dup2(nm_c);
-          const float4* cs4 = reinterpret_cast<const float4*>(&pvec[2][qd * 32]);
-          const float4* cb4 = reinterpret_cast<const float4*>(&pvec[3][qd * 32]);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cs = cs4[j4], cb = cb4[j4];
+          for (int h = 0; h < 2; ++h) {
+            float o[16];
+            tmem_ld16(T2 + coff + h * 16, o);
+            tmem_wait_ld();
+            const float4* cs4 = reinterpret_cast<const float4*>(&pvec[2][qd * 32 + h * 16]);
+            const float4* cb4 = reinterpret_cast<const float4*>(&pvec[3][qd * 32 + h * 16]);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = j4 * 4 + e * 2;
-              const float2 t = max2(fma2(r_c2, make_float2(o[j], o[j + 1]), fma2(nm_c2, e == 0 ? lo2(cs) : hi2(cs), e == 0 ? lo2(cb) : hi2(cb))), 0.f);
-              o1 = add2(o1, t);
-              o2 = fma2(t, t, o2);
-              o[j] = t.x;
-              o[j + 1] = t.y;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 cs = cs4[j4], cb = cb4[j4];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int j = j4 * 4 + e * 2;
+                const float2 t = max2(fma2(r_c2, make_float2(o[j], o[j + 1]), fma2(nm_c2, e == 0 ? lo2(cs) : hi2(cs), e == 0 ? lo2(cb) : hi2(cb))), 0.f);
+                o1 = add2(o1, t);
+                o2 = fma2(t, t, o2);
+                o[j] = t.x;
+                o[j + 1] = t.y;
+              }
             }
+            tmem_st16(T2 + coff + h * 16, o);
           }
           xq[2][qd][row] = o1.x + o1.y;
           xq[3][qd][row] = o2.x + o2.y;
-          CQA_STAMP(tl_ep, 1);
-          asm volatile("bar.sync 1, 512;" ::: "memory");
-          CQA_STAMP(tl_ep, 2);
-          const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
-          const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-          const float nmr = -mean * rstd;
-          if (live) {
-            const float4* g4p = reinterpret_cast<const float4*>(&pvec[4][qd * 32]);
-            const float4* b4p = reinterpret_cast<const float4*>(&pvec[5][qd * 32]);
-            // row-major: my 32 columns are 128 contiguous bytes of the row (a warp touches 32 lines per store);
-            // blocked: float4 c4 of row r sits at (tile*32 + c4)*S + r, so the 32 rows of a warp write 512-byte runs
-            float4* dst = reinterpret_cast<float4*>(p.statement) + (orow >> 2);
-            size_t dstep = 1;
-            if (p.stmt_stride != 0) {
-              const uint32_t trow = srow / p.lq;  // (example, answer, frame) tile index
-              dst = reinterpret_cast<float4*>(p.statement) + (static_cast<size_t>(trow) * 32 + qd * 8) * p.stmt_stride + (srow - trow * p.lq);
-              dstep = p.stmt_stride;
-            }
-#pragma unroll
-            const float2 rstd2 = dup2(rstd), nmr2 = dup2(nmr);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 g = g4p[j >> 2], b = b4p[j >> 2];
-              const float2 y0 = fma2(fma2(make_float2(o[j], o[j + 1]), rstd2, nmr2), lo2(g), lo2(b));
-              const float2 y1 = fma2(fma2(make_float2(o[j + 2], o[j + 3]), rstd2, nmr2), hi2(g), hi2(b));
-              dst[(j >> 2) * dstep] = make_float4(y0.x, y0.y, y1.x, y1.y);
-            }
+          tmem_wait_st();
+          tc_fence_before();
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // (also: everyone has read xq[0..1] before the next tile rewrites them)
+          if (qd == 0) {
+            const float mean = ((xq[2][0][row] + xq[2][1][row]) + (xq[2][2][row] + xq[2][3][row])) * (1.f / 128.f);
+            const float rstd = 1.f / sqrtf(fmaxf(((xq[3][0][row] + xq[3][1][row]) + (xq[3][2][row] + xq[3][3][row])) * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+            ep_stat[row] = make_float2(rstd, -mean * rstd);
+            // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
+            if (live) p.statement_mask[srow] = (ma * any_v != 0.f) ? 1.f : 0.f;
           }
-          CQA_STAMP(tl_ep, 3);
-          // (the ctx region may already be receiving the next frame here, hence any_v was taken at frame start)
-          if (live && qd == 0) p.statement_mask[srow] = (ma * any_v != 0.f) ? 1.f : 0.f;
+          mbar_arrive(&ep_ready);  // my activated cells are in tensor memory (and, for quarter 0, the row statistics in place)
         }
-        tc_fence_before();
-        // no barrier here: the next tile first writes xq[0..1] (softmax sums), which every thread finished reading before the
-        // barrier above; xq[2..3] are rewritten only after the next tile's c2q production, which needs all 512 threads
-        CQA_STAMP(tl_ph, 11);
+        CQA_STAMP(tl_ph, 14);
         if constexpr (TIMELINE) ++tl_tile;
 #undef orow
       }
     }
 #undef CQA_SEG_PUT
-#undef CQA_SEG_DONE
-  } else if (warp == 16) {
-    // =================================================================== MMA issue.  The whole warp runs the control flow
-    // (waits included) and ONE elected lane issues: only in converged code can the compiler keep descriptors in uniform
-    // registers; under a `lane == 0` branch every tcgen05 instruction sits in a lane-by-lane waterfall loop.  The issuer
-    // never waits for a completion.
-    uint32_t ready_cnt = 0, seg_cnt = 0, q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
-    [[maybe_unused]] int tl_tile = (lane == 0) ? 0 : 64;
-    const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
-    const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
-    const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
-    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
-      for (int a_i = 0; a_i < p.n_pt; ++a_i, ++tile_cnt) {
-        CQA_STAMP(1, 0);
-        if (a_i == 0) mbar_wait(&ctx_full, frame_cnt & 1u, 40);
-        mbar_wait(&aq_full, tile_cnt & 1u, 41);
+  } else if (warp < 20) {
+    reg_release_issue();
+    if (warp == 16) {
+      // ================================================================= MMA issue.  The whole warp runs the control flow
+      // (waits included) and ONE elected lane issues: only in converged code can the compiler keep descriptors in uniform
+      // registers; under a `lane == 0` branch every tcgen05 instruction sits in a lane-by-lane waterfall loop.  The issuer
+      // never waits for a completion.
+      uint32_t seg_cnt = 0, q_cnt = 0;
+      [[maybe_unused]] int tl_tile = (lane == 0) ? 0 : 64;
+      [[maybe_unused]] long long w_wait = 0, o_wait = 0;  // timeline build: cycles spent waiting for weights / for operands
+#define CQA_TIMED(acc, stmt)                        \
+  do {                                              \
+    if constexpr (TIMELINE) {                       \
+      const long long t_ = clock64();               \
+      stmt;                                         \
+      acc += clock64() - t_;                        \
+    } else {                                        \
+      stmt;                                         \
+    }                                               \
+  } while (0)
+      const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
+      const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
+      const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
+      // S = a . ctx^T for both streams of tile k (issued right behind the previous tile's concat MMAs)
+      auto issue_s = [&](int k) {
+        const int a_i = k % p.n_pt, f = k / p.n_pt;
+        if (a_i == 0) mbar_wait(&ctx_full, f & 1u, 40);
+        mbar_wait(&aq_full, k & 1u, 41);
         tc_fence_after();
-        CQA_STAMP(1, 1);
-        // ---- S = a . ctx^T for both streams
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -725,12 +744,36 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           }
           umma_commit(&mma_done[0]);  // D1
         }
-        CQA_STAMP(1, 2);
-        // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
-        mbar_wait(&op_ready, ready_cnt & 1u, 42);  // E2
-        ++ready_cnt;
+      };
+      // one K=32 weight chunk against a TS-form A operand (two K=16 steps: hi at `acol`, lo 8 columns further)
+      auto issue_ts_chunk = [&](uint32_t d_tmem, uint32_t a_region, int c, bool first) {
+        const uint32_t i = q_cnt;
+        ++q_cnt;
+        CQA_TIMED(w_wait, mbar_wait(&w_full[i % CqaCfg::W_SLOTS], (i / CqaCfg::W_SLOTS) & 1u, 46));
         tc_fence_after();
-        CQA_STAMP(1, 3);
+        if (elect_one()) {
+          const uint32_t wsl = ps + (i % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t acol = a_region + 32u * c + 16u * s;
+            const uint64_t b_hi = make_smem_desc(wsl + s * 2 * 2048, 2048, 128);
+            const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + s * 2 * 2048, 2048, 128);
+            umma_f16_ts(d_tmem, acol + 8, b_hi, id_g, (first && s == 0) ? 0u : 1u);
+            umma_f16_ts(d_tmem, acol, b_lo, id_g, 1u);
+            umma_f16_ts(d_tmem, acol, b_hi, id_g, 1u);
+          }
+          umma_commit(&w_empty[i % CqaCfg::W_SLOTS]);
+        }
+      };
+      if (my_tiles > 0) issue_s(0);
+      for (int k = 0; k < my_tiles; ++k) {
+        const int a_i = k % p.n_pt;
+        CQA_STAMP(1, 0);
+        // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
+        mbar_wait(&op_ready, k & 1u, 42);  // E2
+        if (k > 0) mbar_wait(&t2_free, (k - 1) & 1u, 43);  // the epilogue warps have read the previous concat accumulator
+        tc_fence_after();
+        CQA_STAMP(1, 1);
         if (elect_one()) {
           for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
             const uint64_t a_hi = make_smem_desc(ps + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
@@ -747,69 +790,79 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
             umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
           }
           umma_commit(&mma_done[1]);  // D2
-          umma_commit(&b_free);    // P_sub (region B) may now become the weight ring
+          umma_commit(&b_free);       // P_sub (region B) may now become the weight ring
           if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         }
-        CQA_STAMP(1, 4);
-        // ---- GEMMs: 14 K=64 A stages (4 c2q sub, 4 c2q vid, 6 concat), each against two K=32 weight slots
-        for (int hs = 0; hs < CqaCfg::HALF_SEGS; ++hs) {
-          const uint32_t h = hs & 1u;
-          mbar_wait(&a_full[h], seg_cnt & 1u, 45);
-          const uint32_t i0 = q_cnt + 2u * hs;
-          mbar_wait(&w_full[i0 % CqaCfg::W_SLOTS], (i0 / CqaCfg::W_SLOTS) & 1u, 46);
-          mbar_wait(&w_full[(i0 + 1u) % CqaCfg::W_SLOTS], ((i0 + 1u) / CqaCfg::W_SLOTS) & 1u, 46);
-          tc_fence_after();
-          if (hs < 8) CQA_STAMP(3, hs * 2);
-          const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
-          const uint32_t dcol = hs < 4 ? T0 : (hs < 8 ? T1 : T2);
-          const bool first = (hs == 8);  // the c2q accumulators start from the stored a.Wa term, concat from zero
-          if (elect_one()) {
+        CQA_STAMP(1, 2);
+        // ---- c2q, stream g: two shared-memory stages (a*U, K=64 each, two weight chunks each), then the U segment in
+        //      tensor memory (four weight chunks); accumulators T0 / T1 start from the stored a.Wa term
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t dcol = g == 0 ? T0 : T1;
+          for (uint32_t h = 0; h < 2; ++h) {
+            CQA_TIMED(o_wait, mbar_wait(&a_full[h], seg_cnt & 1u, 45));
+            const uint32_t i0 = q_cnt;
+            q_cnt += 2;
+            CQA_TIMED(w_wait, mbar_wait(&w_full[i0 % CqaCfg::W_SLOTS], (i0 / CqaCfg::W_SLOTS) & 1u, 46));
+            CQA_TIMED(w_wait, mbar_wait(&w_full[(i0 + 1u) % CqaCfg::W_SLOTS], ((i0 + 1u) / CqaCfg::W_SLOTS) & 1u, 46));
+            tc_fence_after();
+            if (g == 0) CQA_STAMP(3, h * 2);
+            const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t wsl = ps + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
-              const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-              const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-              const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
-              const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
-              umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, (first && ks == 0) ? 0u : 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t wsl = ps + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
+                const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+                const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
+                const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
+                const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
+                umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, 1u);
+              }
+              umma_commit(&a_empty[h]);
+              umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
+              umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
             }
-            umma_commit(&a_empty[h]);
-            umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
-            umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
-            if (hs == 7) umma_commit(&mma_done[2]);  // D3
+            if (g == 0) CQA_STAMP(3, h * 2 + 1);
           }
-          if (hs < 8) CQA_STAMP(3, hs * 2 + 1);
-          if (h == 1u) ++seg_cnt;
-          if (hs == 7) CQA_STAMP(1, 6);
-          if (hs == 3) CQA_STAMP(1, 5);
+          ++seg_cnt;
+          CQA_TIMED(o_wait, mbar_wait(&useg_full[g], k & 1u, 47));
+          tc_fence_after();
+          if (g == 0) CQA_STAMP(3, 4);
+          for (int c = 0; c < 4; ++c) issue_ts_chunk(dcol, g == 0 ? T2 : T3, c, false);
+          if (elect_one()) {
+            umma_commit(&mma_done[2 + g]);       // D3a / D3b
+            if (g == 1) umma_commit(&aq_free);   // both shared-memory stages are drained: the next answer image may land
+          }
+          CQA_STAMP(1, 3 + g);
         }
-        if (elect_one()) {
-          umma_commit(&mma_done[3]);  // D4
-          umma_commit(&aq_free);   // the A stages (AQ region) may receive the next answer image
+        // ---- concat: ms (T0), mv (T1), ms*mv (T3) against four weight chunks each, accumulator T2
+        for (int sgm = 0; sgm < 3; ++sgm) {
+          CQA_TIMED(o_wait, mbar_wait(&cat_full[sgm], k & 1u, 48));
+          tc_fence_after();
+          CQA_STAMP(3, 5 + sgm);
+          for (int c = 0; c < 4; ++c) issue_ts_chunk(T2, sgm == 0 ? T0 : (sgm == 1 ? T1 : T3), c, sgm == 0 && c == 0);
         }
-        CQA_STAMP(1, 7);
-        q_cnt += CqaCfg::CHUNKS;
-        CQA_STAMP(1, 8);
-        if constexpr (TIMELINE) ++tl_tile;
+        if (elect_one()) umma_commit(&mma_done[4]);  // D4
+        CQA_STAMP(1, 5);
+        if (k + 1 < my_tiles) issue_s(k + 1);
+        CQA_STAMP(1, 6);
+        if constexpr (TIMELINE) {
+          if (p.timeline != nullptr && blockIdx.x == 0 && tl_tile < 64) {
+            p.timeline[(1 * 64 + tl_tile) * 16 + 14] = w_wait;
+            p.timeline[(1 * 64 + tl_tile) * 16 + 15] = o_wait;
+          }
+          w_wait = 0;
+          o_wait = 0;
+          ++tl_tile;
+        }
       }
-    }
-  } else if (warp == 17 && lane == 0) {
-    // =================================================================== every bulk copy (one thread)
-    uint32_t q_cnt = 0, frame_cnt = 0, tile_cnt = 0;
-    auto w_src = [&](int q) -> const uint8_t* {
-      return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
-    };
-    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
-      const int n_i = frame / p.t;
-      if (frame_cnt > 0) mbar_wait(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
-      mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
-      bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
-      for (int a_i = 0; a_i < p.n_pt; ++a_i, ++tile_cnt) {
-        const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
-        if (tile_cnt > 0) mbar_wait(&aq_free, (tile_cnt - 1u) & 1u, 51);  // previous tile's concat MMAs have drained the A stages
-        mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
-        bulk_g2s(sAQ, p.a_blob + nj * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
-        mbar_wait(&b_free, tile_cnt & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
+    } else if (warp == 17 && lane == 0) {
+      // ================================================================= weight ring (one thread)
+      uint32_t q_cnt = 0;
+      auto w_src = [&](int q) -> const uint8_t* {
+        return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
+      };
+      for (int k = 0; k < my_tiles; ++k) {
+        mbar_wait(&b_free, k & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
         for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
           const uint32_t i = q_cnt + q, slot = i % CqaCfg::W_SLOTS, use = i / CqaCfg::W_SLOTS;
           mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 53);
@@ -817,6 +870,77 @@ __global__ void __launch_bounds__(576, 1) cqa_kernel(CqaDev p) {
           bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
         }
         q_cnt += CqaCfg::CHUNKS;
+      }
+    } else if (warp == 18 && lane == 0) {
+      // ================================================================= ctx blobs and answer images (one thread)
+      int k = 0;
+      uint32_t frame_cnt = 0;
+      for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
+        const int n_i = frame / p.t;
+        if (frame_cnt > 0) mbar_wait(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
+        mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
+        bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
+        for (int a_i = 0; a_i < p.n_pt; ++a_i, ++k) {
+          const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
+          if (k > 0) mbar_wait(&aq_free, (k - 1) & 1u, 51);  // the previous tile's a*U stages are drained
+          mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
+          bulk_g2s(sAQ, p.a_blob + nj * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
+        }
+      }
+    }
+  } else {
+    reg_release_epilogue();
+    // =================================================================== epilogue warps: thread = row, all 128 columns.
+    //   The compute warps have left relu(...) in place over the concat accumulator and the LayerNorm(128) statistics of
+    //   the row in ep_stat; here: normalise, scale, store, and release the accumulator to the next tile's U as soon as the
+    //   last cells have been read.
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = ((warp & 3) * 32u) << 16;
+    [[maybe_unused]] int tl_tile = (tid == 640) ? 0 : 64;
+    int k = 0;
+    for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+      const int n_i = frame / p.t, t_i = frame - n_i * p.t;
+      for (int a_i = 0; a_i < p.n_pt; ++a_i, ++k) {
+        const int prow = a_i * 128 + row;
+        const bool live = prow < 5 * p.lq;
+        const int ans = live ? prow / p.lq : 0;
+        const uint32_t srow = ((static_cast<uint32_t>(n_i) * 5u + ans) * p.t + t_i) * p.lq + (prow - ans * p.lq);
+        // row-major: the row is 512 contiguous bytes (a warp touches 32 lines per store);
+        // blocked: float4 c4 of row r sits at (tile*32 + c4)*S + r, so the 32 rows of a warp write 512-byte runs
+        float4* dst = reinterpret_cast<float4*>(p.statement) + static_cast<size_t>(srow) * 32;
+        size_t dstep = 1;
+        if (p.stmt_stride != 0) {
+          const uint32_t trow = srow / p.lq;  // (example, answer, frame) tile index
+          dst = reinterpret_cast<float4*>(p.statement) + static_cast<size_t>(trow) * 32 * p.stmt_stride + (srow - trow * p.lq);
+          dstep = p.stmt_stride;
+        }
+        mbar_wait(&ep_ready, k & 1u, 60);
+        tc_fence_after();
+        CQA_STAMP(5, 0);
+        const float2 st = ep_stat[row];
+        const float2 rstd2 = dup2(st.x), nmr2 = dup2(st.y);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float o[16];
+          tmem_ld16(T2 + lane_off + c * 16, o);
+          tmem_wait_ld();
+          if (c == 7) {
+            tc_fence_before();
+            mbar_arrive(&t2_free);  // the accumulator may be overwritten by the next tile's U
+            CQA_STAMP(5, 2);
+          }
+          const float4* g4p = reinterpret_cast<const float4*>(&pvec[4][c * 16]);
+          const float4* b4p = reinterpret_cast<const float4*>(&pvec[5][c * 16]);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 g = g4p[j4], b = b4p[j4];
+            const float2 y0 = fma2(fma2(make_float2(o[j4 * 4], o[j4 * 4 + 1]), rstd2, nmr2), lo2(g), lo2(b));
+            const float2 y1 = fma2(fma2(make_float2(o[j4 * 4 + 2], o[j4 * 4 + 3]), rstd2, nmr2), hi2(g), hi2(b));
+            if (live) dst[(c * 4 + j4) * dstep] = make_float4(y0.x, y0.y, y1.x, y1.y);
+          }
+        }
+        CQA_STAMP(5, 3);
+        if constexpr (TIMELINE) ++tl_tile;
       }
     }
   }
