@@ -53,3 +53,4 @@ c15, c5 = tl[4], tl[7]
 for tile in (4, 5):
     print("tile", tile, "warp 15 minus warp 0 per phase:", "  ".join("%s %+d" % (names_c[i], int(c15[tile][i]) - int(c[tile][i])) for i in range(15)))
     print("tile", tile, "warp 5 minus warp 0 per phase: ", "  ".join("%s %+d" % (names_c[i], int(c5[tile][i]) - int(c[tile][i])) for i in range(15)))
+

@@ -37,10 +37,11 @@
 //                  ring of K=32 weight chunks for the three 384->128 GEMMs
 //   TMEM (512 columns): T0 = S_sub -> c2q(sub) accumulator -> ms operand,  T1 = S_vid -> c2q(vid) -> mv operand,
 //                  T2 = U_sub -> U_sub operand -> concat accumulator,  T3 = U_vid -> U_vid operand -> ms*mv operand
-// Warp roles (768 threads, register budgets set per role with setmaxnreg): warps 0-15 compute (thread = row x column
-// quarter, 96 registers: everything is produced 16 columns at a time; shared memory takes the whole L1 carve-out, a
-// spill would be an L2 round trip), warp 16 = MMA issue (never waits for a completion), warp 17 = weight ring copies,
-// warp 18 = ctx / answer image copies, warp 19 idle, warps 20-23 = epilogue.
+// Warp roles (768 threads, register budgets set per role with setmaxnreg): warp 0 = MMA issue (never waits for a
+// completion; it carries the lowest warp id because the schedulers favour older warps and the issuer must not starve
+// behind busy compute warps), warp 1 = weight ring copies, warp 2 = ctx / answer image copies, warp 3 idle, warps 4-19
+// compute (thread = row x column quarter, 96 registers: everything is produced 16 columns at a time; shared memory takes
+// the whole L1 carve-out, a spill would be an L2 round trip), warps 20-23 = epilogue.
 // The 5 x Lq answer rows of an example are packed into 128-row tiles (4 tiles instead of 5 at Lq = 100); per-thread
 // global accesses (fp32 answers, Za, and optionally the statement) use a blocked [4-column group][row] layout so that a
 // warp's 32 rows touch whole lines.
@@ -83,11 +84,12 @@ struct CqaCfg {
   static constexpr uint32_t OFF_B = (OFF_AQ + AQ_BYTES + 127u) & ~127u;  // P_sub; later the weight ring
   static constexpr uint32_t B_BYTES = W_SLOTS * W_SLOT;                  // 65536 >= 2*PS_PART (57792)
   static constexpr uint32_t SMEM_BYTES = OFF_B + B_BYTES + 1024u;
-  static constexpr int THREADS = 768;        // 16 compute warps | MMA, weight copies, ctx/answer copies, idle | 4 epilogue warps
-  static constexpr int CHUNKS = 8 + 8 + 12;  // K=32 weight chunks per tile: c2q(sub), c2q(vid), concat
+  static constexpr int THREADS = 768;        // MMA, weight copies, ctx/answer copies, idle | 16 compute warps | 4 epilogue warps
+  static constexpr int CHUNKS = 8 + 12;  // K=32 weight chunks per tile: c2q (each used by both streams), concat
   static_assert(2u * AST_BYTES <= AQ_BYTES, "the two A stages overlay the answer image");
   static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
   static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
+  static_assert(CHUNKS % W_SLOTS == 0, "a tile's local chunk j must always sit in ring slot j % W_SLOTS");
 };
 
 struct CqaDev {
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
     pvec[0][i] = p.c2q_cs[i]; pvec[1][i] = p.c2q_cb[i]; pvec[2][i] = p.cat_cs[i];
     pvec[3][i] = p.cat_cb[i]; pvec[4][i] = p.out_g[i]; pvec[5][i] = p.out_b[i];
   }
-  if (warp == 16) tmem_alloc<512>(&tmem_slot);
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,19 +289,20 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
   const int my_frames = static_cast<int>(blockIdx.x) < n_frames ? (n_frames - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
   const int my_tiles = my_frames * p.n_pt;
 
-  if (warp < 16) {
+  if (warp >= 4 && warp < 20) {
     reg_alloc_compute();
     // =================================================================== compute warps
     // thread = (row, quarter): row = 32*(warp & 3) + lane (the TMEM lane quadrant a warp may touch is warp % 4),
     // quarter = warp / 4 owns columns [32*quarter, +32) of every 128-wide segment = exactly one K=32 chunk per segment
-    const int row = (warp & 3) * 32 + lane, qd = warp >> 2;
+    const int row = (warp & 3) * 32 + lane, qd = (warp >> 2) - 1;
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
     const uint32_t coff = lane_off + qd * 32;
+    const uint32_t ctid = tid - 128;  // index among the compute threads
     uint32_t done_cnt = 0, a_use = 0, frame_cnt = 0;
     // timeline build: thread 0 stamps rows 0 (phases) and 2 (a*U stages); thread 480 (warp 15) rows 4 / 6; thread 160
     // (warp 5) row 7 (phases only)
-    [[maybe_unused]] int tl_tile = (tid == 0 || tid == 160 || tid == 480) ? 0 : 64;
-    [[maybe_unused]] const int tl_ph = tid == 0 ? 0 : (tid == 480 ? 4 : 7), tl_st = tid == 0 ? 2 : (tid == 480 ? 6 : 8);
+    [[maybe_unused]] int tl_tile = (ctid == 0 || ctid == 160 || ctid == 480) ? 0 : 64;
+    [[maybe_unused]] const int tl_ph = ctid == 0 ? 0 : (ctid == 480 ? 4 : 7), tl_st = ctid == 0 ? 2 : (ctid == 480 ? 6 : 8);
     float any_v = 0.f, any_s = 0.f;  // does this frame have a valid region / subtitle token?  (S_mask.sum(-1) != 0, stage.py:386)
 
     // The a*U segment of a c2q GEMM = two K=64 stages in shared memory; stage h holds columns [32*quarter + 16*h, +16) of
@@ -515,24 +518,24 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         //      from (TS-form operand, natural K order), the a*U segment through the two shared-memory stages; LayerNorm(384)
         //      statistics on the fly.  (The stores of Za above are ordered before the first c2q MMA by the fence that
         //      precedes my first arrival below.)
-        float st_s1[2], st_s2[2];
+        // Both streams are produced side by side, half by half, because the c2q weights are the same for both: every weight
+        // chunk that lands in the ring is used twice (sub, then vid).  Stage g of the shared-memory ring belongs to stream g.
+        float2 s1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t tU = (g == 0 ? T2 : T3) + coff;
-          const float isum = g == 0 ? is : iv;
-          float* att = g == 0 ? p.att_sub : p.att_vid;
-          float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-          const float2 isum2 = dup2(isum);
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t tU = (g == 0 ? T2 : T3) + coff;
+            float* att = g == 0 ? p.att_sub : p.att_vid;
+            const float2 isum2 = dup2(g == 0 ? is : iv);
             float u[16];
             tmem_ld16(tU + h * 16, u);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const float2 t = mul2(make_float2(u[j], u[j + 1]), isum2);
-              s1 = add2(s1, t);
-              s2 = fma2(t, t, s2);
+              s1[g] = add2(s1[g], t);
+              s2[g] = fma2(t, t, s2[g]);
               u[j] = t.x;
               u[j + 1] = t.y;
             }
@@ -545,20 +548,21 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const float2 t = mul2(make_float2(u[j], u[j + 1]), make_float2(a_reg[h * 16 + j], a_reg[h * 16 + j + 1]));
-              s1 = add2(s1, t);
-              s2 = fma2(t, t, s2);
+              s1[g] = add2(s1[g], t);
+              s2[g] = fma2(t, t, s2[g]);
               u[j] = t.x;
               u[j + 1] = t.y;
             }
             tmem_wait_st();
             tc_fence_before();  // Za (first pass) and my operand cells are in tensor memory before I arrive anywhere
-            CQA_SEG_PUT(h, u, 33)
+            CQA_SEG_PUT(g, u, 33)
           }
           ++a_use;
-          mbar_arrive(&useg_full[g]);  // my 32 cells of the U operand are in place
-          st_s1[g] = s1.x + s1.y;
-          st_s2[g] = s2.x + s2.y;
+          mbar_arrive(&useg_full[h]);  // my cells of this half of both U operands are in place
         }
+        float st_s1[2], st_s2[2];
+        st_s1[0] = s1[0].x + s1[0].y; st_s2[0] = s2[0].x + s2[0].y;
+        st_s1[1] = s1[1].x + s1[1].y; st_s2[1] = s2[1].x + s2[1].y;
         CQA_STAMP(tl_ph, 6);
         float r_s, r_v, nm_s, nm_v;  // rstd and -rstd*mean of the two LayerNorm(384) rows
         {
@@ -589,8 +593,10 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
           const uint32_t tC = (g == 0 ? T0 : T1) + coff;
           const float2 rr = dup2(g == 0 ? r_s : r_v), nm = dup2(g == 0 ? nm_s : nm_v);
           float* mixed = g == 0 ? p.mixed_sub : p.mixed_vid;
-          mbar_wait(&mma_done[2 + g], done_cnt & 1u, 35);  // D3a / D3b: this stream's c2q accumulator is complete
-          tc_fence_after();
+          if (g == 0) {
+            mbar_wait(&mma_done[2], done_cnt & 1u, 35);  // D3: both c2q accumulators are complete
+            tc_fence_after();
+          }
           CQA_STAMP(tl_ph, 8 + 2 * g);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -701,14 +707,16 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
       }
     }
 #undef CQA_SEG_PUT
-  } else if (warp < 20) {
+  } else if (warp < 4) {
     reg_release_issue();
-    if (warp == 16) {
+    if (warp == 0) {
       // ================================================================= MMA issue.  The whole warp runs the control flow
       // (waits included) and ONE elected lane issues: only in converged code can the compiler keep descriptors in uniform
       // registers; under a `lane == 0` branch every tcgen05 instruction sits in a lane-by-lane waterfall loop.  The issuer
-      // never waits for a completion.
-      uint32_t seg_cnt = 0, q_cnt = 0;
+      // never waits for a completion.  The per-tile program is fully unrolled straight-line code: every shared-memory
+      // descriptor is a base descriptor (built once, below) plus a compile-time constant, every weight-ring slot index is a
+      // constant (20 chunks per tile, 4 slots) — measured: with descriptors rebuilt from run-time indices the issuing warp
+      // needed 300-400 cycles of dependent uniform-datapath instructions per K=16 step, twice the tensor time of the step.
       [[maybe_unused]] int tl_tile = (lane == 0) ? 0 : 64;
       [[maybe_unused]] long long w_wait = 0, o_wait = 0;  // timeline build: cycles spent waiting for weights / for operands
 #define CQA_TIMED(acc, stmt)                        \
@@ -723,7 +731,15 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
   } while (0)
       const uint32_t id_ssub = make_idesc_f16(p.ls_pad), id_svid = make_idesc_f16(p.r_pad);
       const uint32_t id_u = make_idesc_f16(128, 0, 1), id_g = make_idesc_f16(128);
-      const uint32_t aq = smem_u32(sAQ), cs = smem_u32(sCS), cv = smem_u32(sCV), ps = smem_u32(sB), pv = smem_u32(sAQ);
+      // base descriptors; desc(addr + off) = desc(addr) + (off >> 4) while the address stays inside shared memory
+      const uint64_t dA = make_smem_desc(smem_u32(sAQ), CqaCfg::LBO_A, 128);    // answer image / P_vid / a*U stages (K-major, 128 rows)
+      const uint64_t dP = make_smem_desc(smem_u32(sB), CqaCfg::LBO_A, 128);     // P_sub
+      const uint64_t dW = make_smem_desc(smem_u32(sB), 2048, 128);              // weight ring (K-major, 128 rows)
+      const uint64_t dCS = make_smem_desc(smem_u32(sCS), CqaCfg::LBO_CS, 128);  // sub-title tile, K-major (S)
+      const uint64_t dCV = make_smem_desc(smem_u32(sCV), CqaCfg::LBO_CV, 128);  // region tile, K-major (S)
+      const uint64_t dCSt = make_smem_desc(smem_u32(sCS), 128, CqaCfg::LBO_CS); // sub-title tile, MN-major (U)
+      const uint64_t dCVt = make_smem_desc(smem_u32(sCV), 128, CqaCfg::LBO_CV); // region tile, MN-major (U)
+#define DOFF(d, bytes) ((d) + static_cast<uint64_t>((bytes) >> 4))
       // S = a . ctx^T for both streams of tile k (issued right behind the previous tile's concat MMAs)
       auto issue_s = [&](int k) {
         const int a_i = k % p.n_pt, f = k / p.n_pt;
@@ -732,114 +748,127 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t a_hi = make_smem_desc(aq + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t a_lo = make_smem_desc(aq + CqaCfg::AQ_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t s_hi = make_smem_desc(cs + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
-            const uint64_t s_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 2 * CqaCfg::LBO_CS, CqaCfg::LBO_CS, 128);
-            umma_split3(T0, a_hi, a_lo, s_hi, s_lo, id_ssub, ks > 0 ? 1u : 0u);
-            const uint64_t v_hi = make_smem_desc(cv + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
-            const uint64_t v_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 2 * CqaCfg::LBO_CV, CqaCfg::LBO_CV, 128);
-            umma_split3(T1, a_hi, a_lo, v_hi, v_lo, id_svid, ks > 0 ? 1u : 0u);
+          for (uint32_t ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = DOFF(dA, ks * 2 * CqaCfg::LBO_A), a_lo = DOFF(dA, CqaCfg::AQ_PART + ks * 2 * CqaCfg::LBO_A);
+            umma_split3(T0, a_hi, a_lo, DOFF(dCS, ks * 2 * CqaCfg::LBO_CS), DOFF(dCS, CqaCfg::CS_PART + ks * 2 * CqaCfg::LBO_CS), id_ssub, ks > 0 ? 1u : 0u);
+            umma_split3(T1, a_hi, a_lo, DOFF(dCV, ks * 2 * CqaCfg::LBO_CV), DOFF(dCV, CqaCfg::CV_PART + ks * 2 * CqaCfg::LBO_CV), id_svid, ks > 0 ? 1u : 0u);
           }
           umma_commit(&mma_done[0]);  // D1
-        }
-      };
-      // one K=32 weight chunk against a TS-form A operand (two K=16 steps: hi at `acol`, lo 8 columns further)
-      auto issue_ts_chunk = [&](uint32_t d_tmem, uint32_t a_region, int c, bool first) {
-        const uint32_t i = q_cnt;
-        ++q_cnt;
-        CQA_TIMED(w_wait, mbar_wait(&w_full[i % CqaCfg::W_SLOTS], (i / CqaCfg::W_SLOTS) & 1u, 46));
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t wsl = ps + (i % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const uint32_t acol = a_region + 32u * c + 16u * s;
-            const uint64_t b_hi = make_smem_desc(wsl + s * 2 * 2048, 2048, 128);
-            const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + s * 2 * 2048, 2048, 128);
-            umma_f16_ts(d_tmem, acol + 8, b_hi, id_g, (first && s == 0) ? 0u : 1u);
-            umma_f16_ts(d_tmem, acol, b_lo, id_g, 1u);
-            umma_f16_ts(d_tmem, acol, b_hi, id_g, 1u);
-          }
-          umma_commit(&w_empty[i % CqaCfg::W_SLOTS]);
         }
       };
       if (my_tiles > 0) issue_s(0);
       for (int k = 0; k < my_tiles; ++k) {
         const int a_i = k % p.n_pt;
+        const uint32_t wuse = static_cast<uint32_t>(k) * (CqaCfg::CHUNKS / CqaCfg::W_SLOTS);  // uses of every ring slot before this tile
+        // local chunk j of this tile sits in slot j % 4; it is that slot's (wuse + j / 4)-th use
+#define W_WAIT(j) CQA_TIMED(w_wait, mbar_wait(&w_full[(j) % CqaCfg::W_SLOTS], (wuse + (j) / CqaCfg::W_SLOTS) & 1u, 46))
+#define W_DESC(j, off) DOFF(dW, ((j) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT + (off))
         CQA_STAMP(1, 0);
-        // ---- U = P . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups)
+        // ---- U = P' . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups).
+        //      (Issuing the K=16 steps one by one while the softmax is still producing later chunks was measured and lost:
+        //      the per-chunk fences and arrivals cost the compute warps more than the overlap returned.)
         mbar_wait(&op_ready, k & 1u, 42);  // E2
-        if (k > 0) mbar_wait(&t2_free, (k - 1) & 1u, 43);  // the epilogue warps have read the previous concat accumulator
+        if (k > 0) CQA_TIMED(o_wait, mbar_wait(&t2_free, (k - 1) & 1u, 43));  // the epilogue warps have read the previous concat accumulator
         tc_fence_after();
         CQA_STAMP(1, 1);
         if (elect_one()) {
-          for (int ks = 0; ks < p.ls_pad / 16; ++ks) {
-            const uint64_t a_hi = make_smem_desc(ps + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t a_lo = make_smem_desc(ps + CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t b_hi = make_smem_desc(cs + ks * 256, 128, CqaCfg::LBO_CS);
-            const uint64_t b_lo = make_smem_desc(cs + CqaCfg::CS_PART + ks * 256, 128, CqaCfg::LBO_CS);
-            umma_split3(T2, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
-          }
-          for (int ks = 0; ks < p.r_pad / 16; ++ks) {
-            const uint64_t a_hi = make_smem_desc(pv + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t a_lo = make_smem_desc(pv + CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-            const uint64_t b_hi = make_smem_desc(cv + ks * 256, 128, CqaCfg::LBO_CV);
-            const uint64_t b_lo = make_smem_desc(cv + CqaCfg::CV_PART + ks * 256, 128, CqaCfg::LBO_CV);
-            umma_split3(T3, a_hi, a_lo, b_hi, b_lo, id_u, ks > 0 ? 1u : 0u);
-          }
+#pragma unroll
+          for (uint32_t ks = 0; ks < CqaCfg::LS_MAX / 16; ++ks)
+            if (static_cast<int>(ks * 16) < p.ls_pad)
+              umma_split3(T2, DOFF(dP, ks * 2 * CqaCfg::LBO_A), DOFF(dP, CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A),
+                          DOFF(dCSt, ks * 256), DOFF(dCSt, CqaCfg::CS_PART + ks * 256), id_u, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (uint32_t ks = 0; ks < CqaCfg::R_MAX / 16; ++ks)
+            if (static_cast<int>(ks * 16) < p.r_pad)
+              umma_split3(T3, DOFF(dA, ks * 2 * CqaCfg::LBO_A), DOFF(dA, CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A),
+                          DOFF(dCVt, ks * 256), DOFF(dCVt, CqaCfg::CV_PART + ks * 256), id_u, ks > 0 ? 1u : 0u);
           umma_commit(&mma_done[1]);  // D2
           umma_commit(&b_free);       // P_sub (region B) may now become the weight ring
           if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         }
         CQA_STAMP(1, 2);
-        // ---- c2q, stream g: two shared-memory stages (a*U, K=64 each, two weight chunks each), then the U segment in
-        //      tensor memory (four weight chunks); accumulators T0 / T1 start from the stored a.Wa term
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t dcol = g == 0 ? T0 : T1;
-          for (uint32_t h = 0; h < 2; ++h) {
-            CQA_TIMED(o_wait, mbar_wait(&a_full[h], seg_cnt & 1u, 45));
-            const uint32_t i0 = q_cnt;
-            q_cnt += 2;
-            CQA_TIMED(w_wait, mbar_wait(&w_full[i0 % CqaCfg::W_SLOTS], (i0 / CqaCfg::W_SLOTS) & 1u, 46));
-            CQA_TIMED(w_wait, mbar_wait(&w_full[(i0 + 1u) % CqaCfg::W_SLOTS], ((i0 + 1u) / CqaCfg::W_SLOTS) & 1u, 46));
+        // ---- c2q: per half h of the K range, the a*U stages of both streams (shared memory, K=64, two weight chunks used by
+        //      sub then vid) and then that half of the U operands (tensor memory, two weight chunks, again sub then vid);
+        //      accumulators T0 / T1 start from the stored a.Wa term.  Local chunks: h0: 0,1 (a*U) 2,3 (U); h1: 4,5 / 6,7.
+#pragma unroll
+        for (uint32_t h = 0; h < 2; ++h) {
+#pragma unroll
+          for (uint32_t g = 0; g < 2; ++g) {
+            CQA_TIMED(o_wait, mbar_wait(&a_full[g], h, 45));  // two phases per tile: h = 0, 1
+            if (g == 0) {
+              W_WAIT(4 * h);
+              W_WAIT(4 * h + 1);
+            }
             tc_fence_after();
-            if (g == 0) CQA_STAMP(3, h * 2);
-            const uint32_t ast = aq + h * CqaCfg::AST_BYTES;
+            if (h == 0) CQA_STAMP(3, g * 2);
             if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t wsl = ps + ((i0 + (ks >> 1)) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT;
-                const uint64_t a_hi = make_smem_desc(ast + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-                const uint64_t a_lo = make_smem_desc(ast + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A, CqaCfg::LBO_A, 128);
-                const uint64_t b_hi = make_smem_desc(wsl + (ks & 1) * 2 * 2048, 2048, 128);
-                const uint64_t b_lo = make_smem_desc(wsl + CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048, 2048, 128);
-                umma_split3(dcol, a_hi, a_lo, b_hi, b_lo, id_g, 1u);
+              for (uint32_t ks = 0; ks < 4; ++ks) {
+                const uint32_t j = 4 * h + (ks >> 1);
+                umma_split3(g == 0 ? T0 : T1, DOFF(dA, g * CqaCfg::AST_BYTES + ks * 2 * CqaCfg::LBO_A),
+                            DOFF(dA, g * CqaCfg::AST_BYTES + CqaCfg::AST_PART + ks * 2 * CqaCfg::LBO_A),
+                            W_DESC(j, (ks & 1) * 2 * 2048), W_DESC(j, CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048), id_g, 1u);
               }
-              umma_commit(&a_empty[h]);
-              umma_commit(&w_empty[i0 % CqaCfg::W_SLOTS]);
-              umma_commit(&w_empty[(i0 + 1u) % CqaCfg::W_SLOTS]);
+              umma_commit(&a_empty[g]);
+              if (g == 1) {
+                umma_commit(&w_empty[(4 * h) % CqaCfg::W_SLOTS]);
+                umma_commit(&w_empty[(4 * h + 1) % CqaCfg::W_SLOTS]);
+              }
             }
-            if (g == 0) CQA_STAMP(3, h * 2 + 1);
+            if (h == 0) CQA_STAMP(3, g * 2 + 1);
           }
-          ++seg_cnt;
-          CQA_TIMED(o_wait, mbar_wait(&useg_full[g], k & 1u, 47));
+          CQA_TIMED(o_wait, mbar_wait(&useg_full[h], k & 1u, 47));
           tc_fence_after();
-          if (g == 0) CQA_STAMP(3, 4);
-          for (int c = 0; c < 4; ++c) issue_ts_chunk(dcol, g == 0 ? T2 : T3, c, false);
-          if (elect_one()) {
-            umma_commit(&mma_done[2 + g]);       // D3a / D3b
-            if (g == 1) umma_commit(&aq_free);   // both shared-memory stages are drained: the next answer image may land
+          if (h == 0) CQA_STAMP(3, 4);
+          // packed K-step (h, q) of the U segment = tensor-memory columns [32q + 16h, +16) of T2 / T3
+#pragma unroll
+          for (uint32_t c = 0; c < 2; ++c) {
+            const uint32_t j = 4 * h + 2 + c;
+            W_WAIT(j);  // (bulk-copied shared memory: the mbarrier orders it, no tcgen05 fence — a fence here stalls the issue)
+            if (elect_one()) {
+#pragma unroll
+              for (uint32_t g = 0; g < 2; ++g) {
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < 2; ++s2) {
+                  const uint32_t acol = (g == 0 ? T2 : T3) + 32u * (2u * c + s2) + 16u * h;
+                  const uint64_t b_hi = W_DESC(j, s2 * 2 * 2048), b_lo = W_DESC(j, CqaCfg::W_SLOT / 2 + s2 * 2 * 2048);
+                  umma_f16_ts(g == 0 ? T0 : T1, acol + 8, b_hi, id_g, 1u);
+                  umma_f16_ts(g == 0 ? T0 : T1, acol, b_lo, id_g, 1u);
+                  umma_f16_ts(g == 0 ? T0 : T1, acol, b_hi, id_g, 1u);
+                }
+              }
+              umma_commit(&w_empty[j % CqaCfg::W_SLOTS]);
+            }
           }
-          CQA_STAMP(1, 3 + g);
         }
-        // ---- concat: ms (T0), mv (T1), ms*mv (T3) against four weight chunks each, accumulator T2
-        for (int sgm = 0; sgm < 3; ++sgm) {
+        if (elect_one()) {
+          umma_commit(&mma_done[2]);  // D3: both c2q accumulators
+          umma_commit(&aq_free);      // both shared-memory stages are drained: the next answer image may land
+        }
+        CQA_STAMP(1, 3);
+        CQA_STAMP(1, 4);
+        // ---- concat: ms (T0), mv (T1), ms*mv (T3) against four weight chunks each (local chunks 8..19), accumulator T2
+#pragma unroll
+        for (uint32_t sgm = 0; sgm < 3; ++sgm) {
           CQA_TIMED(o_wait, mbar_wait(&cat_full[sgm], k & 1u, 48));
           tc_fence_after();
           CQA_STAMP(3, 5 + sgm);
-          for (int c = 0; c < 4; ++c) issue_ts_chunk(T2, sgm == 0 ? T0 : (sgm == 1 ? T1 : T3), c, sgm == 0 && c == 0);
+#pragma unroll
+          for (uint32_t c = 0; c < 4; ++c) {
+            const uint32_t j = 8 + 4 * sgm + c;
+            W_WAIT(j);  // (bulk-copied shared memory: the mbarrier orders it, no tcgen05 fence — a fence here stalls the issue)
+            if (elect_one()) {
+#pragma unroll
+              for (uint32_t s2 = 0; s2 < 2; ++s2) {
+                const uint32_t acol = (sgm == 0 ? T0 : (sgm == 1 ? T1 : T3)) + 32u * c + 16u * s2;
+                const uint64_t b_hi = W_DESC(j, s2 * 2 * 2048), b_lo = W_DESC(j, CqaCfg::W_SLOT / 2 + s2 * 2 * 2048);
+                umma_f16_ts(T2, acol + 8, b_hi, id_g, (sgm == 0 && c == 0 && s2 == 0) ? 0u : 1u);
+                umma_f16_ts(T2, acol, b_lo, id_g, 1u);
+                umma_f16_ts(T2, acol, b_hi, id_g, 1u);
+              }
+              umma_commit(&w_empty[j % CqaCfg::W_SLOTS]);
+            }
+          }
         }
         if (elect_one()) umma_commit(&mma_done[4]);  // D4
         CQA_STAMP(1, 5);
@@ -854,12 +883,15 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
           o_wait = 0;
           ++tl_tile;
         }
+#undef W_WAIT
+#undef W_DESC
       }
-    } else if (warp == 17 && lane == 0) {
+#undef DOFF
+    } else if (warp == 1 && lane == 0) {
       // ================================================================= weight ring (one thread)
       uint32_t q_cnt = 0;
       auto w_src = [&](int q) -> const uint8_t* {
-        return q < 16 ? p.c2q_w + static_cast<size_t>(q & 7) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 16) * CqaCfg::W_SLOT;
+        return q < 8 ? p.c2q_w + static_cast<size_t>(q) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 8) * CqaCfg::W_SLOT;
       };
       for (int k = 0; k < my_tiles; ++k) {
         mbar_wait(&b_free, k & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
@@ -871,7 +903,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         }
         q_cnt += CqaCfg::CHUNKS;
       }
-    } else if (warp == 18 && lane == 0) {
+    } else if (warp == 2 && lane == 0) {
       // ================================================================= ctx blobs and answer images (one thread)
       int k = 0;
       uint32_t frame_cnt = 0;
@@ -947,7 +979,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc<512>(tbase);
+  if (warp == 0) tmem_dealloc<512>(tbase);
 }
 
 }  // namespace stg

@@ -58,6 +58,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int ld, int k0, 
   }
 }
 
+// One half (h = 0 / 1) of a 128-column segment [k0, k0 + 128) in the fused CQA kernel's K order: packed position
+// q*16 + j of the half  <-  source column q*32 + h*16 + j (q = 0..3).  g = pack_geom(n, 64, 32): two K=32 chunks.
+__global__ void pack_weight_half_kernel(const float* __restrict__ w, int ld, int k0, const float* __restrict__ col_scale,
+                                        PackGeom g, int h, uint8_t* __restrict__ out) {
+  const int total = (g.kpad / 8) * g.npad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int n = idx % g.npad, k8 = idx / g.npad;
+    const int kk = k8 * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pos = kk + j;  // 0..63 inside the half
+      const int src = (pos >> 4) * 32 + h * 16 + (pos & 15);
+      float x = n < g.n ? w[static_cast<size_t>(n) * ld + k0 + src] : 0.f;
+      if (col_scale != nullptr) x *= col_scale[k0 + src];
+      v[j] = x;
+    }
+    HL8 hl = split8(v);
+    const int c = kk / g.kc, s = (kk % g.kc) / 8;
+    uint8_t* base = out + static_cast<size_t>(c) * g.chunk_bytes + static_cast<size_t>(s) * g.lbo + static_cast<size_t>(n) * 16;
+    *reinterpret_cast<uint4*>(base) = hl.hi;
+    *reinterpret_cast<uint4*>(base + g.part_bytes) = hl.lo;
+  }
+}
+
 // LayerNorm folded into the Linear that follows it:  LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * cs) + cb  with
 //   cs[n] = sum_k W[n,k] gamma[k],  cb[n] = sum_k W[n,k] beta[k] + b[n].          One warp per output feature n.
 __global__ void fold_layernorm_kernel(const float* __restrict__ w, int n, int k, const float* __restrict__ gamma,

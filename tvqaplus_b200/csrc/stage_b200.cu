@@ -206,7 +206,7 @@ int stage_mha_fwd(const StageMhaArgs* a, void* stream) {
 
 // weight blob layout of the fused CQA kernel
 static constexpr size_t WB_WA = 0;                      // (Wc*gamma)[:, 0:128]   packed kc=64 (Za = a . Wa^T via the linear kernel)
-static constexpr size_t WB_WU = 65536;                  // (Wc*gamma)[:, 256:384] (stage order) | [:, 128:256] (natural), kc=32, 4 + 4 chunks
+static constexpr size_t WB_WU = 65536;                  // (Wc*gamma): [aU h0 | U h0 | aU h1 | U h1] in the kernel's K order, kc=32, 2 chunks each
 static constexpr size_t WB_WF = WB_WU + 8 * 16384;      // (Wf*gamma)             packed kc=32, 12 chunks
 static constexpr size_t WB_VEC = WB_WF + 12 * 16384;    // c2q cs | c2q cb | cat cs | cat cb | zeros, 128 floats each
 static constexpr size_t WB_BYTES = WB_VEC + 5 * 512;
@@ -226,11 +226,14 @@ int stage_cqa_prepare_weights(const float* c2q_ln_g, const float* c2q_ln_b, cons
     PackGeom g = pack_geom(128, 128, 64);
     pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 0, c2q_ln_g, g, wb + WB_WA);
   }
-  {  // c2q chunks in the order the fused kernel consumes them: the a*U segment (columns 256..383) in the column order of
-     // the two shared-memory A stages, then the U segment (columns 128..255) in natural order (TS-form operand)
-    PackGeom g = pack_geom(128, 128, 32);
-    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 256, c2q_ln_g, g, wb + WB_WU, 1);
-    pack_weight_kernel<<<((g.kpad / 8) * g.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 128, c2q_ln_g, g, wb + WB_WU + 4 * 16384, 0);
+  {  // c2q chunks in the order the fused kernel consumes them.  Both segments use the kernel's K order (perm128: packed
+     // position h*64 + q*16 + j <- column q*32 + h*16 + j): per half h, the two a*U chunks (columns 256..383) and then
+     // the two U chunks (columns 128..255)  ->  blob = [aU h0 | U h0 | aU h1 | U h1], two chunks each
+    PackGeom gh = pack_geom(128, 64, 32);  // one half (h) of a permuted segment = 2 chunks = packed positions [64h, 64h+64)
+    for (int h = 0; h < 2; ++h) {
+      pack_weight_half_kernel<<<((gh.kpad / 8) * gh.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 256, c2q_ln_g, gh, h, wb + WB_WU + (4 * h) * 16384);
+      pack_weight_half_kernel<<<((gh.kpad / 8) * gh.npad + 255) / 256, 256, 0, s>>>(c2q_w, 384, 128, c2q_ln_g, gh, h, wb + WB_WU + (4 * h + 2) * 16384);
+    }
   }
   {
     PackGeom g = pack_geom(128, 384, 32);
