@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         return q < 8 ? p.c2q_w + static_cast<size_t>(q) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 8) * CqaCfg::W_SLOT;
       };
       for (int k = 0; k < my_tiles; ++k) {
-        mbar_wait(&b_free, k & 1u, 52);  // U has completed: region B turns from P_sub into the weight ring
+        mbar_wait_relaxed(&b_free, k & 1u, 52, 128);  // U has completed: region B turns from P_sub into the weight ring
         for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
           const uint32_t i = q_cnt + q, slot = i % CqaCfg::W_SLOTS, use = i / CqaCfg::W_SLOTS;
           mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 53);
@@ -909,12 +909,12 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
       uint32_t frame_cnt = 0;
       for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x, ++frame_cnt) {
         const int n_i = frame / p.t;
-        if (frame_cnt > 0) mbar_wait(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
+        if (frame_cnt > 0) mbar_wait_relaxed(&ctx_free, (frame_cnt - 1u) & 1u, 50);  // the previous frame's last U has completed
         mbar_arrive_expect_tx(&ctx_full, CqaCfg::CTX_BYTES);
         bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
         for (int a_i = 0; a_i < p.n_pt; ++a_i, ++k) {
           const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
-          if (k > 0) mbar_wait(&aq_free, (k - 1) & 1u, 51);  // the previous tile's a*U stages are drained
+          if (k > 0) mbar_wait_relaxed(&aq_free, (k - 1) & 1u, 51);  // the previous tile's a*U stages are drained
           mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
           bulk_g2s(sAQ, p.a_blob + nj * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
         }
@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
           dst = reinterpret_cast<float4*>(p.statement) + static_cast<size_t>(trow) * 32 * p.stmt_stride + (srow - trow * p.lq);
           dstep = p.stmt_stride;
         }
-        mbar_wait(&ep_ready, k & 1u, 60);
+        mbar_wait_relaxed(&ep_ready, k & 1u, 60);  // (most of a tile away: sleep between polls)
         tc_fence_after();
         CQA_STAMP(5, 0);
         const float2 st = ep_stat[row];

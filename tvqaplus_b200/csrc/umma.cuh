@@ -75,6 +75,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
+// The same bounded wait for waiters that are far from any critical path (a warp that waits most of a tile for its next
+// hand-over): sleeps between attempts, so its polling does not compete with the working warps for issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned code = 1, unsigned sleep_ns = 256) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) {
+      atomicMax(&g_dev_error, 0x100u + code);
+      return;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // proxy fences + bulk copy (global -> shared, completes on an mbarrier)
 // ------------------------------------------------------------------------------------------------
