@@ -306,6 +306,54 @@ def main():
                "note": "pinned host inputs, double-buffered H2D on a copy stream, answer + span probs read back every step"}
         del bufs
 
+        # ------------------------------------------------------------ end-to-end on the RAGGED variant of the same config
+        # (QA length ~U[0.5 Lq, Lq], sub-title tokens ~U[0.3 Ls, Ls], regions ~U[0.5 R, R], frames ~U[0.7 T, T]):
+        # the collate keeps only the valid rows (tvqaplus_b200/collate.py), every step uploads them from pinned memory and pads
+        # on the device (stage_pad_rows) before the forward; answer + span probabilities are read back as above.
+        from tvqaplus_b200 import collate
+        rb = collate.pad_collate(collate.synthetic_items(N, T, R, Lq, Ls, seed=2018 + rank), pin=True)
+        maxl = dict(max_qa_l=Lq, max_vid_l=T, max_sub_l=Ls)
+        rg_h2d = rb.h2d_bytes()
+
+        def run_ragged(steps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            staged, evs = [None, None], [torch.cuda.Event(), torch.cuda.Event()]
+
+            def upload(slot):
+                with torch.cuda.stream(copy_stream):
+                    inp, _, _ = collate.prepare_inputs(rb, maxl, dev)
+                    for v in inp.values():
+                        if torch.is_tensor(v):
+                            v.record_stream(main_stream)
+                    staged[slot] = inp
+                    evs[slot].record()
+
+            with torch.cuda.stream(copy_stream):
+                s0.record()
+            upload(0)
+            for i in range(steps):
+                cur = i % 2
+                if i + 1 < steps:
+                    upload(1 - cur)
+                main_stream.wait_event(evs[cur])
+                ans, _, _, _, probs = model(staged[cur])
+                res_host[cur]["a"].copy_(ans, non_blocking=True)
+                res_host[cur]["p"][:, :, :probs.shape[2]].copy_(probs, non_blocking=True)
+            s1.record()
+            torch.cuda.synchronize()
+            return s0.elapsed_time(s1)
+
+        run_ragged(2)
+        barrier()
+        ms_rg = max_over_ranks(run_ragged(args.steps))
+        barrier()
+        e2e["ragged"] = {"value": N * world * args.steps / (ms_rg * 1e-3), "unit": "examples/s", "h2d_bytes_per_step": rg_h2d,
+                         "ms_per_step": ms_rg / args.steps, "h2d_gb_per_s_per_rank": rg_h2d / (ms_rg / args.steps * 1e-3) / 1e9,
+                         "bytes_vs_dense": rg_h2d / h2d,
+                         "note": "ragged masks of SURVEY 8d; valid rows only travel host->device, padding + masks are built on the device "
+                                 "(tvqaplus_b200.collate.prepare_inputs = the reference's prepare_inputs signature)"}
+        del rb
+
     # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0 timing, own stream)
     with torch.no_grad():
         a_embed = model.base_encoder(dbatch.qas_bert.view(N * 5, Lq, 768), dbatch.qas_mask.view(N * 5, Lq), model._text_fc, None, model.input_encoder).view(N, 5, Lq, H)

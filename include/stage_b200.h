@@ -232,6 +232,14 @@ int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, i
 int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64_t row_stride, int elem_stride,
                         int32_t* spans, double* val, void* stream);
 
+/* ---- pad_sequences_2d on the device (collate / prepare_inputs, tvqa_dataset.py:515-553,631-688) -------------------
+ * The host uploads only the VALID rows of a ragged feature tensor, concatenated (`rows`, d floats each, d % 4 == 0), plus
+ * per-sequence row offsets and lengths; out[n_seq, l_pad, d] gets sequence s's first min(len[s], l_pad) rows and zeros
+ * behind them (pads must be zero: the reference's outputs depend on pad values), mask[n_seq, l_pad] = (j < len[s]).
+ * The clipping to l_pad is prepare_inputs' `[:, :, :max_*_l]`. */
+int stage_pad_rows(const float* rows, const int64_t* off, const int32_t* len, int64_t n_seq, int l_pad, int d, float* out,
+                   float* mask, void* stream);
+
 /* ---- mask_logits (model/model_utils.py:14-15): y = x*m + (1-m)*(-1e10), m broadcast over the last `inner` elems ---- */
 int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream);
 

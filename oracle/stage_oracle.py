@@ -503,3 +503,45 @@ def find_max_pair(p1, p2):
         if v1 * p2[i] > max_val:
             best, max_val = (k1, i), v1 * p2[i]
     return best, float(max_val)
+
+
+# ----------------------------------------------------------------------------------------------
+# collate — tvqa_dataset.py:515-553 (pad_sequences_2d) and :631-688 (prepare_inputs' clipping)
+# ----------------------------------------------------------------------------------------------
+def pad_sequences_2d(sequences, dtype=torch.float):
+    """Double-nested list of (len, D) tensors -> zero-padded (B, max_para, max_sen, D) tensor + (B, max_para, max_sen) mask."""
+    bsz = len(sequences)
+    max_para = max(len(seq) for seq in sequences)
+    max_sen = max(len(w) for seq in sequences for w in seq)
+    extra = tuple(sequences[0][0].shape[1:]) if torch.is_tensor(sequences[0][0]) else ()
+    if not torch.is_tensor(sequences[0][0]):
+        sequences = [[torch.LongTensor(w) for w in seq] for seq in sequences]
+    padded = torch.zeros((bsz, max_para, max_sen) + extra, dtype=dtype)
+    mask = torch.zeros(bsz, max_para, max_sen).float()
+    for b in range(bsz):
+        for s, w in enumerate(sequences[b]):
+            padded[b, s, :len(w)] = w
+            mask[b, s, :len(w)] = 1
+    return padded, mask
+
+
+def collate_and_prepare(items, max_len_dict):
+    """pad_collate + prepare_inputs of the reference for the fields STAGE.forward reads (host tensors)."""
+    qas_bert, qas_mask = pad_sequences_2d([d["qas_bert"] for d in items])
+    sub_bert, sub_mask = pad_sequences_2d([d["sub_bert"] for d in items])
+    vid, vid_mask = pad_sequences_2d([d["vfeat"] for d in items])
+    qas, _ = pad_sequences_2d([[x.tolist() for x in d["qas"]] for d in items], dtype=torch.long)
+    lens = [len(d["image_indices"]) for d in items]
+    ts_mask = torch.zeros(len(items), max(lens))
+    for i, l in enumerate(lens):
+        ts_mask[i, :l] = 1
+    ql = min(qas_bert.shape[2], max_len_dict["max_qa_l"])
+    vl, sl = max_len_dict["max_vid_l"], max_len_dict["max_sub_l"]
+    return Batch(qas=qas[:, :, :ql], qas_bert=qas_bert[:, :, :ql].contiguous(), qas_mask=qas_mask[:, :, :ql].contiguous(),
+                 sub_bert=sub_bert[:, :vl, :sl].contiguous(), sub_mask=sub_mask[:, :vl, :sl].contiguous(),
+                 vid=vid[:, :vl].contiguous(), vid_mask=vid_mask[:, :vl].contiguous(), ts_label_mask=ts_mask[:, :vl].contiguous(),
+                 target=torch.tensor([d["target"] for d in items]),
+                 ts_label=dict(st=torch.tensor([d["ts_label"][0] for d in items]), ed=torch.tensor([d["ts_label"][1] for d in items])),
+                 qid=[d["qid"] for d in items], vid_name=[d["vid_name"] for d in items], att_labels=None, anno_st_idx=[0] * len(items),
+                 q_l=[d["q_l"] for d in items], image_indices=[d["image_indices"] for d in items], boxes=None,
+                 use_hard_negatives=False, eval_object_word_ids=None)

@@ -283,6 +283,29 @@ __global__ void find_max_pair_kernel(const float* __restrict__ p1, const float* 
   val[r] = best;
 }
 
+// pad_sequences_2d on the device (tvqa_dataset.py:515-553): the valid rows of all sequences arrive concatenated
+// (`rows`, D floats each, sequence s at row offset off[s]); sequence s becomes rows [s*l_pad, (s+1)*l_pad) of `out`, its
+// first min(len[s], l_pad) rows copied, the rest zero-filled, and mask[s, j] = j < len[s].  One warp per output row.
+__global__ void pad_rows_kernel(const float* __restrict__ rows, const long long* __restrict__ off, const int* __restrict__ len,
+                                long long n_seq, int l_pad, int d4, float* __restrict__ out, float* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long n_rows = n_seq * l_pad;
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n_rows;
+       r += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    const long long s = r / l_pad;
+    const int j = static_cast<int>(r - s * l_pad);
+    const bool on = j < __ldg(len + s);
+    float4* dst = reinterpret_cast<float4*>(out) + r * d4;
+    if (on) {
+      const float4* src = reinterpret_cast<const float4*>(rows) + (__ldg(off + s) + j) * d4;
+      for (int c = lane; c < d4; c += 32) dst[c] = __ldg(src + c);
+    } else {
+      for (int c = lane; c < d4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (lane == 0) mask[r] = on ? 1.f : 0.f;
+  }
+}
+
 __global__ void mask_logits_kernel(const float* __restrict__ x, const float* __restrict__ m, long long outer, int inner,
                                    float* __restrict__ y) {
   const long long total = outer * inner;

@@ -368,6 +368,18 @@ int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64
   return check_launch("find_max_pair");
 }
 
+int stage_pad_rows(const float* rows, const int64_t* off, const int32_t* len, int64_t n_seq, int l_pad, int d, float* out,
+                   float* mask, void* stream) {
+  STG_REQUIRE(off && len && out && mask, STAGE_E_BADARG, "pad_rows: null pointer");
+  STG_REQUIRE(n_seq > 0 && l_pad > 0 && d > 0 && d % 4 == 0, STAGE_E_BADARG, "pad_rows: n_seq=%lld l_pad=%d d=%d", (long long)n_seq, l_pad, d);
+  STG_REQUIRE((rows == nullptr || aligned16(rows)) && aligned16(out), STAGE_E_BADARG, "pad_rows: pointers must be 16-byte aligned");
+  const long long n_rows = n_seq * l_pad;
+  const long long want = (n_rows + 7) / 8;  // 8 warps per block
+  const int grid = static_cast<int>(want < 148ll * 32 ? want : 148ll * 32);
+  pad_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, reinterpret_cast<const long long*>(off), len, n_seq, l_pad, d / 4, out, mask);
+  return check_launch("pad_rows");
+}
+
 int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream) {
   STG_REQUIRE(x && mask && y, STAGE_E_BADARG, "mask_logits: null pointer");
   STG_REQUIRE(outer > 0 && inner > 0, STAGE_E_BADARG, "mask_logits: outer=%lld inner=%d", (long long)outer, inner);

@@ -332,6 +332,22 @@ def find_max_pairs(probs: torch.Tensor):
 
 
 @_guarded
+def pad_rows(rows: torch.Tensor, off: torch.Tensor, lens: torch.Tensor, l_pad: int):
+    """``pad_sequences_2d`` on the device (stage_pad_rows): ``rows`` (R, D) = the valid rows of all sequences concatenated,
+    ``off`` (n_seq,) int64 row offsets, ``lens`` (n_seq,) int32 -> (out (n_seq, l_pad, D) zero-padded, mask (n_seq, l_pad))."""
+    rows = _f32(rows)
+    if off.dtype != torch.int64 or lens.dtype != torch.int32:
+        raise RuntimeError("tvqaplus_b200: pad_rows needs int64 offsets and int32 lengths")
+    n_seq, D = lens.numel(), rows.shape[1]
+    out = torch.empty(n_seq, l_pad, D, dtype=torch.float32, device=rows.device)
+    mask = torch.empty(n_seq, l_pad, dtype=torch.float32, device=rows.device)
+    check(lib().stage_pad_rows(ptr(rows) if rows.numel() else None, ptr(off.contiguous()), ptr(lens.contiguous()), n_seq, int(l_pad), D,
+                               ptr(out), ptr(mask), current_stream()), "stage_pad_rows")
+    _count()
+    return out, mask
+
+
+@_guarded
 def mask_logits_fwd(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """x*m + (1-m)*(-1e10) with m broadcast over the trailing axes of x it lacks (stage_mask_logits)."""
     x = _f32(x)
