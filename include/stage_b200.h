@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define STAGE_ABI_VERSION 2
+#define STAGE_ABI_VERSION 3
 #define STAGE_HSZ 128          /* opt.hsz the kernels are specialised for (config.py:103) */
 #define STAGE_MAX_SEQ 128      /* longest token/region axis one encoder tile holds */
 #define STAGE_MAX_CONV 4       /* n_conv per encoder block (config.py:108,114 default 2) */
@@ -217,8 +217,40 @@ typedef struct {
   float* span_conf;    /* [n*5] p_st*p_ed of the chosen span */
   float* answer;       /* [n,5] */
   float* workspace;    /* n*5*t*128 floats (encoded max_statement) */
+  /* optional (all NULL = off): get_ts_loss (model/stage.py:539-555) fused into the same launch — the cross-entropy terms
+   * of the ground-truth answer's row and their sum over the batch, (st + ed) / 2 — and what the train-mode proposal pass
+   * below reads */
+  const int64_t* target;   /* [n] ground-truth answer index */
+  const int64_t* ts_st;    /* [n] ground-truth start frame */
+  const int64_t* ts_ed;    /* [n] ground-truth end frame (inclusive) */
+  float* ts_terms;         /* [n,2] scratch: -log softmax(scores)[label] for start / end */
+  float* ts_loss;          /* [1] temporal loss */
+  float* frame_mask;       /* [n*5,t] max_statement_mask */
+  float* gfeat;            /* [n*5,128] masked max over all frames of the encoded statement */
 } StageHeadArgs;
 int stage_span_head_fwd(const StageHeadArgs* a, void* stream);
+
+/* ---- train branch of get_proposals + classifier (model/stage.py:407-438,536), run after stage_span_head_fwd -----------
+ * Candidate row 2*i is example i's ground-truth span, row 2*i + 1 its predicted span (the best st <= ed pair of the
+ * ground-truth answer's row), valid only if confidence >= ce_prob_thd and temporal IoU with the ground truth >= 0.5
+ * (model_utils.py:37-51).  Valid rows hold the five answer scores of that proposal; the caller compacts the valid rows
+ * (in order) into the reference's (N_new, 5) output and (N_new,) targets. */
+typedef struct {
+  int n, t;
+  int extra_span_length;
+  float ce_prob_thd;
+  const float* encoded;     /* [n,5,t,128] workspace of stage_span_head_fwd */
+  const float* frame_mask;  /* [n*5,t] */
+  const float* gfeat;       /* [n*5,128] */
+  const int32_t* spans;     /* [n*5,2] */
+  const float* span_conf;   /* [n*5] */
+  const int64_t* target; const int64_t* ts_st; const int64_t* ts_ed;  /* [n] each */
+  const float* cls_ln_g; const float* cls_ln_b; const float* cls_w; const float* cls_b;   /* classifier (256 -> 1) */
+  float* answer_rows;       /* [2n,5] */
+  int32_t* row_valid;       /* [2n] */
+  int64_t* row_target;      /* [2n] */
+} StageProposalArgs;
+int stage_train_proposals_fwd(const StageProposalArgs* a, void* stream);
 
 /* ---- best span search on its own (find_max_triples topN=1, model/model_utils.py:92-121) -------------------------- */
 int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, int32_t* spans, float* conf,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libstage_b200.so does not export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
-    assert _lib.lib().stage_abi_version() == 2
+    assert _lib.lib().stage_abi_version() == 3
 
 
 def test_bad_arguments_return_error_codes_not_crashes():
@@ -70,10 +70,11 @@ def test_position_table_matches_oracle():
     assert torch.equal(PositionEncoding().pe, O.position_encoding_table())
 
 
-def test_train_mode_fails_loudly():
+def test_train_mode_with_dropout_fails_loudly():
+    """dropout > 0 in train mode needs the reference's RNG stream: refused, never approximated."""
     from tvqaplus_b200.model import STAGE
     m = STAGE(O.default_opt()).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError, match="dropout"):
         m(O.make_synthetic_batch(1, 2, 2, 3, 3))
 
 
@@ -103,7 +104,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         pytest.skip("gcc not available")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = [("StageLinearArgs", _lib.LinearArgs), ("StageEncoderArgs", _lib.EncoderArgs), ("StageMhaArgs", _lib.MhaArgs),
-             ("StageCqaArgs", _lib.CqaArgs), ("StageHeadArgs", _lib.HeadArgs), ("StageProbeArgs", _lib.ProbeArgs)]
+             ("StageCqaArgs", _lib.CqaArgs), ("StageHeadArgs", _lib.HeadArgs), ("StageProposalArgs", _lib.ProposalArgs),
+             ("StageProbeArgs", _lib.ProbeArgs)]
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "stage_b200.h"', "int main(void) {"]
     for cname, ct in pairs:
         lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))

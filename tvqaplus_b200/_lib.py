@@ -53,7 +53,16 @@ class HeadArgs(C.Structure):
                 ("st_ln_g", _f), ("st_ln_b", _f), ("st_w", _f), ("st_b", _f),
                 ("ed_ln_g", _f), ("ed_ln_b", _f), ("ed_w", _f), ("ed_b", _f),
                 ("cls_ln_g", _f), ("cls_ln_b", _f), ("cls_w", _f), ("cls_b", _f),
-                ("t_scores", _f), ("t_probs", _f), ("spans", _f), ("span_conf", _f), ("answer", _f), ("workspace", _f)]
+                ("t_scores", _f), ("t_probs", _f), ("spans", _f), ("span_conf", _f), ("answer", _f), ("workspace", _f),
+                ("target", _f), ("ts_st", _f), ("ts_ed", _f), ("ts_terms", _f), ("ts_loss", _f), ("frame_mask", _f), ("gfeat", _f)]
+
+
+class ProposalArgs(C.Structure):
+    _fields_ = [("n", C.c_int), ("t", C.c_int), ("extra_span_length", C.c_int), ("ce_prob_thd", C.c_float),
+                ("encoded", _f), ("frame_mask", _f), ("gfeat", _f), ("spans", _f), ("span_conf", _f),
+                ("target", _f), ("ts_st", _f), ("ts_ed", _f),
+                ("cls_ln_g", _f), ("cls_ln_b", _f), ("cls_w", _f), ("cls_b", _f),
+                ("answer_rows", _f), ("row_valid", _f), ("row_target", _f)]
 
 
 class ProbeArgs(C.Structure):
@@ -85,6 +94,7 @@ SYMBOLS = {
     "stage_cqa_ctx_blob_bytes": (C.c_size_t, []),
     "stage_cqa_fused_fwd": (C.c_int, [C.POINTER(CqaArgs), C.c_void_p]),
     "stage_span_head_fwd": (C.c_int, [C.POINTER(HeadArgs), C.c_void_p]),
+    "stage_train_proposals_fwd": (C.c_int, [C.POINTER(ProposalArgs), C.c_void_p]),
     "stage_find_max_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stage_find_max_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
@@ -109,7 +119,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.stage_abi_version() != 2:
+        if l.stage_abi_version() != 3:
             raise RuntimeError("tvqaplus_b200: ABI version mismatch in %s" % LIB_PATH)
         _lib = l
     return _lib

@@ -24,6 +24,12 @@ struct HeadDev {
   const float *ed_g, *ed_b, *ed_w, *ed_bias;
   const float *cls_g, *cls_b, *cls_w, *cls_bias;
   float* t_scores; float* t_probs; int* spans; float* span_conf; float* answer; float* enc;
+  // optional: temporal loss terms of the ground-truth answer rows (get_ts_loss, stage.py:539-555) and what the train-mode
+  // proposal kernel needs (frame mask, global feature)
+  const long long* target; const long long* ts_st; const long long* ts_ed;
+  float* ts_terms;     // [n,2]: -log softmax(scores[:, c])[label_c] of the ground-truth answer row
+  float* frame_mask;   // [n*5, t]
+  float* gfeat;        // [n*5, 128]
 };
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red, int tid) {
@@ -93,6 +99,8 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
     }
   }
   __syncthreads();
+  if (p.frame_mask != nullptr)
+    for (int t = tid; t < T; t += 256) p.frame_mask[static_cast<size_t>(row) * T + t] = fm[t];
 
   const float4 pg = __ldg(reinterpret_cast<const float4*>(p.proj_g) + lane), pb = __ldg(reinterpret_cast<const float4*>(p.proj_b) + lane);
   const float4 pbias = __ldg(reinterpret_cast<const float4*>(p.proj_bias) + lane);
@@ -159,10 +167,14 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
   *reinterpret_cast<float4*>(lnv + warp * 256 + lane * 4) = gmax;  // the staging rows are free now: [warp][128] partial maxima
   __syncthreads();
 
-  // ---- softmax over frames for st (c=0) and ed (c=1)
+  // ---- softmax over frames for st (c=0) and ed (c=1); on the ground-truth answer's row also the cross-entropy term of
+  //      get_ts_loss (stage.py:539-555): -log_softmax(scores)[label] = mx + log(sum exp(s - mx)) - s[label]
+  const bool gt_row = p.ts_terms != nullptr && (row - n_i * 5) == static_cast<int>(__ldg(p.target + n_i));
   for (int c = 0; c < 2; ++c) {
-    float mx = -3.0e38f;
+    float mx = -3.0e38f, raw_label = 0.f;
     for (int t = tid; t < T; t += 256) mx = fmaxf(mx, sc[2 * t + c]);
+    // (read before the reduction's barriers: behind them the other threads start turning the scores into exponentials)
+    if (gt_row && tid == 0) raw_label = sc[2 * static_cast<int>(__ldg((c == 0 ? p.ts_st : p.ts_ed) + n_i)) + c];
     mx = block_reduce(mx, true, red, tid);
     float s = 0.f;
     for (int t = tid; t < T; t += 256) {
@@ -171,6 +183,7 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
       s += e;
     }
     s = block_reduce(s, false, red, tid);
+    if (gt_row && tid == 0) p.ts_terms[2 * n_i + c] = (mx + logf(s)) - raw_label;
     for (int t = tid; t < T; t += 256) {
       const float pr = sc[2 * t + c] / s;
       sc[2 * t + c] = pr;
@@ -204,6 +217,7 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
 #pragma unroll
       for (int w = 1; w < 8; ++w) mx = fmaxf(mx, lnv[w * 256 + c]);
       feat[p.add_local ? tid : c] = mx;
+      if (p.gfeat != nullptr) p.gfeat[static_cast<size_t>(row) * 128 + c] = mx;
     } else if (p.add_local) {
       int lo = span_sh[0] - p.extra, hi = span_sh[1] + 1 + p.extra;
       if (lo < 0) lo = 0;
@@ -241,6 +255,93 @@ __global__ void __launch_bounds__(256, 2) head_kernel(HeadDev p) {
     const float term = tid < F ? (d * rs * __ldg(p.cls_g + tid) + __ldg(p.cls_b + tid)) * __ldg(p.cls_w + tid) : 0.f;
     const float tot = block_reduce(term, false, red, tid);
     if (tid == 0) p.answer[row] = tot + __ldg(p.cls_bias);
+  }
+}
+
+// (st + ed) / 2 summed over the examples, in a fixed order (one thread: n is a batch size)
+__global__ void ts_loss_sum_kernel(const float* __restrict__ terms, int n, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float st = 0.f, ed = 0.f;
+    for (int i = 0; i < n; ++i) { st += terms[2 * i]; ed += terms[2 * i + 1]; }
+    *loss = (st + ed) / 2.f;
+  }
+}
+
+// Train branch of get_proposals + classifier (stage.py:407-438,536).  Candidate row r = 2*example + kind: kind 0 = the
+// ground-truth span [st, ed+1), kind 1 = the predicted span of the ground-truth answer's row (head_kernel's prefix-max
+// search on that row, as find_max_triples(topN=1, prob_thd) does), kept only if its confidence >= ce_prob_thd and its
+// temporal IoU with the ground truth >= 0.5 (compute_temporal_iou: intersection over the convex hull, model_utils.py:37-51).
+// Every kept row scores all five answers: [masked max over the span's frames (+- extra), masked max over all frames] ->
+// LayerNorm(256) -> Linear.  One CTA per candidate row.
+struct ProposalDev {
+  int n, t, extra;
+  float ce_prob_thd;
+  const float* enc;          // [n,5,t,128] encoded max_statement (head_kernel workspace)
+  const float* frame_mask;   // [n*5,t]
+  const float* gfeat;        // [n*5,128]
+  const int* spans;          // [n*5,2] inclusive (st, ed) of every row
+  const float* span_conf;    // [n*5]
+  const long long* target; const long long* ts_st; const long long* ts_ed;
+  const float *cls_g, *cls_b, *cls_w, *cls_bias;
+  float* answer_rows;        // [2n,5]
+  int* row_valid;            // [2n]
+  long long* row_target;     // [2n]
+};
+
+__global__ void __launch_bounds__(256) proposal_cls_kernel(ProposalDev p) {
+  __shared__ float feat[256];
+  __shared__ float red[8];
+  __shared__ int sh[3];
+  const int tid = threadIdx.x, r = blockIdx.x, n_i = r >> 1, kind = r & 1, T = p.t;
+  if (tid == 0) {
+    const int tgt = static_cast<int>(__ldg(p.target + n_i));
+    const int g0 = static_cast<int>(__ldg(p.ts_st + n_i)), g1 = static_cast<int>(__ldg(p.ts_ed + n_i)) + 1;
+    int s0 = g0, s1 = g1, ok = 1;
+    if (kind == 1) {
+      const int row = n_i * 5 + tgt;
+      s0 = p.spans[2 * row];
+      s1 = p.spans[2 * row + 1] + 1;
+      const int inter = max(0, min(s1, g1) - max(s0, g0)), uni = max(s1, g1) - min(s0, g0);
+      // float(conf) >= prob_thd and 1.0*inter/union >= 0.5 of the reference, both evaluated exactly
+      ok = (static_cast<double>(p.span_conf[row]) >= static_cast<double>(p.ce_prob_thd)) && uni != 0 && 2 * inter >= uni;
+    }
+    sh[0] = max(0, s0 - p.extra);       // expand_span + python slice clipping (model_utils.py:78-89)
+    sh[1] = min(T, s1 + p.extra);
+    sh[2] = ok;
+    p.row_valid[r] = ok;
+    p.row_target[r] = tgt;
+  }
+  __syncthreads();
+  const int lo = sh[0], hi = sh[1];
+  if (!sh[2]) {
+    if (tid < 5) p.answer_rows[r * 5 + tid] = 0.f;
+    return;
+  }
+  const int c = tid & 127;
+  for (int a = 0; a < 5; ++a) {
+    const int row = n_i * 5 + a;
+    if (tid >= 128) {
+      feat[tid] = __ldg(p.gfeat + static_cast<size_t>(row) * 128 + c);
+    } else {
+      const float* e = p.enc + static_cast<size_t>(row) * T * 128 + c;
+      const float* fm = p.frame_mask + static_cast<size_t>(row) * T;
+      float mx = -3.0e38f;  // an empty slice cannot occur: st <= ed
+      for (int t = lo; t < hi; ++t) {
+        const float m = __ldg(fm + t);
+        mx = fmaxf(mx, __ldg(e + static_cast<size_t>(t) * 128) * m + (1.f - m) * STG_NEG);
+      }
+      feat[tid] = mx;
+    }
+    __syncthreads();
+    const float v = feat[tid];
+    const float mean = block_reduce(v, false, red, tid) / 256.f;
+    const float d = v - mean;
+    const float var = block_reduce(d * d, false, red, tid) / 256.f;
+    const float rs = 1.f / sqrtf(var + 1e-5f);
+    const float term = (d * rs * __ldg(p.cls_g + tid) + __ldg(p.cls_b + tid)) * __ldg(p.cls_w + tid);
+    const float tot = block_reduce(term, false, red, tid);
+    if (tid == 0) p.answer_rows[r * 5 + a] = tot + __ldg(p.cls_bias);
+    __syncthreads();
   }
 }
 

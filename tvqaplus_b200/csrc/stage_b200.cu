@@ -346,11 +346,32 @@ int stage_span_head_fwd(const StageHeadArgs* a, void* stream) {
   d.cls_g = a->cls_ln_g; d.cls_b = a->cls_ln_b; d.cls_w = a->cls_w; d.cls_bias = a->cls_b;
   d.t_scores = a->t_scores; d.t_probs = a->t_probs; d.spans = a->spans; d.span_conf = a->span_conf; d.answer = a->answer;
   d.enc = a->workspace;
+  STG_REQUIRE(a->ts_terms == nullptr || (a->target && a->ts_st && a->ts_ed && a->ts_loss), STAGE_E_BADARG,
+              "span_head: the temporal loss needs target, ts_st, ts_ed and ts_loss");
+  d.target = reinterpret_cast<const long long*>(a->target); d.ts_st = reinterpret_cast<const long long*>(a->ts_st);
+  d.ts_ed = reinterpret_cast<const long long*>(a->ts_ed); d.ts_terms = a->ts_terms; d.frame_mask = a->frame_mask; d.gfeat = a->gfeat;
   const size_t smem = (128 * 128 + 16 * 128 + 3 * static_cast<size_t>(a->t) + 256) * sizeof(float);
   int rc = set_smem(head_kernel, smem, "span_head");
   if (rc) return rc;
   head_kernel<<<a->n * 5, 256, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  if (a->ts_terms != nullptr) ts_loss_sum_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a->ts_terms, a->n, a->ts_loss);
   return check_launch("span_head");
+}
+
+int stage_train_proposals_fwd(const StageProposalArgs* a, void* stream) {
+  STG_REQUIRE(a && a->encoded && a->frame_mask && a->gfeat && a->spans && a->span_conf && a->target && a->ts_st && a->ts_ed &&
+                  a->cls_ln_g && a->cls_ln_b && a->cls_w && a->cls_b && a->answer_rows && a->row_valid && a->row_target,
+              STAGE_E_BADARG, "train_proposals: null pointer");
+  STG_REQUIRE(a->n > 0 && a->t > 0 && a->extra_span_length >= 0, STAGE_E_BADARG, "train_proposals: n=%d t=%d", a->n, a->t);
+  ProposalDev d;
+  d.n = a->n; d.t = a->t; d.extra = a->extra_span_length; d.ce_prob_thd = a->ce_prob_thd;
+  d.enc = a->encoded; d.frame_mask = a->frame_mask; d.gfeat = a->gfeat; d.spans = a->spans; d.span_conf = a->span_conf;
+  d.target = reinterpret_cast<const long long*>(a->target); d.ts_st = reinterpret_cast<const long long*>(a->ts_st);
+  d.ts_ed = reinterpret_cast<const long long*>(a->ts_ed);
+  d.cls_g = a->cls_ln_g; d.cls_b = a->cls_ln_b; d.cls_w = a->cls_w; d.cls_bias = a->cls_b;
+  d.answer_rows = a->answer_rows; d.row_valid = a->row_valid; d.row_target = reinterpret_cast<long long*>(a->row_target);
+  proposal_cls_kernel<<<2 * a->n, 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+  return check_launch("train_proposals");
 }
 
 int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, int32_t* spans, float* conf, void* stream) {

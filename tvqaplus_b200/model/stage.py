@@ -11,8 +11,9 @@ fourteen kernel launches (csrc/*.cuh):
     encoder (cls, masked max-pool)       max_statement (5N*T, 128)
     span_head                            t_scores, spans, answer        [no device->host sync]
 
-What is not built yet raises ``NotImplementedError`` (never a silent CPU path): train-mode forward (dropout, autograd,
-``get_att_loss``), single-stream models, ``add_non_visual``.
+Train mode runs the same kernels plus the train branch of ``get_proposals`` (N_new >= N rows) as long as ``opt.dropout``
+is 0; there is no backward (the kernels are forward-only).  What is not built raises ``NotImplementedError`` (never a
+silent CPU path): dropout > 0 in train mode, ``add_non_visual``.
 """
 from __future__ import annotations
 
@@ -80,6 +81,7 @@ class STAGE(nn.Module):
         super().__init__()
         self.opt = opt
         self.inference_mode = False
+        self._last_ts_loss = None
         self.error_checks = True  # watch the device error flag (no synchronisation; see _forward_eval)
         self.sub_flag = opt.sub_flag
         self.vfeat_flag = opt.vfeat_flag
@@ -156,10 +158,10 @@ class STAGE(nn.Module):
         """batch: the edict ``prepare_inputs`` builds (tvqa_dataset.py:631-688); see the reference docstring
         (model/stage.py:200-219).  Eval returns ``(out, att_loss, att_predictions, temporal_loss, softmax(t_scores),
         other_outputs)``; ``inference_mode`` returns the prediction dict (model/stage.py:297-312)."""
-        if self.training:
+        if self.training and self.dropout > 0:
             raise NotImplementedError(
-                "tvqaplus_b200: only the eval / inference forward is built (no dropout, autograd or attention loss yet); "
-                "call model.eval()")
+                "tvqaplus_b200: the train-mode forward is built for dropout = 0 only (no dropout RNG; and no backward at all: "
+                "the kernels are forward-only, the outputs carry no autograd graph); call model.eval() or set opt.dropout = 0")
         if self.flag_cnt != 2:
             raise NotImplementedError("tvqaplus_b200: single-stream models (sub-only / vfeat-only) are not built yet")
         with torch.no_grad():
@@ -275,6 +277,9 @@ class STAGE(nn.Module):
             cq["statement"], cq["statement_mask"], batch.target, batch.ts_label, batch.ts_label_mask,
             extra_span_length=self.extra_span_length, _blocked=blocked)
         other_outputs["temporal_scores"] = t_scores
+        if self.training:  # ([out (N_new, 5), target (N_new,)], att_loss, att_predictions, temporal_loss, raw t_scores, ...)
+            att_loss = 0
+            return [out, target], att_loss, None, self._last_ts_loss, t_scores, other_outputs
 
         if self.inference_mode:
             return {"answer": out, "t_scores": t_probs,
@@ -282,7 +287,7 @@ class STAGE(nn.Module):
                         scores=other_outputs["vid_raw_s"], object_vocab=batch.eval_object_word_ids, words=batch.qas,
                         vid_names=batch.vid_name, qids=batch.qid, img_indices=batch.image_indices, boxes=batch.boxes,
                         start_indices=batch.anno_st_idx) if self.vfeat_flag else None}
-        temporal_loss = self.get_ts_loss(t_scores, batch.ts_label, batch.target)
+        temporal_loss = self._last_ts_loss if self._last_ts_loss is not None else self.get_ts_loss(t_scores, batch.ts_label, batch.target)
         return out, 0, None, temporal_loss, t_probs, other_outputs
 
     # ------------------------------------------------------------------------------------------------ heads
@@ -299,9 +304,26 @@ class STAGE(nn.Module):
         else:
             max_statement = self.cls_encoder(statement.view(n_seq, num_words, -1), statement_mask.view(n_seq, num_words),
                                              pool=True)
-        head = ops.span_head_fwd(max_statement.view(bsz * num_a, num_img, -1), statement_mask, ts_labels_mask.float(),
-                                 self._head_weights(), add_local=self.add_local, extra_span_length=extra_span_length)
+        # get_ts_loss (model/stage.py:539-555) rides in the same launch whenever the st/ed labels are there
+        labels = None
+        if isinstance(ts_labels, dict) and targets is not None:
+            labels = (targets, ts_labels["st"], ts_labels["ed"])
+        train = self.training and self.add_local
+        if train and labels is None:
+            raise RuntimeError("tvqaplus_b200: the train-mode proposal pass needs targets and ts_labels = {st, ed}")
+        w = self._head_weights()
+        head = ops.span_head_fwd(max_statement.view(bsz * num_a, num_img, -1), statement_mask, ts_labels_mask.float(), w,
+                                 add_local=self.add_local, extra_span_length=extra_span_length, labels=labels, want_train=train)
         self._last_spans = head["spans"]
+        self._last_ts_loss = head.get("ts_loss")
+        if train:
+            # train branch of get_proposals (model/stage.py:407-438): ground-truth span + predicted span with IoU >= iou_thd
+            # (the kernel implements the reference's defaults max_num_proposal = 1, iou_thd = 0.5)
+            if max_num_proposal != 1 or iou_thd != 0.5:
+                raise NotImplementedError("tvqaplus_b200: train-mode proposals are built for max_num_proposal=1, iou_thd=0.5")
+            prop = ops.train_proposals_fwd(head, labels, w, extra_span_length=extra_span_length, ce_prob_thd=ce_prob_thd)
+            keep = prop["row_valid"].bool()  # N_new is data dependent: this is the one host sync of the train-mode forward
+            return prop["answer_rows"][keep], prop["row_target"][keep], head["t_scores"], head["t_probs"]
         return head["answer"], targets, head["t_scores"], head["t_probs"]
 
     def residual_temporal_predictor(self, layer_idx, input_tensor):

@@ -275,12 +275,14 @@ def cqa_fused_fwd(a_embed, a_mask, sub_embed, sub_mask, vid_embed, vid_mask, w: 
 
 
 @_guarded
-def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local: bool, extra_span_length: int) -> dict:
+def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local: bool, extra_span_length: int,
+                  labels=None, want_train: bool = False) -> dict:
     """Span + answer heads, eval branch (stage_span_head_fwd).
 
     max_statement (N*5, T, 128), statement_mask (N,5,T,Lq), ts_mask (N,T).  ``w``: proj_/st_/ed_/cls_ + ln_g, ln_b, w, b.
     Returns t_scores (N,5,T,2) masked raw logits, t_probs, spans (N*5,2) int32 inclusive, span_conf, answer (N,5),
-    encoded (N,5,T,128)."""
+    encoded (N,5,T,128).  ``labels = (target, ts_st, ts_ed)`` (int64 (N,) each) adds ``ts_loss`` (get_ts_loss fused into the
+    launch); ``want_train`` adds ``frame_mask`` (N*5,T) and ``gfeat`` (N*5,128) for ``train_proposals_fwd``."""
     max_statement, statement_mask, ts_mask = _f32(max_statement), _f32(statement_mask), _f32(ts_mask)
     N, _, T, Lq = statement_mask.shape
     dev = max_statement.device
@@ -290,14 +292,51 @@ def span_head_fwd(max_statement, statement_mask, ts_mask, w: dict, *, add_local:
              span_conf=torch.empty(N * 5, dtype=torch.float32, device=dev),
              answer=torch.empty(N, 5, dtype=torch.float32, device=dev),
              encoded=torch.empty(N, 5, T, HSZ, dtype=torch.float32, device=dev))
+    extra = {}
+    keep_lab = None
+    if labels is not None:
+        keep_lab = [t.to(device=dev, dtype=torch.int64).contiguous() for t in labels]
+        o["ts_terms"] = torch.empty(N, 2, dtype=torch.float32, device=dev)
+        o["ts_loss"] = torch.empty((), dtype=torch.float32, device=dev)
+        extra.update(target=ptr(keep_lab[0]), ts_st=ptr(keep_lab[1]), ts_ed=ptr(keep_lab[2]), ts_terms=ptr(o["ts_terms"]),
+                     ts_loss=ptr(o["ts_loss"]))
+    if want_train:
+        o["frame_mask"] = torch.empty(N * 5, T, dtype=torch.float32, device=dev)
+        o["gfeat"] = torch.empty(N * 5, HSZ, dtype=torch.float32, device=dev)
+        extra.update(frame_mask=ptr(o["frame_mask"]), gfeat=ptr(o["gfeat"]))
     keep = {k: _f32(v) for k, v in w.items()}
     a = _lib.HeadArgs(n=N, t=T, add_local=int(add_local), extra_span_length=int(extra_span_length),
                       max_statement=ptr(max_statement), statement_mask=ptr(statement_mask), lq=Lq, ts_mask=ptr(ts_mask),
                       **{"%s_%s" % (grp, f): ptr(keep["%s_%s" % (grp, f)])
                          for grp in ("proj", "st", "ed", "cls") for f in ("ln_g", "ln_b", "w", "b")},
                       t_scores=ptr(o["t_scores"]), t_probs=ptr(o["t_probs"]), spans=ptr(o["spans"]),
-                      span_conf=ptr(o["span_conf"]), answer=ptr(o["answer"]), workspace=ptr(o["encoded"]))
+                      span_conf=ptr(o["span_conf"]), answer=ptr(o["answer"]), workspace=ptr(o["encoded"]), **extra)
     check(lib().stage_span_head_fwd(C.byref(a), current_stream()), "stage_span_head_fwd")
+    _count(2 if labels is not None else 1)
+    return o
+
+
+@_guarded
+def train_proposals_fwd(head: dict, labels, w: dict, *, extra_span_length: int, ce_prob_thd: float = 0.01) -> dict:
+    """Train branch of get_proposals + classifier (stage_train_proposals_fwd) on the outputs of
+    ``span_head_fwd(..., labels=labels, want_train=True)``.  Returns answer_rows (2N,5), row_valid (2N,) int32, row_target
+    (2N,) int64: candidate row 2i = example i's ground-truth span, 2i+1 = its predicted span if it passed the IoU test."""
+    enc = head["encoded"]
+    N, _, T, _ = enc.shape
+    dev = enc.device
+    lab = [t.to(device=dev, dtype=torch.int64).contiguous() for t in labels]
+    keep = {k: _f32(w[k]) for k in ("cls_ln_g", "cls_ln_b", "cls_w", "cls_b")}
+    if keep["cls_w"].numel() != 2 * HSZ:
+        raise RuntimeError("tvqaplus_b200: the train-mode proposal pass needs the add_local classifier (256 -> 1)")
+    o = dict(answer_rows=torch.empty(2 * N, 5, dtype=torch.float32, device=dev),
+             row_valid=torch.empty(2 * N, dtype=torch.int32, device=dev),
+             row_target=torch.empty(2 * N, dtype=torch.int64, device=dev))
+    a = _lib.ProposalArgs(n=N, t=T, extra_span_length=int(extra_span_length), ce_prob_thd=float(ce_prob_thd),
+                          encoded=ptr(enc), frame_mask=ptr(head["frame_mask"]), gfeat=ptr(head["gfeat"]), spans=ptr(head["spans"]),
+                          span_conf=ptr(head["span_conf"]), target=ptr(lab[0]), ts_st=ptr(lab[1]), ts_ed=ptr(lab[2]),
+                          cls_ln_g=ptr(keep["cls_ln_g"]), cls_ln_b=ptr(keep["cls_ln_b"]), cls_w=ptr(keep["cls_w"]), cls_b=ptr(keep["cls_b"]),
+                          answer_rows=ptr(o["answer_rows"]), row_valid=ptr(o["row_valid"]), row_target=ptr(o["row_target"]))
+    check(lib().stage_train_proposals_fwd(C.byref(a), current_stream()), "stage_train_proposals_fwd")
     _count()
     return o
 
