@@ -264,6 +264,14 @@ int stage_find_max_span(const float* p_st, const float* p_ed, int rows, int t, i
 int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64_t row_stride, int elem_stride,
                         int32_t* spans, double* val, void* stream);
 
+/* ---- attention ranking loss (get_att_loss, model/stage.py:731-746) ---------------------------------------------------
+ * scores = vid_raw_s (N,5,T,Lq,R) of stage_cqa_fused_fwd (masked entries are -1e10); pos_off / neg_off [m] = flat element
+ * offsets into it of the sampled (positive, negative) region pairs (the host builds them from att_labels exactly as
+ * model/stage.py:613-694 does).  loss_type 0 = "lse": sum log1p(exp(alpha*(s_neg - s_pos))); 1 = "hinge": sum
+ * max(0, margin + s_neg - s_pos).  partials: caller-owned scratch of (m + 255) / 256 floats; loss[1]. */
+int stage_att_loss_fwd(const float* scores, const int64_t* pos_off, const int64_t* neg_off, int64_t m, int loss_type,
+                       float alpha, float margin, float* partials, float* loss, void* stream);
+
 /* ---- pad_sequences_2d on the device (collate / prepare_inputs, tvqa_dataset.py:515-553,631-688) -------------------
  * The host uploads only the VALID rows of a ragged feature tensor, concatenated (`rows`, d floats each, d % 4 == 0), plus
  * per-sequence row offsets and lengths; out[n_seq, l_pad, d] gets sequence s's first min(len[s], l_pad) rows and zeros

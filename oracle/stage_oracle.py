@@ -545,3 +545,73 @@ def collate_and_prepare(items, max_len_dict):
                  qid=[d["qid"] for d in items], vid_name=[d["vid_name"] for d in items], att_labels=None, anno_st_idx=[0] * len(items),
                  q_l=[d["q_l"] for d in items], image_indices=[d["image_indices"] for d in items], boxes=None,
                  use_hard_negatives=False, eval_object_word_ids=None)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention ranking loss — model/stage.py:556-746 (use_hard_negatives=False, the only mode the defaults ever reach)
+# ----------------------------------------------------------------------------------------------
+def att_loss_pairs(att_labels, target, start_indices, num_negatives: int = 2):
+    """The (positive, negative) index lists of get_att_loss — model/stage.py:613-694 with sample_negatives' random branch
+    (:603-606).  Rows are (batch, answer, image, word, region); the negatives are drawn with ``torch.randint`` on the global
+    CPU generator, one call per (example, image, word) in loop order, exactly like the reference."""
+    pos_c, neg_c = [], []
+    for b in range(len(target)):
+        ca = int(target[b])
+        gt = att_labels[b]
+        st = start_indices[b]
+        bpos, bneg = [], []
+        for i, lab in enumerate(gt):
+            lab = lab.cpu()
+            p = torch.nonzero(lab)
+            if len(p) == 0:
+                continue
+            bpos.append(torch.cat([p.new_full([len(p), 1], st + i), p], dim=1))
+            q = torch.nonzero(lab == 0)
+            bneg.append(torch.cat([q.new_full([len(q), 1], st + i), q], dim=1))
+        if not bpos:
+            continue
+        bpos, bneg = torch.cat(bpos, 0), torch.cat(bneg, 0)
+        for img in bpos[:, 0].unique().tolist():
+            ip, ineg = bpos[bpos[:, 0] == img], bneg[bneg[:, 0] == img]
+            for w in ip[:, 1].unique().tolist():
+                wp, wn = ip[ip[:, 1] == w], ineg[ineg[:, 1] == w]
+                sp = torch.cat([wp] * num_negatives, dim=0)
+                sn = wn[torch.randint(low=0, high=len(wn), size=(len(sp),), dtype=torch.long)]
+                base = torch.LongTensor([[b, ca]] * len(sp))
+                pos_c.append(torch.cat([base, sp], dim=1))
+                neg_c.append(torch.cat([base, sn], dim=1))
+    return torch.cat(pos_c, 0), torch.cat(neg_c, 0)
+
+
+def get_att_loss(scores, att_labels, target, start_indices, num_negatives=2, att_loss_type="lse", alpha=20.0, margin=0.1):
+    """model/stage.py:731-746 on the pairs above."""
+    pos, neg = att_loss_pairs(att_labels, target, start_indices, num_negatives)
+    ps = scores[pos[:, 0], pos[:, 1], pos[:, 2], pos[:, 3], pos[:, 4]]
+    ns = scores[neg[:, 0], neg[:, 1], neg[:, 2], neg[:, 3], neg[:, 4]]
+    if att_loss_type == "hinge":
+        return torch.clamp(margin + ns - ps, min=0).sum()
+    return torch.log1p(torch.exp(alpha * (ns - ps))).sum()
+
+
+def make_att_labels(batch, n_img_max: int = 4, seed: int = 0):
+    """Synthetic att_labels / anno_st_idx for a synthetic batch: per example a few annotated frames inside the clip, each a
+    (Lq, R_valid) 0/1 matrix with a handful of positives (tvqa_dataset.py builds them from the bounding-box annotations)."""
+    g = torch.Generator().manual_seed(seed)
+    N, _, Lq = batch.qas_mask.shape
+    labels, starts = [], []
+    for b in range(N):
+        n_frames = int(batch.ts_label_mask[b].sum())
+        n_img = int(torch.randint(1, min(n_img_max, n_frames) + 1, (1,), generator=g))
+        st = int(torch.randint(0, n_frames - n_img + 1, (1,), generator=g))
+        q_len = int(batch.qas_mask[b, int(batch.target[b])].sum())
+        cur = []
+        for i in range(n_img):
+            r_valid = max(2, int(batch.vid_mask[b, st + i].sum()))
+            lab = (torch.rand(q_len, r_valid, generator=g) < 0.08).float()
+            if i == 0:
+                lab[0, 0] = 1  # at least one positive per example
+            lab[:, -1] = 0     # and at least one negative per word
+            cur.append(lab)
+        labels.append(cur)
+        starts.append(st)
+    return labels, starts

@@ -86,3 +86,28 @@ def test_synthetic_batch_schema():
     assert torch.all((b.ts_label["st"] <= b.ts_label["ed"]))
     d = O.make_synthetic_batch(2, 4, 3, 5, 6, dense=True)
     assert d.sub_mask.min() == 1 and d.vid_mask.min() == 1 and d.qas_mask.min() == 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference not present on this host")
+@pytest.mark.parametrize("loss_type", ["lse", "hinge"])
+def test_att_loss_restatement_matches_live_reference(loss_type):
+    """get_att_loss / sample_negatives (model/stage.py:556-746): the oracle's restatement against the unmodified reference
+    method, same labels and the same host RNG seed -> bit-identical loss."""
+    import contextlib
+    import io
+    from oracle.make_golden import load_reference
+    ref_stage = load_reference()
+    opt = O.default_opt(att_loss_type=loss_type)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_stage.STAGE(opt)
+    ref.train()
+    batch = O.make_synthetic_batch(3, 12, 9, 10, 8, seed=4)
+    labels, starts = O.make_att_labels(batch, seed=1)
+    scores = torch.rand(3, 5, 12, 10, 9, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    scores[:, :, :, :, -1] = -1e10
+    torch.manual_seed(7)
+    want, _ = ref.get_att_loss(scores, labels, batch.target, batch.qas, batch.vid_name, batch.qid, batch.q_l, None, None, starts,
+                               num_negatives=2)
+    torch.manual_seed(7)
+    got = O.get_att_loss(scores, labels, batch.target, starts, 2, loss_type, opt.alpha, opt.margin)
+    assert torch.equal(want, got)

@@ -384,6 +384,33 @@ __global__ void find_max_pair_kernel(const float* __restrict__ p1, const float* 
   val[r] = best;
 }
 
+// Attention ranking loss (get_att_loss, stage.py:731-746): for every sampled (positive, negative) pair of region scores
+//   lse:   log1p(exp(alpha * (s_neg - s_pos)))          hinge:   max(0, margin + s_neg - s_pos)
+// summed over the pairs.  The pair lists are built once on the host from att_labels (they depend on the labels and the
+// host RNG only, not on any device value); here: gather, loss, block sums; a second one-thread pass adds the block sums in
+// order so that the result does not depend on the launch's timing.
+__global__ void __launch_bounds__(256) att_loss_kernel(const float* __restrict__ scores, const long long* __restrict__ pos_off,
+                                                       const long long* __restrict__ neg_off, long long m, int hinge, float alpha,
+                                                       float margin, float* __restrict__ partials) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + tid;
+  float v = 0.f;
+  if (i < m) {
+    const float d = __ldg(scores + __ldg(neg_off + i)) - __ldg(scores + __ldg(pos_off + i));
+    v = hinge ? fmaxf(margin + d, 0.f) : log1pf(expf(alpha * d));
+  }
+  const float tot = block_reduce(v, false, red, tid);
+  if (tid == 0) partials[blockIdx.x] = tot;
+}
+__global__ void sum_in_order_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += partials[i];
+    *out = s;
+  }
+}
+
 // pad_sequences_2d on the device (tvqa_dataset.py:515-553): the valid rows of all sequences arrive concatenated
 // (`rows`, D floats each, sequence s at row offset off[s]); sequence s becomes rows [s*l_pad, (s+1)*l_pad) of `out`, its
 // first min(len[s], l_pad) rows copied, the rest zero-filled, and mask[s, j] = j < len[s].  One warp per output row.

@@ -389,6 +389,19 @@ int stage_find_max_pair(const float* p1, const float* p2, int rows, int t, int64
   return check_launch("find_max_pair");
 }
 
+int stage_att_loss_fwd(const float* scores, const int64_t* pos_off, const int64_t* neg_off, int64_t m, int loss_type,
+                       float alpha, float margin, float* partials, float* loss, void* stream) {
+  STG_REQUIRE(scores && pos_off && neg_off && partials && loss, STAGE_E_BADARG, "att_loss: null pointer");
+  STG_REQUIRE(m > 0 && m < (1ll << 31) * 256, STAGE_E_BADARG, "att_loss: m=%lld", (long long)m);
+  STG_REQUIRE(loss_type == 0 || loss_type == 1, STAGE_E_UNSUPPORTED, "att_loss: loss_type=%d (0 = lse, 1 = hinge)", loss_type);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = static_cast<int>((m + 255) / 256);
+  att_loss_kernel<<<blocks, 256, 0, s>>>(scores, reinterpret_cast<const long long*>(pos_off), reinterpret_cast<const long long*>(neg_off),
+                                        m, loss_type, alpha, margin, partials);
+  sum_in_order_kernel<<<1, 32, 0, s>>>(partials, blocks, loss);
+  return check_launch("att_loss");
+}
+
 int stage_pad_rows(const float* rows, const int64_t* off, const int32_t* len, int64_t n_seq, int l_pad, int d, float* out,
                    float* mask, void* stream) {
   STG_REQUIRE(off && len && out && mask, STAGE_E_BADARG, "pad_rows: null pointer");

@@ -267,7 +267,7 @@ class STAGE(nn.Module):
         vid_embed = self.base_encoder(batch.vid.view(bsz * T, R, -1), vid_mask.view(bsz * T, R),
                                       self._vid_fc, None, self.input_encoder).view(bsz, T, R, hsz)
 
-        need_raw = self.inference_mode
+        need_raw = self.inference_mode or (self.training and self.use_sup_att)  # vid_raw_s feeds get_att_prediction / get_att_loss
         blocked = ops.blocked_fits(Lq)  # the statement goes to the cls encoder in the blocked tile layout (never seen outside)
         cq = ops.cqa_fused_fwd(a_embed, qas_mask.view(bsz, num_a, Lq), sub_embed, sub_mask, vid_embed, vid_mask,
                                self._cqa_weights(), self.scale, want=("vid_raw_s",) if need_raw else (), blocked=blocked,
@@ -278,8 +278,14 @@ class STAGE(nn.Module):
             extra_span_length=self.extra_span_length, _blocked=blocked)
         other_outputs["temporal_scores"] = t_scores
         if self.training:  # ([out (N_new, 5), target (N_new,)], att_loss, att_predictions, temporal_loss, raw t_scores, ...)
-            att_loss = 0
-            return [out, target], att_loss, None, self._last_ts_loss, t_scores, other_outputs
+            att_loss, att_predictions = 0, None
+            if self.use_sup_att and self.vfeat_flag:  # model/stage.py:317-341
+                cur_loss, att_predictions = self.get_att_loss(
+                    other_outputs["vid_raw_s"], batch.att_labels, batch.target, batch.qas, qids=batch.qid, q_lens=batch.q_l,
+                    vid_names=batch.vid_name, img_indices=batch.image_indices, boxes=batch.boxes, start_indices=batch.anno_st_idx,
+                    num_negatives=self.num_negatives, use_hard_negatives=batch.use_hard_negatives, drop_topk=self.drop_topk)
+                att_loss = att_loss + cur_loss
+            return [out, target], att_loss, att_predictions, self._last_ts_loss, t_scores, other_outputs
 
         if self.inference_mode:
             return {"answer": out, "t_scores": t_probs,
@@ -354,6 +360,80 @@ class STAGE(nn.Module):
         st = F.cross_entropy(ca[:, :, 0], ts_labels["st"].to(ca.device), reduction="sum")
         ed = F.cross_entropy(ca[:, :, 1], ts_labels["ed"].to(ca.device), reduction="sum")
         return (st + ed) / 2.0
+
+    # ------------------------------------------------------------------------------------------------ attention ranking loss
+    @classmethod
+    def sample_negatives(cls, pred_score, pos_indices, neg_indices, num_negatives=2, use_hard_negatives=False,
+                         negative_pool_size=0, num_hard=2, drop_topk=0):
+        """Random negatives for the positives of one (image, word) pair (model/stage.py:556-607, the branch the reference's
+        defaults always take: ``hard_negative_start`` equals ``n_epoch``, config.py:25,77).  Index tensors live on the host;
+        the draw is ``torch.randint`` on the global CPU generator, like the reference's."""
+        if use_hard_negatives:
+            raise NotImplementedError("tvqaplus_b200: hard-negative sampling is not built (never active with the reference's "
+                                      "defaults, and its top-k branch crashes in the reference when a word has few negatives)")
+        sampled_pos = torch.cat([pos_indices] * num_negatives, dim=0)
+        sampled_neg = neg_indices[torch.randint(low=0, high=len(neg_indices), size=(len(sampled_pos),), dtype=torch.long)]
+        return sampled_pos, sampled_neg
+
+    def _att_pairs(self, att_labels, target, start_indices, num_negatives, use_hard_negatives, drop_topk):
+        """(batch, answer, image, word, region) rows of every sampled positive / negative — the index bookkeeping of
+        model/stage.py:613-694, on the host (it depends on the labels and the host RNG only)."""
+        tgt = target.tolist() if torch.is_tensor(target) else list(target)
+        pos_c, neg_c = [], []
+        for b in range(len(tgt)):
+            ca, st = int(tgt[b]), start_indices[b]
+            bpos, bneg = [], []
+            for i, lab in enumerate(att_labels[b]):
+                lab = lab.cpu()
+                p = torch.nonzero(lab)
+                if len(p) == 0:
+                    continue
+                bpos.append(torch.cat([p.new_full([len(p), 1], st + i), p], dim=1))
+                q = torch.nonzero(lab == 0)
+                bneg.append(torch.cat([q.new_full([len(q), 1], st + i), q], dim=1))
+            if not bpos:
+                continue
+            bpos, bneg = torch.cat(bpos, 0), torch.cat(bneg, 0)
+            for img in bpos[:, 0].unique().tolist():
+                ip, ineg = bpos[bpos[:, 0] == img], bneg[bneg[:, 0] == img]
+                for wd in ip[:, 1].unique().tolist():
+                    sp, sn = self.sample_negatives(None, ip[ip[:, 1] == wd], ineg[ineg[:, 1] == wd], num_negatives=num_negatives,
+                                                   use_hard_negatives=use_hard_negatives, negative_pool_size=self.negative_pool_size,
+                                                   num_hard=self.num_hard, drop_topk=drop_topk)
+                    base = torch.LongTensor([[b, ca]] * len(sp))
+                    pos_c.append(torch.cat([base, sp], dim=1))
+                    neg_c.append(torch.cat([base, sn], dim=1))
+        if not pos_c:  # the reference's torch.cat of an empty list raises here as well
+            raise RuntimeError("get_att_loss: no positive attention label in the batch")
+        return torch.cat(pos_c, 0), torch.cat(neg_c, 0)
+
+    def get_att_loss(self, scores, att_labels, target, words, vid_names, qids, q_lens, img_indices, boxes, start_indices,
+                     num_negatives=2, use_hard_negatives=False, drop_topk=0):
+        """Ranking loss between labelled and sampled unlabelled regions of the ground-truth answer's words
+        (model/stage.py:609-746).  ``scores`` = vid_raw_s (N, 5, Li, Lqa, Lr) on the device.  The pair lists are built on the
+        host, the gather + loss + sum is one kernel pair (stage_att_loss_fwd): no per-element ``.item()`` round trips.
+        Returns ``(att_loss, att_predictions)``; ``att_predictions`` (eval mode only) as the reference builds it."""
+        pos, neg = self._att_pairs(att_labels, target, start_indices, num_negatives, use_hard_negatives, drop_topk)
+        strides = torch.tensor(scores.stride(), dtype=torch.long)
+        if not scores.is_contiguous():
+            raise RuntimeError("tvqaplus_b200: scores must be contiguous")
+        att_loss = ops.att_loss_fwd(scores, (pos * strides).sum(1).to(scores.device), (neg * strides).sum(1).to(scores.device),
+                                    loss_type=self.att_loss_type, alpha=self.alpha, margin=self.margin)
+        att_predictions = None
+        if not self.training and self.vfeat_flag:
+            att_predictions = dict(det_q=[], det_ca=[])
+            uniq = np.unique(pos.numpy(), axis=0)
+            rows = scores[uniq[:, 0], uniq[:, 1], uniq[:, 2], uniq[:, 3]].cpu()  # ONE gather + device->host copy
+            for row, sc in zip(uniq, rows):
+                b, ca, img, wd, _ = [int(v) for v in row]
+                st = start_indices[b]
+                n_reg = att_labels[b][img - st].shape[1]
+                if boxes is not None and n_reg != len(boxes[b][img - st]):
+                    raise AssertionError("scores / boxes length mismatch for %s" % (row,))
+                det = {"pred": sc[:n_reg].clone(), "word": words[b, ca, wd], "qid": qids[b], "vid_name": vid_names[b],
+                       "img_idx": img_indices[b][img], "boxes": boxes[b][img - st] if boxes is not None else None}
+                (att_predictions["det_q"] if wd < q_lens[b] else att_predictions["det_ca"]).append(det)
+        return att_loss, att_predictions
 
     # ------------------------------------------------------------------------------------------------ inference post-processing
     def get_att_prediction(self, scores, object_vocab, words, vid_names, qids, img_indices, boxes, start_indices,

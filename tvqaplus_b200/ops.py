@@ -371,6 +371,26 @@ def find_max_pairs(probs: torch.Tensor):
 
 
 @_guarded
+def att_loss_fwd(scores: torch.Tensor, pos_off: torch.Tensor, neg_off: torch.Tensor, *, loss_type: str, alpha: float,
+                 margin: float) -> torch.Tensor:
+    """Attention ranking loss over sampled (positive, negative) pairs (stage_att_loss_fwd): ``scores`` = vid_raw_s,
+    ``pos_off`` / ``neg_off`` int64 flat offsets into it.  Returns a 0-d tensor."""
+    scores = _f32(scores)
+    if loss_type not in ("lse", "hinge"):
+        raise NotImplementedError("Only support hinge and lse")
+    m = pos_off.numel()
+    dev = scores.device
+    pos_off = pos_off.to(device=dev, dtype=torch.int64).contiguous()
+    neg_off = neg_off.to(device=dev, dtype=torch.int64).contiguous()
+    partials = torch.empty((m + 255) // 256, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    check(lib().stage_att_loss_fwd(ptr(scores), ptr(pos_off), ptr(neg_off), m, 0 if loss_type == "lse" else 1, float(alpha),
+                                   float(margin), ptr(partials), ptr(loss), current_stream()), "stage_att_loss_fwd")
+    _count(2)
+    return loss
+
+
+@_guarded
 def pad_rows(rows: torch.Tensor, off: torch.Tensor, lens: torch.Tensor, l_pad: int):
     """``pad_sequences_2d`` on the device (stage_pad_rows): ``rows`` (R, D) = the valid rows of all sequences concatenated,
     ``off`` (n_seq,) int64 row offsets, ``lens`` (n_seq,) int32 -> (out (n_seq, l_pad, D) zero-padded, mask (n_seq, l_pad))."""
