@@ -251,3 +251,13 @@ def test_device_error_monitor_is_silent_on_clean_runs():
     model(H.batch_to(batch, torch.device("cuda:0")))  # polls the flag posted by the previous call
     model.check_device_errors()
     assert model._err_monitor.event is not None and int(model._err_monitor.flag.item()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub_flag,vfeat_flag", [(True, False), (False, True)])
+def test_single_stream_models(sub_flag, vfeat_flag):
+    """sub-only / vfeat-only models (model/stage.py:283-290): statement = that stream's mixed tensor, mask = its own."""
+    opt, model = _model(sub_flag=sub_flag, vfeat_flag=vfeat_flag)
+    assert ("vid_fc.0.weight" in model.state_dict()) == vfeat_flag and "concat_fc.0.weight" not in model.state_dict()
+    batch = O.make_synthetic_batch(2, 14, 12, 20, 24, seed=23)
+    _check(model, opt, batch, "single stream sub=%s vfeat=%s" % (sub_flag, vfeat_flag))

@@ -162,8 +162,8 @@ class STAGE(nn.Module):
             raise NotImplementedError(
                 "tvqaplus_b200: the train-mode forward is built for dropout = 0 only (no dropout RNG; and no backward at all: "
                 "the kernels are forward-only, the outputs carry no autograd graph); call model.eval() or set opt.dropout = 0")
-        if self.flag_cnt != 2:
-            raise NotImplementedError("tvqaplus_b200: single-stream models (sub-only / vfeat-only) are not built yet")
+        if self.flag_cnt == 0:
+            raise NotImplementedError  # model/stage.py:291-292
         with torch.no_grad():
             return self._forward_eval(batch)
 
@@ -251,6 +251,8 @@ class STAGE(nn.Module):
         Lq = a_embed.shape[1]
         a_embed = a_embed.view(bsz, num_a, Lq, hsz)
 
+        if self.flag_cnt == 1:
+            return self._forward_single_stream(batch, a_embed, qas_mask)
         T, Ls = batch.sub_bert.shape[1:3]
         sub_mask = batch.sub_mask.float()
         # the sub-title encoder writes its output straight into the operand images of the fused CQA kernel's workspace
@@ -277,6 +279,10 @@ class STAGE(nn.Module):
             cq["statement"], cq["statement_mask"], batch.target, batch.ts_label, batch.ts_label_mask,
             extra_span_length=self.extra_span_length, _blocked=blocked)
         other_outputs["temporal_scores"] = t_scores
+        return self._finish(batch, out, target, t_scores, t_probs, other_outputs)
+
+    def _finish(self, batch, out, target, t_scores, t_probs, other_outputs):
+        """Return conventions of forward_main (model/stage.py:297-348)."""
         if self.training:  # ([out (N_new, 5), target (N_new,)], att_loss, att_predictions, temporal_loss, raw t_scores, ...)
             att_loss, att_predictions = 0, None
             if self.use_sup_att and self.vfeat_flag:  # model/stage.py:317-341
@@ -286,7 +292,6 @@ class STAGE(nn.Module):
                     num_negatives=self.num_negatives, use_hard_negatives=batch.use_hard_negatives, drop_topk=self.drop_topk)
                 att_loss = att_loss + cur_loss
             return [out, target], att_loss, att_predictions, self._last_ts_loss, t_scores, other_outputs
-
         if self.inference_mode:
             return {"answer": out, "t_scores": t_probs,
                     "att_predictions": self.get_att_prediction(
@@ -295,6 +300,27 @@ class STAGE(nn.Module):
                         start_indices=batch.anno_st_idx) if self.vfeat_flag else None}
         temporal_loss = self._last_ts_loss if self._last_ts_loss is not None else self.get_ts_loss(t_scores, batch.ts_label, batch.target)
         return out, 0, None, temporal_loss, t_probs, other_outputs
+
+    def _forward_single_stream(self, batch, a_embed, qas_mask):
+        """sub-only / vfeat-only models (model/stage.py:283-290): the statement is that stream's mixed tensor, its mask the
+        stream's own.  Not a hot path (``run_main.sh`` always uses both streams): it runs through the module-level kernels
+        (attention-only CQA launch + the 384 -> 128 projection), which materialise the (N,5,T,Lq,384) concatenation."""
+        bsz, num_a, hsz = self.bsz, self.num_a, self.hsz
+        Lq = a_embed.shape[2]
+        if self.sub_flag:
+            raw, mask, fc = batch.sub_bert, batch.sub_mask.float(), self._text_fc
+        else:
+            raw, mask, fc = batch.vid, batch.vid_mask.float(), self._vid_fc
+        T, Lc = raw.shape[1:3]
+        ctx = self.base_encoder(raw.view(bsz * T, Lc, -1), mask.view(bsz * T, Lc), fc, None, self.input_encoder).view(bsz, 1, T, Lc, hsz)
+        statement, statement_mask, raw_s, _ = self.qa_ctx_attention(
+            a_embed.view(bsz, num_a, 1, Lq, hsz), ctx, qas_mask.view(bsz, num_a, 1, Lq), mask.view(bsz, 1, T, Lc), None, None)
+        other_outputs = {"vid_raw_s": raw_s if self.vfeat_flag else None}
+        out, target, t_scores, t_probs = self.classfier_head_multi_proposal(
+            statement, statement_mask.contiguous(), batch.target, batch.ts_label, batch.ts_label_mask,
+            extra_span_length=self.extra_span_length)
+        other_outputs["temporal_scores"] = t_scores
+        return self._finish(batch, out, target, t_scores, t_probs, other_outputs)
 
     # ------------------------------------------------------------------------------------------------ heads
     def classfier_head_multi_proposal(self, statement, statement_mask, targets, ts_labels, ts_labels_mask,
