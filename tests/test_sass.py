@@ -57,8 +57,8 @@ def test_hot_kernels_use_tcgen05_and_bulk_copies(sass):
 
 def test_mma_warps_issue_from_converged_code(sass):
     """Under a `lane == 0` branch the compiler wraps every tcgen05 instruction in a waterfall loop (BRA.U.ANY): the
-    linear / encoder / CQA kernels must have (almost) none, certainly fewer than one per MMA."""
-    for key in ("linear_kernel", "encoder_kernel", "cqa_kernel"):
+    linear / encoder / CQA / MHA kernels must have (almost) none, certainly fewer than one per MMA."""
+    for key in ("linear_kernel", "encoder_kernel", "cqa_kernel", "mha_kernel"):
         for name, c in kernels(sass, key).items():
             assert c["waterfall"] <= 4, "%s: %d waterfall loops for %d MMAs" % (name, c["waterfall"], c["mma"])
 

@@ -14,7 +14,8 @@
 //        R1: xn image -> Q image -> P_h image -> O image        (A operands, thread/warp-per-row layout)
 //        R2: Wq -> Wv -> K image -> Wo                          (B operands)
 //        R3: Wk -> V image (read MN-major for P.V) -> fp32 staging for the max-pool
-// 256 threads; thread 0 issues every MMA and bulk copy, epilogues are thread = (row, column half).
+// 256 threads; warp 0 runs the issue control flow and elects the lane that issues every MMA and bulk copy, epilogues are
+// thread = (row, column half).
 //
 // Algorithmic work per token: 4*2*128*128 + 4*128*L FLOP.
 #pragma once
@@ -170,24 +171,30 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
     fence_async_smem();
     __syncthreads();
 
-    // ---- phase 1: Q -> T0, K -> T1, V -> T2   (w2_cnt / w3_cnt / q_cnt are private to thread 0)
-    if (tid == 0) {
+    // ---- phase 1: Q -> T0, K -> T1, V -> T2   (w2_cnt / w3_cnt / q_cnt are tracked by warp 0 only)
+    if (warp == 0) {  // the whole warp runs the waits, one elected lane issues (no lane-by-lane waterfall around the MMAs)
       tc_fence_after();
       mbar_wait(&w2_bar, w2_cnt & 1u, 60);
       ++w2_cnt;
-      issue_weight_gemm(T0, r1, r2);
-      umma_commit(&q_bar);
+      if (elect_one()) {
+        issue_weight_gemm(T0, r1, r2);
+        umma_commit(&q_bar);
+      }
       mbar_wait(&w3_bar, w3_cnt & 1u, 61);
       ++w3_cnt;
-      issue_weight_gemm(T1, r1, r3);
+      if (elect_one()) issue_weight_gemm(T1, r1, r3);
       mbar_wait(&q_bar, q_cnt & 1u, 62);  // Q done: Wq may be replaced by Wv
       ++q_cnt;
-      mbar_arrive_expect_tx(&w2_bar, MhaCfg::W_BYTES);
-      bulk_g2s(R2, p.w[2], MhaCfg::W_BYTES, &w2_bar);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w2_bar, MhaCfg::W_BYTES);
+        bulk_g2s(R2, p.w[2], MhaCfg::W_BYTES, &w2_bar);
+      }
       mbar_wait(&w2_bar, w2_cnt & 1u, 63);
       ++w2_cnt;
-      issue_weight_gemm(T2, r1, r2);
-      umma_commit(&mma_bar);
+      if (elect_one()) {
+        issue_weight_gemm(T2, r1, r2);
+        umma_commit(&mma_bar);
+      }
     }
     mbar_wait(&mma_bar, mma_cnt & 1u, 64);  // all three projections complete
     ++mma_cnt;
@@ -202,8 +209,9 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
     __syncthreads();
 
     // ---- phase 3: S_h = Q_h K_h^T for every head -> T_h
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
       for (int h = 0; h < nh; ++h) {
         for (int ks = 0; ks < dk / 16; ++ks) {
           const uint32_t off = (h * (dk / 8) + ks * 2) * MhaCfg::LBO;
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
         }
       }
       umma_commit(&mma_bar);
+      }
     }
     mbar_wait(&mma_bar, mma_cnt & 1u, 65);
     ++mma_cnt;
@@ -274,8 +283,9 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
       fence_async_smem();
       tc_fence_before();
       __syncthreads();  // P_h complete, S_h consumed by every thread
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
+        if (elect_one()) {
         // V image read MN-major: N = the dk channels of head h (8-channel groups are LBO apart), K = key rows (16 rows = 256 B)
         const uint32_t vh = r3 + h * (dk / 8) * MhaCfg::LBO;
 #pragma unroll
@@ -287,6 +297,7 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
           umma_split3(T0 + h * dk, a_hi, a_lo, b_hi, b_lo, idesc_pv, ks > 0 ? 1u : 0u);
         }
         umma_commit(&mma_bar);
+        }
       }
       mbar_wait(&mma_bar, mma_cnt & 1u, 66);  // P buffer is reused by the next head
       ++mma_cnt;
@@ -298,12 +309,14 @@ __global__ void __launch_bounds__(256, 1) mha_kernel(MhaDev p) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       mbar_wait(&w2_bar, w2_cnt & 1u, 67);
       ++w2_cnt;
-      issue_weight_gemm(T1, r1, r2);
-      umma_commit(&mma_bar);
+      if (elect_one()) {
+        issue_weight_gemm(T1, r1, r2);
+        umma_commit(&mma_bar);
+      }
     }
     mbar_wait(&mma_bar, mma_cnt & 1u, 68);
     ++mma_cnt;
