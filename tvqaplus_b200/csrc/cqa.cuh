@@ -66,6 +66,7 @@ struct CqaCfg {
   static constexpr uint32_t AST_BYTES = 2u * AST_PART;       // 33024: hi | lo
   static constexpr uint32_t W_SLOT = 2u * 4u * 2048u;        // 16384: one kc=32 weight chunk (hi | lo)
   static constexpr int W_SLOTS = 4;
+  static constexpr int AQ_W_SLOTS = 4;  // four more weight slots inside the AQ region between the last a*U stage and the next answer image
   // per-frame ctx blob (global and shared layout are identical)
   static constexpr uint32_t CTX_CS = 0;                                  // sub image hi | lo
   static constexpr uint32_t CTX_CS_INV = 2u * CS_PART;                   // 57856: inv norms [112]
@@ -89,7 +90,14 @@ struct CqaCfg {
   static_assert(2u * AST_BYTES <= AQ_BYTES, "the two A stages overlay the answer image");
   static_assert(2u * PV_PART <= AQ_BYTES && 2u * PS_PART <= B_BYTES, "P images overlay AQ / the weight ring");
   static_assert(CTX_BYTES % 16 == 0 && ABLOB_BYTES % 16 == 0 && CTX_CV % 16 == 0, "bulk copies / descriptors need 16 B");
-  static_assert(CHUNKS % W_SLOTS == 0, "a tile's local chunk j must always sit in ring slot j % W_SLOTS");
+  static_assert(CHUNKS == 20 && W_SLOTS == 4 && AQ_W_SLOTS == 4, "the slot schedule below is written for 8 + 12 chunks, 4 + 4 slots");
+  static_assert(AQ_W_SLOTS * W_SLOT <= AQ_BYTES, "the extra weight slots live inside the AQ region");
+  // Slot schedule of a tile's 20 weight chunks: c2q chunks 0..7 and concat chunks 8..11, 16..19 go through the 4-slot ring
+  // in region B (slot j % 4: four uses per slot and tile); concat chunks 12..15 (segment mv) sit in the AQ region, which is
+  // idle between the last a*U stage (D3) and the next answer image.  All eight concat chunks of segments ms / mv are thus
+  // requested at D3, while the compute warps are still producing the first concat operand.
+  __host__ __device__ static constexpr bool w_in_aq(int j) { return j >= 12 && j < 16; }
+  __host__ __device__ static constexpr int w_use(int j) { return j < 4 ? 0 : (j < 8 ? 1 : (j < 12 ? 2 : 3)); }
 };
 
 struct CqaDev {
@@ -233,9 +241,10 @@ template <bool TIMELINE>
 __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Completion events of a tile, each with its OWN barrier (a thread that wakes up late from a suspended wait must never
-  // find its barrier two phases further on): D1 S, D2 U, D3a c2q(sub), D3b c2q(vid), D4 concat.
+  // find its barrier two phases further on): mma_done[0] D1 S, [1] D2v U_vid, [2] D3 c2q, [3] D2s U_sub, [4] D4 concat.
   __shared__ uint64_t op_ready, mma_done[5], ctx_full, aq_full, ctx_free, aq_free, b_free, a_full[2], a_empty[2],
-      useg_full[2], cat_full[3], ep_ready, t2_free, w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS];
+      useg_full[2], cat_full[3], ep_ready, t2_free, w_full[CqaCfg::W_SLOTS], w_empty[CqaCfg::W_SLOTS],
+      wq_full[CqaCfg::AQ_W_SLOTS], aq_w_free;
   __shared__ uint32_t tmem_slot;
   __shared__ float xq[4][4][128];  // cross-quarter exchange: [quantity][quarter][row]
   __shared__ float2 ep_stat[128];  // (rstd, -rstd*mean) of the concat LayerNorm(384) row, compute -> epilogue warps
@@ -273,6 +282,8 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
+    for (int i = 0; i < CqaCfg::AQ_W_SLOTS; ++i) mbar_init(&wq_full[i], 1);
+    mbar_init(&aq_w_free, 1);
     mbar_fence_init();
   }
   for (int i = tid; i < 128; i += CqaCfg::THREADS) {  // per-column vectors of the folded GEMM epilogues
@@ -489,7 +500,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
             const float4 v = live ? __ldg(zsrc + j * (5 * p.lq)) : make_float4(0.f, 0.f, 0.f, 0.f);
             za[j * 4] = v.x; za[j * 4 + 1] = v.y; za[j * 4 + 2] = v.z; za[j * 4 + 3] = v.w;
           }
-          mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2: U ready
+          mbar_wait(&mma_done[1], done_cnt & 1u, 32);  // D2v: U_vid ready (issued first: its 6 MMAs hide under nothing else)
           tc_fence_after();
           CQA_STAMP(tl_ph, 5);
           tmem_st16(T0 + coff, za);
@@ -521,10 +532,17 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         // Both streams are produced side by side, half by half, because the c2q weights are the same for both: every weight
         // chunk that lands in the ring is used twice (sub, then vid).  Stage g of the shared-memory ring belongs to stream g.
         float2 s1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        // The vid stream goes first in every half: U_vid (6 MMAs) completes ~1.4 k cycles before U_sub (21 MMAs), so its
+        // first operands are produced while the tensor pipe still works on U_sub.
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int gi = 0; gi < 2; ++gi) {
+            const int g = 1 - gi;
+            if (h == 0 && g == 0) {
+              mbar_wait(&mma_done[3], done_cnt & 1u, 32);  // D2s: U_sub ready
+              tc_fence_after();
+            }
             const uint32_t tU = (g == 0 ? T2 : T3) + coff;
             float* att = g == 0 ? p.att_sub : p.att_vid;
             const float2 isum2 = dup2(g == 0 ? is : iv);
@@ -735,6 +753,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
       const uint64_t dA = make_smem_desc(smem_u32(sAQ), CqaCfg::LBO_A, 128);    // answer image / P_vid / a*U stages (K-major, 128 rows)
       const uint64_t dP = make_smem_desc(smem_u32(sB), CqaCfg::LBO_A, 128);     // P_sub
       const uint64_t dW = make_smem_desc(smem_u32(sB), 2048, 128);              // weight ring (K-major, 128 rows)
+      const uint64_t dAW = make_smem_desc(smem_u32(sAQ), 2048, 128);            // the four extra weight slots in the AQ region
       const uint64_t dCS = make_smem_desc(smem_u32(sCS), CqaCfg::LBO_CS, 128);  // sub-title tile, K-major (S)
       const uint64_t dCV = make_smem_desc(smem_u32(sCV), CqaCfg::LBO_CV, 128);  // region tile, K-major (S)
       const uint64_t dCSt = make_smem_desc(smem_u32(sCS), 128, CqaCfg::LBO_CS); // sub-title tile, MN-major (U)
@@ -759,30 +778,39 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
       if (my_tiles > 0) issue_s(0);
       for (int k = 0; k < my_tiles; ++k) {
         const int a_i = k % p.n_pt;
-        const uint32_t wuse = static_cast<uint32_t>(k) * (CqaCfg::CHUNKS / CqaCfg::W_SLOTS);  // uses of every ring slot before this tile
-        // local chunk j of this tile sits in slot j % 4; it is that slot's (wuse + j / 4)-th use
-#define W_WAIT(j) CQA_TIMED(w_wait, mbar_wait(&w_full[(j) % CqaCfg::W_SLOTS], (wuse + (j) / CqaCfg::W_SLOTS) & 1u, 46))
-#define W_DESC(j, off) DOFF(dW, ((j) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT + (off))
+        const uint32_t wuse = static_cast<uint32_t>(k) * 4u;  // uses of every region-B ring slot before this tile
+        // local chunk j: region-B slot j % 4 (its (wuse + w_use(j))-th use) or, for j = 12..15, AQ slot j - 12 (once per tile)
+#define W_WAIT(j)                                                                                                       \
+  CQA_TIMED(w_wait, (CqaCfg::w_in_aq(j) ? mbar_wait(&wq_full[((j) - 12) & 3], k & 1u, 46)                                \
+                                        : mbar_wait(&w_full[(j) % CqaCfg::W_SLOTS], (wuse + CqaCfg::w_use(j)) & 1u, 46)))
+#define W_DESC(j, off) \
+  (CqaCfg::w_in_aq(j) ? DOFF(dAW, (((j) - 12) & 3) * CqaCfg::W_SLOT + (off)) : DOFF(dW, ((j) % CqaCfg::W_SLOTS) * CqaCfg::W_SLOT + (off)))
         CQA_STAMP(1, 0);
         // ---- U = P' . ctx  (ctx image read MN-major: LBO = 128 between 8-row k groups, SBO = image LBO between n groups).
         //      (Issuing the K=16 steps one by one while the softmax is still producing later chunks was measured and lost:
         //      the per-chunk fences and arrivals cost the compute warps more than the overlap returned.)
         mbar_wait(&op_ready, k & 1u, 42);  // E2
-        if (k > 0) CQA_TIMED(o_wait, mbar_wait(&t2_free, (k - 1) & 1u, 43));  // the epilogue warps have read the previous concat accumulator
         tc_fence_after();
         CQA_STAMP(1, 1);
+        if (elect_one()) {  // U_vid first (T3: the previous tile's product operand there is dead, its MMAs were issued earlier)
+#pragma unroll
+          for (uint32_t ks = 0; ks < CqaCfg::R_MAX / 16; ++ks)
+            if (static_cast<int>(ks * 16) < p.r_pad)
+              umma_split3(T3, DOFF(dA, ks * 2 * CqaCfg::LBO_A), DOFF(dA, CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A),
+                          DOFF(dCVt, ks * 256), DOFF(dCVt, CqaCfg::CV_PART + ks * 256), id_u, ks > 0 ? 1u : 0u);
+          umma_commit(&mma_done[1]);  // D2v
+        }
+        if (k > 0) {
+          CQA_TIMED(o_wait, mbar_wait(&t2_free, (k - 1) & 1u, 43));  // the epilogue warps have read the previous concat accumulator (T2)
+          tc_fence_after();
+        }
         if (elect_one()) {
 #pragma unroll
           for (uint32_t ks = 0; ks < CqaCfg::LS_MAX / 16; ++ks)
             if (static_cast<int>(ks * 16) < p.ls_pad)
               umma_split3(T2, DOFF(dP, ks * 2 * CqaCfg::LBO_A), DOFF(dP, CqaCfg::PS_PART + ks * 2 * CqaCfg::LBO_A),
                           DOFF(dCSt, ks * 256), DOFF(dCSt, CqaCfg::CS_PART + ks * 256), id_u, ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (uint32_t ks = 0; ks < CqaCfg::R_MAX / 16; ++ks)
-            if (static_cast<int>(ks * 16) < p.r_pad)
-              umma_split3(T3, DOFF(dA, ks * 2 * CqaCfg::LBO_A), DOFF(dA, CqaCfg::PV_PART + ks * 2 * CqaCfg::LBO_A),
-                          DOFF(dCVt, ks * 256), DOFF(dCVt, CqaCfg::CV_PART + ks * 256), id_u, ks > 0 ? 1u : 0u);
-          umma_commit(&mma_done[1]);  // D2
+          umma_commit(&mma_done[3]);  // D2s
           umma_commit(&b_free);       // P_sub (region B) may now become the weight ring
           if (a_i == p.n_pt - 1) umma_commit(&ctx_free);  // last use of this frame's ctx tiles
         }
@@ -793,14 +821,15 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
 #pragma unroll
         for (uint32_t h = 0; h < 2; ++h) {
 #pragma unroll
-          for (uint32_t g = 0; g < 2; ++g) {
+          for (uint32_t gi = 0; gi < 2; ++gi) {
+            const uint32_t g = 1u - gi;  // vid first, like the producers
             CQA_TIMED(o_wait, mbar_wait(&a_full[g], h, 45));  // two phases per tile: h = 0, 1
-            if (g == 0) {
+            if (gi == 0) {
               W_WAIT(4 * h);
               W_WAIT(4 * h + 1);
             }
             tc_fence_after();
-            if (h == 0) CQA_STAMP(3, g * 2);
+            if (h == 0) CQA_STAMP(3, gi * 2);
             if (elect_one()) {
 #pragma unroll
               for (uint32_t ks = 0; ks < 4; ++ks) {
@@ -810,12 +839,12 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
                             W_DESC(j, (ks & 1) * 2 * 2048), W_DESC(j, CqaCfg::W_SLOT / 2 + (ks & 1) * 2 * 2048), id_g, 1u);
               }
               umma_commit(&a_empty[g]);
-              if (g == 1) {
+              if (gi == 1) {
                 umma_commit(&w_empty[(4 * h) % CqaCfg::W_SLOTS]);
                 umma_commit(&w_empty[(4 * h + 1) % CqaCfg::W_SLOTS]);
               }
             }
-            if (h == 0) CQA_STAMP(3, g * 2 + 1);
+            if (h == 0) CQA_STAMP(3, gi * 2 + 1);
           }
           CQA_TIMED(o_wait, mbar_wait(&useg_full[h], k & 1u, 47));
           tc_fence_after();
@@ -843,7 +872,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         }
         if (elect_one()) {
           umma_commit(&mma_done[2]);  // D3: both c2q accumulators
-          umma_commit(&aq_free);      // both shared-memory stages are drained: the next answer image may land
+          umma_commit(&aq_free);      // both shared-memory stages are drained: the AQ region can take weight chunks 12..15
         }
         CQA_STAMP(1, 3);
         CQA_STAMP(1, 4);
@@ -866,7 +895,8 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
                 umma_f16_ts(T2, acol, b_lo, id_g, 1u);
                 umma_f16_ts(T2, acol, b_hi, id_g, 1u);
               }
-              umma_commit(&w_empty[j % CqaCfg::W_SLOTS]);
+              if (!CqaCfg::w_in_aq(j)) umma_commit(&w_empty[j % CqaCfg::W_SLOTS]);
+              if (j == 15) umma_commit(&aq_w_free);  // the AQ region's weight slots are drained: the next answer image may land
             }
           }
         }
@@ -889,19 +919,24 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
 #undef DOFF
     } else if (warp == 1 && lane == 0) {
       // ================================================================= weight ring (one thread)
-      uint32_t q_cnt = 0;
       auto w_src = [&](int q) -> const uint8_t* {
         return q < 8 ? p.c2q_w + static_cast<size_t>(q) * CqaCfg::W_SLOT : p.cat_w + static_cast<size_t>(q - 8) * CqaCfg::W_SLOT;
       };
       for (int k = 0; k < my_tiles; ++k) {
         mbar_wait_relaxed(&b_free, k & 1u, 52, 128);  // U has completed: region B turns from P_sub into the weight ring
         for (int q = 0; q < CqaCfg::CHUNKS; ++q) {
-          const uint32_t i = q_cnt + q, slot = i % CqaCfg::W_SLOTS, use = i / CqaCfg::W_SLOTS;
-          mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 53);
-          mbar_arrive_expect_tx(&w_full[slot], CqaCfg::W_SLOT);
-          bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
+          if (CqaCfg::w_in_aq(q)) {
+            if (q == 12) mbar_wait(&aq_free, k & 1u, 54);  // D3: the a*U stages in the AQ region are drained
+            const int sl = q - 12;
+            mbar_arrive_expect_tx(&wq_full[sl], CqaCfg::W_SLOT);
+            bulk_g2s(sAQ + sl * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &wq_full[sl]);
+          } else {
+            const uint32_t slot = q % CqaCfg::W_SLOTS, use = static_cast<uint32_t>(k) * 4u + CqaCfg::w_use(q);
+            mbar_wait(&w_empty[slot], (use & 1u) ^ 1u, 53);
+            mbar_arrive_expect_tx(&w_full[slot], CqaCfg::W_SLOT);
+            bulk_g2s(sB + slot * CqaCfg::W_SLOT, w_src(q), CqaCfg::W_SLOT, &w_full[slot]);
+          }
         }
-        q_cnt += CqaCfg::CHUNKS;
       }
     } else if (warp == 2 && lane == 0) {
       // ================================================================= ctx blobs and answer images (one thread)
@@ -914,7 +949,7 @@ __global__ void __launch_bounds__(768, 1) cqa_kernel(CqaDev p) {
         bulk_g2s(sCTX, p.ctx_blob + static_cast<size_t>(frame) * CqaCfg::CTX_BYTES, CqaCfg::CTX_BYTES, &ctx_full);
         for (int a_i = 0; a_i < p.n_pt; ++a_i, ++k) {
           const size_t nj = static_cast<size_t>(n_i) * p.n_pt + a_i;
-          if (k > 0) mbar_wait_relaxed(&aq_free, (k - 1) & 1u, 51);  // the previous tile's a*U stages are drained
+          if (k > 0) mbar_wait(&aq_w_free, (k - 1) & 1u, 51);  // the previous tile's a*U stages and AQ weight slots are drained
           mbar_arrive_expect_tx(&aq_full, CqaCfg::AQ_BYTES);
           bulk_g2s(sAQ, p.a_blob + nj * CqaCfg::ABLOB_BYTES, CqaCfg::AQ_BYTES, &aq_full);
         }
