@@ -17,7 +17,8 @@ a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(2018)
 model = STAGE(host.default_opt()).to(dev).eval()
-batch = bench.to_device(bench.make_host_batch(a.batch, pin=False), dev)
+shape = {k: bench.CONFIGS["cfg2"][k] for k in ("T", "R", "Lq", "Ls")}
+batch = bench.to_device(bench.make_host_batch(a.batch, pin=False, shape=shape), dev)
 for _ in range(a.iters):
     model(batch)
 torch.cuda.synchronize()
