@@ -92,7 +92,7 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 256);
+      mbar_init(&full_bar[s], 257);  // 256 producers behind their own stores + the weight copy's expect_tx arrival
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
             }
           }
           fence_async_smem();
-          if (ptid != 0) mbar_arrive(&full_bar[s]);
+          mbar_arrive(&full_bar[s]);  // (thread 0 too: its expect_tx arrival above came before its own A rows were stored)
           ++it;
           if (++c == p.n_chunks) {
             if (ptid == 0) LIN_STAMP(tl, 1);
