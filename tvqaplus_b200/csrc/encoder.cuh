@@ -21,6 +21,13 @@
 //   tail      closing LayerNorm -> store, or mask_logits + max over the sequence (model/stage.py:503)
 // Warp roles (320 threads): warps 0-7 compute, warp 8 = MMA issue, warp 9 = weight-ring copies.
 //
+// Packed tiling (round 2, masked max-pool output only).  With one 100-row sequence per 128-row tile 22 % of every phase
+// worked on rows nobody reads.  In packed mode the rows of ALL sequences are treated as one long array that is cut into
+// tiles of 128 input rows advancing by OUT = 128 - 2*halo rows (halo = n_conv * (k/2): the receptive field of the conv
+// stack): every tile recomputes `halo` rows on either side, the rows [halo, 128 - halo) are exact, and a sequence that
+// straddles a cut gets its column maxima from two tiles through an order-independent atomic max.  5 sequences of 100
+// rows take 4.17 tiles instead of 5.
+//
 // Padded tokens are processed like real ones (the reference never masks before the convs, SURVEY.md §7 quirk i); the
 // depthwise conv sees zeros outside [0, L) of its own sequence only.
 //
@@ -65,6 +72,7 @@ struct EncDev {
   long long n_seq;
   int L, n_conv, out_mode, flags;
   int S;  // row stride of the blocked input layout (STAGE_ENC_IN_BLOCKED)
+  int packed;  // 1: tiles cut the concatenated rows of all sequences every 128 - 2*halo rows (out_mode 1 only; see below)
   long long* timeline;  // optional debug: [32 tiles][16] SM clock stamps of thread 0 of CTA 0 (tools/encoder_timeline.py)
   // out_mode 2: geometry of the CQA context blob the sequence is written into (filled from CqaCfg by the host code)
   uint32_t blob_bytes, blob_lbo, blob_part, blob_inv_off, blob_mask_off;
@@ -78,7 +86,7 @@ struct EncDev {
   } while (0)
 #define ENC_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
-template <int KS>
+template <int KS, bool PACKED>
 __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t a_full, mma_done, w_full[EncCfg::W_SLOTS], w_empty[EncCfg::W_SLOTS];
@@ -96,7 +104,9 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 
   const int L = p.L;
   const int G = 128 / L;  // sequences per tile
-  const long long n_tiles = (p.n_seq + G - 1) / G;
+  const int halo = p.n_conv * (KS / 2), OUT = 128 - 2 * halo;  // packed mode: rows of a tile whose whole receptive field is inside it
+  const int total_rows = PACKED ? static_cast<int>(p.n_seq * L) : 0;  // (host-checked: fits 31 bits)
+  const long long n_tiles = PACKED ? (total_rows + OUT - 1) / OUT : (p.n_seq + G - 1) / G;
   const long long n_my = static_cast<long long>(blockIdx.x) < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (tid == 0) {
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
     // =================================================================== compute warps: thread = (row, column half)
     const int r = (warp & 3) * 32 + lane, h = warp >> 2;
     const uint32_t lane_off = ((warp & 3) * 32u) << 16;
-    const int sq = r / L, pos = r - sq * L;  // my row's sequence within the tile and position within the sequence
+    int sq = r / L, pos = r - sq * L;  // my row's sequence within the tile and position within the sequence (per tile when packed)
     // tap j of the depthwise conv lies inside my row's own sequence.  Rows behind the last sequence of a tile belong to no
     // sequence; nothing reads what they produce, so they run as interior rows (every tap on, neighbours clamped to the tile)
     uint32_t vbits = 0;
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
       const int pp = pos + j - P;
       if (sq >= G || (pp >= 0 && pp < L)) vbits |= 1u << j;
     }
-    const bool interior = vbits == (1u << KS) - 1u;
+    bool interior = vbits == (1u << KS) - 1u;
     float* xrow = X + r * XS;
     float* xh = xrow + h * 64;
     const bool blocked = (p.flags & STAGE_ENC_IN_BLOCKED) != 0;
@@ -174,19 +184,47 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long seq0 = tile * G;
+      long long seq0 = tile * G;  // first sequence of the tile; packed: the sequence of my row
       const int n_here = static_cast<int>((p.n_seq - seq0) < G ? (p.n_seq - seq0) : G);
-      const int n_valid = n_here * L;
-      const bool live = r < n_valid;
+      int n_valid = n_here * L;
+      bool live = r < n_valid;
+      const int g0 = PACKED ? static_cast<int>(tile) * OUT - halo : 0;  // packed: global row of tile row 0
+      if constexpr (PACKED) {
+        const int g = g0 + r;
+        live = g >= 0 && g < total_rows;
+        const int sg = live ? g / L : 0;
+        seq0 = sg;
+        sq = 0;  // (address arithmetic below uses seq0 + sq)
+        pos = live ? g - sg * L : 0;
+        vbits = 0;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          const int pp = pos + j - P;
+          if (!live || (pp >= 0 && pp < L)) vbits |= 1u << j;
+        }
+        interior = vbits == (1u << KS) - 1u;
+        const int left = total_rows - g0;
+        n_valid = left < 128 ? left : 128;  // rows of the tile that exist (row-major loads)
+      }
       ENC_STAMP(0);
-      if (tid == 0 && tile + gridDim.x < n_tiles) {  // the next tile of this CTA starts its way into L2 now (contiguous in both layouts)
+      if (PACKED && tid < 3 && tile + gridDim.x < n_tiles) {
+        // packed: the next tile of this CTA touches at most three sequences; their blocks / rows start their way into L2 now
+        const int gn = static_cast<int>(tile + gridDim.x) * OUT - halo;
+        const int sn = (gn < 0 ? 0 : gn) / L + static_cast<int>(tid);
+        if (static_cast<long long>(sn) < p.n_seq && sn * L < gn + 128) {
+          const float* nx = p.x + static_cast<long long>(sn) * (blocked ? 128ll * p.S : 128ll * L);
+          const uint32_t nbytes = blocked ? 512u * p.S : 512u * L;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(nbytes) : "memory");
+        }
+      }
+      if (!PACKED && tid == 0 && tile + gridDim.x < n_tiles) {  // the next tile of this CTA starts its way into L2 now (contiguous in both layouts)
         const long long nseq0 = (tile + gridDim.x) * G;
         const long long nn = (p.n_seq - nseq0) < G ? (p.n_seq - nseq0) : G;
         const float* nx = p.x + nseq0 * (blocked ? 128ll * p.S : 128ll * L);
         const uint32_t nbytes = static_cast<uint32_t>(nn) * (blocked ? 512u * p.S : 512u * L);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(nbytes) : "memory");
       }
-      const float m_row = (live && p.mask != nullptr) ? __ldg(p.mask + seq0 * L + r) : 0.f;
+      const float m_row = (live && p.mask != nullptr) ? __ldg(p.mask + (PACKED ? static_cast<long long>(g0 + r) : seq0 * L + r)) : 0.f;
 
       // ---- phase 0: raw rows (+ position encoding) -> X, first LayerNorm statistics
       float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);  // packed partial sums: (even, odd) float2 lanes
@@ -218,9 +256,10 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = static_cast<int>(warp) + 8 * (b * 4 + i);
-            const bool on = rr < n_valid;
-            v[i] = on ? __ldg(reinterpret_cast<const float4*>(p.x + (seq0 * L + rr) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            e[i] = (on && use_pe) ? __ldg(reinterpret_cast<const float4*>(p.pe + (rr - (rr / L) * L) * 128) + lane)
+            const long long grow = PACKED ? static_cast<long long>(g0 + rr) : seq0 * L + rr;  // global row (all sequences concatenated)
+            const bool on = PACKED ? (grow >= 0 && grow < total_rows) : rr < n_valid;
+            v[i] = on ? __ldg(reinterpret_cast<const float4*>(p.x + grow * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            e[i] = (on && use_pe) ? __ldg(reinterpret_cast<const float4*>(p.pe + (PACKED ? static_cast<int>(grow) % L : rr - (rr / L) * L) * 128) + lane)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
@@ -407,7 +446,23 @@ __global__ void __launch_bounds__(320, 2) encoder_kernel(EncDev p) {
       } else {
         const int c = tid & 127, part = tid >> 7;
         float* pm = reinterpret_cast<float*>(row_stat);  // [2][128]; row_stat is dead until the next tile's phase 0
-        if (G == 1) {  // one long sequence: the two thread halves take half the rows each
+        if constexpr (PACKED) {
+          // exact rows of this tile: [halo, 128 - halo) (and inside the data); every sequence segment in there sends its
+          // column maxima to the sequence's output row (max is exact and order independent; y starts at -inf)
+          const int ga = g0 + halo < 0 ? 0 : g0 + halo;
+          const int gb = g0 + 128 - halo < total_rows ? g0 + 128 - halo : total_rows;
+          for (int sg = ga / L; sg * L < gb; ++sg) {
+            const int a0 = (sg * L > ga ? sg * L : ga) - g0, b0 = ((sg + 1) * L < gb ? (sg + 1) * L : gb) - g0;
+            float mx = -3.0e38f;
+#pragma unroll 4
+            for (int rr = a0 + part; rr < b0; rr += 2) mx = fmaxf(mx, X[rr * XS + c]);
+            if (a0 + part < b0) {
+              float* dst = p.y + static_cast<long long>(sg) * 128 + c;
+              if (mx >= 0.f) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(mx));
+              else atomicMin(reinterpret_cast<unsigned int*>(dst), __float_as_uint(mx));
+            }
+          }
+        } else if (G == 1) {  // one long sequence: the two thread halves take half the rows each
           const int half_rows = (L + 1) >> 1;
           const int lo = part * half_rows, hi = min(L, lo + half_rows);
           float mx = -3.0e38f;

@@ -29,16 +29,33 @@ static int launch_linear(const LinearDev& d, cudaStream_t s) {
   return check_launch("linear");
 }
 
+__global__ void fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) p[i] = v;
+}
+
 template <int KS>
-static int launch_encoder(const EncDev& d, cudaStream_t s) {
+static int launch_encoder(EncDev& d, cudaStream_t s) {
   constexpr size_t smem = EncCfg::smem_bytes(KS);
-  int rc = set_smem(encoder_kernel<KS>, smem, "encoder");
-  if (rc) return rc;
   const int G = 128 / d.L;
-  const long long tiles = (d.n_seq + G - 1) / G;
+  // Packed tiling (masked max-pool output only, see encoder.cuh): worth it whenever whole sequences fill a tile worse than
+  // the 128 - 2*halo exact rows of a packed tile do (L = 100: 100 rows per tile -> 120)
+  const int halo = d.n_conv * (KS / 2), out_rows = 128 - 2 * halo;
+  d.packed = (d.out_mode == 1 && out_rows > 0 && G * d.L < out_rows && d.n_seq * d.L < (1ll << 30)) ? 1 : 0;
+  long long tiles = (d.n_seq + G - 1) / G;
+  if (d.packed) tiles = (d.n_seq * d.L + out_rows - 1) / out_rows;
   const long long slots = 2ll * num_sms();  // two CTAs fit on an SM (shared memory, 256 TMEM columns each)
   const int grid = static_cast<int>(tiles < slots ? tiles : slots);
-  encoder_kernel<KS><<<grid, EncCfg::THREADS, smem, s>>>(d);
+  if (d.packed) {
+    int rc = set_smem(encoder_kernel<KS, true>, smem, "encoder");
+    if (rc) return rc;
+    const long long n = d.n_seq * 128;
+    fill_f32_kernel<<<static_cast<int>((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, s>>>(d.y, n, -INFINITY);
+    encoder_kernel<KS, true><<<grid, EncCfg::THREADS, smem, s>>>(d);
+  } else {
+    int rc = set_smem(encoder_kernel<KS, false>, smem, "encoder");
+    if (rc) return rc;
+    encoder_kernel<KS, false><<<grid, EncCfg::THREADS, smem, s>>>(d);
+  }
   return check_launch("encoder");
 }
 }  // namespace
