@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define STAGE_ABI_VERSION 3
+#define STAGE_ABI_VERSION 4
 #define STAGE_HSZ 128          /* opt.hsz the kernels are specialised for (config.py:103) */
 #define STAGE_MAX_SEQ 128      /* longest token/region axis one encoder tile holds */
 #define STAGE_MAX_CONV 4       /* n_conv per encoder block (config.py:108,114 default 2) */
@@ -282,6 +282,83 @@ int stage_pad_rows(const float* rows, const int64_t* off, const int32_t* len, in
 
 /* ---- mask_logits (model/model_utils.py:14-15): y = x*m + (1-m)*(-1e10), m broadcast over the last `inner` elems ---- */
 int stage_mask_logits(const float* x, const float* mask, int64_t outer, int inner, float* y, void* stream);
+
+/* ==== training primitives (train_b200.cu): forward-with-saved-state and backward of every operator of the path ========
+ * The reference trains through PyTorch autograd (main.py:53-66: loss.backward(), clip_grad_norm_, Adam.step()).  Here the
+ * backward is a sequence of these entries driven by tvqaplus_b200/train.py from inside one autograd.Function, exact fp32
+ * (CUDA cores).  Row order of the attended tensors in the training engine: (n, a, i, t) - see train.py.
+ * Gradients of parameters are ACCUMULATED (+=, atomics) into caller-zeroed buffers: weights shared by the three input
+ * streams collect their three contributions in place. */
+
+/* C[b0,b1] (op)= alpha * A[b0,b1] * B[b0,b1] (+ bias[n]) (ReLU).  A(m,k) at a + m*a_sm + k*a_sk (one of the two strides
+ * must be 1), B(k,n) at b + k*b_sk + n*b_sn (one must be 1), C row-major with leading dimension ldc; all strides in
+ * elements.  mode 0: C = ..., 1: C += ..., 2: atomicAdd (required when split_k > 1 or when batches share C).
+ * Stands in for F.linear / torch.matmul and their autograd formulas (dX = dY W, dW = dY^T X). */
+typedef struct {
+  const float* a; const float* b; float* c; const float* bias;
+  int32_t m, n, k, nb0, nb1;
+  int64_t a_sm, a_sk, b_sk, b_sn, ldc;
+  int64_t a_b0, a_b1, b_b0, b_b1, c_b0, c_b1;
+  int32_t split_k, mode, relu;
+  float alpha;
+} StageGemmArgs;
+int stage_gemm(const StageGemmArgs* a, void* stream);
+
+/* nn.LayerNorm(d), eps 1e-5 (d <= 768); saves mean / rstd per row for the backward */
+int stage_ln_fwd(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int64_t rows, int d, void* stream);
+/* dx = [add +] dLN/dx (dy) [masked by x > 0 when relu_x: x is a ReLU output and the gradient wanted is the ReLU input's];
+ * dg += sum dy*xhat, db += sum dy.  dx may be NULL (parameter gradients only); add may alias dx. */
+int stage_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* g, const float* add, float* dx,
+                 float* dg, float* db, int64_t rows, int d, int relu_x, void* stream);
+/* out[c] += sum_r x[r*ld + c] (bias gradients) */
+int stage_colsum(const float* x, int64_t rows, int d, int64_t ld, float* out, void* stream);
+int stage_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+/* y = a + b; period > 0: b has `period` elements and repeats (PositionEncoding, model/position_encoding.py:33-43) */
+int stage_add(const float* a, const float* b, float* y, int64_t n, int64_t period, void* stream);
+/* x *= (*scalar) * mult: chain rule with a device-resident upstream gradient, no host read */
+int stage_scale(float* x, int64_t n, const float* scalar, float mult, void* stream);
+/* (groups, I, T, d) -> (groups, T, I, d) */
+int stage_permute_it(const float* x, float* y, int64_t groups, int i_dim, int t_dim, int d, void* stream);
+/* depthwise Conv1d(groups = d, padding = k/2) of DepthwiseSeparableConv (model/cnn.py:25-28), d = 128, odd k <= 7 */
+int stage_dwconv_fwd(const float* x, const float* w, const float* bias, float* y, int64_t n_seq, int l, int d, int k, void* stream);
+int stage_dwconv_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int64_t n_seq, int l, int d, int k, void* stream);
+/* F.normalize(p=2, dim=-1) of rows, d % 4 == 0 (model/context_query_attention.py:54-55, model/stage.py:256); inv may be NULL */
+int stage_l2norm_fwd(const float* x, float* y, float* inv, int64_t rows, int d, void* stream);
+int stage_l2norm_bwd(const float* dy, const float* y, const float* inv, float* dx, int64_t rows, int d, int accumulate, void* stream);
+/* s[n, rows_per_n, t, lc] raw cosines -> masked in place (raw - 1e10 (1 - cm*qm)); p = softmax(scale*s) * cm*qm
+ * (model/context_query_attention.py:57-66,100).  c_mask [n*rows_per_n], q_mask [n, t, lc]. */
+int stage_attn_softmax_fwd(float* s, const float* c_mask, const float* q_mask, float* p, int64_t n, int rows_per_n, int t, int lc, float scale, void* stream);
+/* dp <- scale * p * (dp - sum_j dp*p) */
+int stage_attn_softmax_bwd(float* dp, const float* p, int64_t rows, int lc, float scale, void* stream);
+/* out[r] = [a[r / a_div], b[r], a*b], 128 + 128 + 128 (torch.cat of model/stage.py:376 and :276) and its backward */
+int stage_cat3_fwd(const float* a, const float* b, float* out, int64_t rows, int a_div, void* stream);
+int stage_cat3_bwd(const float* dcat, const float* a, const float* b, float* da, float* db, int64_t a_rows, int a_div, int accumulate_a, void* stream);
+/* max over the rows of each sequence of mask_logits(x, mask) (model/stage.py:503), 128 channels, with the argmax */
+int stage_maxpool_fwd(const float* x, const float* mask, float* y, int32_t* arg, int64_t n_seq, int l, void* stream);
+int stage_maxpool_bwd(const float* dy, const float* mask, const int32_t* arg, float* dx, int64_t n_seq, int l, void* stream);
+/* get_ts_loss (model/stage.py:539-555) on the masked scores [n,5,t,2]: terms[n,2] = CE_st, CE_ed of the GT answer's rows,
+ * probs[2,n,t] = their softmax over frames (input of the span search), dscores[n,5,t,2] (caller-zeroed) = gradient of
+ * 0.5*(CE_st + CE_ed) w.r.t. the UNMASKED scores (already times the frame mask). */
+int stage_ts_loss_grad(const float* t_scores, const float* ts_mask, const int64_t* target, const int64_t* st, const int64_t* ed, int n, int t,
+                       float* terms, float* probs, float* dscores, void* stream);
+/* train branch of get_proposals (model/stage.py:407-438): rows 2n = GT span, 2n+1 = predicted span (valid if confident and
+ * IoU >= 0.5); feat[2n,5,256] = [span-local max, global max] of mask_logits(x[n,5,t,128], frame_mask[n,5,t]) + argmax */
+int stage_proposal_pool_fwd(const float* x, const float* frame_mask, const int64_t* target, const int64_t* st, const int64_t* ed,
+                            const int32_t* spans, const float* conf, int n, int t, int extra, float prob_thd, float* feat, int32_t* arg,
+                            int32_t* valid, int64_t* row_target, void* stream);
+int stage_proposal_pool_bwd(const float* dfeat, const int32_t* arg, const int32_t* valid, const float* frame_mask, int n, int t, float* dx, void* stream);
+/* gradient of stage_att_loss_fwd scattered (atomicAdd) into dscores; upstream = device scalar */
+int stage_att_loss_bwd(const float* scores, const int64_t* pos_off, const int64_t* neg_off, int64_t m, int loss_type, float alpha, float margin,
+                       const float* upstream, float* dscores, void* stream);
+/* cls loss of main.py:57-59 over the VALID proposal rows [n_rows,5]: out[0] = sum CE * (n_examples / n_valid), out[1] =
+ * n_valid, out[2] = correct rows; drows[n_rows,5] = its gradient (0 on invalid rows).  No host read, no compaction. */
+int stage_answer_ce(const float* rows, const int32_t* valid, const int64_t* row_target, int n_rows, int n_examples, float* out, float* drows, void* stream);
+/* out[0] += sum g^2 (caller zeroes out): the global norm of clip_grad_norm_ (main.py:65) */
+int stage_grad_sumsq(const float* g, int64_t n, float* out, void* stream);
+/* clip (coef = min(1, max_norm / (sqrt(*sumsq)*grad_scale + 1e-6)); max_norm <= 0: off) + torch.optim.Adam with L2 weight
+ * decay on flat buffers (main.py:209-212); bc1 = 1 - beta1^step, bc2 = 1 - beta2^step.  g is left holding the clipped grad. */
+int stage_adam_step(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm, float lr, float beta1, float beta2,
+                    float eps, float wd, float bc1, float bc2, float grad_scale, void* stream);
 
 /* ---- UMMA layout probe (test-only; pins the descriptor conventions the kernels rely on) ------------------------------ */
 typedef struct {

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libstage_b200.so does not export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
-    assert _lib.lib().stage_abi_version() == 3
+    assert _lib.lib().stage_abi_version() == 4
 
 
 def test_bad_arguments_return_error_codes_not_crashes():

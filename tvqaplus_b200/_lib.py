@@ -65,6 +65,14 @@ class ProposalArgs(C.Structure):
                 ("answer_rows", _f), ("row_valid", _f), ("row_target", _f)]
 
 
+class GemmArgs(C.Structure):
+    _fields_ = [("a", _f), ("b", _f), ("c", _f), ("bias", _f),
+                ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("nb0", C.c_int32), ("nb1", C.c_int32),
+                ("a_sm", C.c_int64), ("a_sk", C.c_int64), ("b_sk", C.c_int64), ("b_sn", C.c_int64), ("ldc", C.c_int64),
+                ("a_b0", C.c_int64), ("a_b1", C.c_int64), ("b_b0", C.c_int64), ("b_b1", C.c_int64), ("c_b0", C.c_int64),
+                ("c_b1", C.c_int64), ("split_k", C.c_int32), ("mode", C.c_int32), ("relu", C.c_int32), ("alpha", C.c_float)]
+
+
 class ProbeArgs(C.Structure):
     _fields_ = [("a_img", _f), ("b_img", _f), ("a_bytes", C.c_uint32), ("b_bytes", C.c_uint32),
                 ("a_lbo", C.c_uint32), ("a_sbo", C.c_uint32), ("a_step", C.c_uint32),
@@ -103,6 +111,31 @@ SYMBOLS = {
     "stage_pad_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "stage_mask_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "stage_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "stage_ln_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "stage_ln_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "stage_colsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "stage_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stage_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "stage_scale": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p]),
+    "stage_permute_it": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "stage_dwconv_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "stage_dwconv_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "stage_l2norm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "stage_l2norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "stage_attn_softmax_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "stage_attn_softmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "stage_cat3_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "stage_cat3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "stage_maxpool_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "stage_maxpool_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "stage_ts_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_proposal_pool_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_proposal_pool_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "stage_att_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_answer_ce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stage_grad_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "stage_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "stage_umma_probe": (C.c_int, [C.POINTER(ProbeArgs), C.c_void_p]),
 }
 
@@ -121,7 +154,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.stage_abi_version() != 3:
+        if l.stage_abi_version() != 4:
             raise RuntimeError("tvqaplus_b200: ABI version mismatch in %s" % LIB_PATH)
         _lib = l
     return _lib
