@@ -160,10 +160,12 @@ class STAGE(nn.Module):
         other_outputs)``; ``inference_mode`` returns the prediction dict (model/stage.py:297-312)."""
         if self.training and self.dropout > 0:
             raise NotImplementedError(
-                "tvqaplus_b200: the train-mode forward is built for dropout = 0 only (no dropout RNG; and no backward at all: "
-                "the kernels are forward-only, the outputs carry no autograd graph); call model.eval() or set opt.dropout = 0")
+                "tvqaplus_b200: the train-mode forward and the backward are built for dropout = 0 only (no dropout RNG); "
+                "call model.eval() or set opt.dropout = 0")
         if self.flag_cnt == 0:
             raise NotImplementedError  # model/stage.py:291-292
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(batch)  # outputs carry an autograd graph whose backward is our kernels (train.py)
         with torch.no_grad():
             return self._forward_eval(batch)
 
@@ -300,6 +302,27 @@ class STAGE(nn.Module):
                         start_indices=batch.anno_st_idx) if self.vfeat_flag else None}
         temporal_loss = self._last_ts_loss if self._last_ts_loss is not None else self.get_ts_loss(t_scores, batch.ts_label, batch.target)
         return out, 0, None, temporal_loss, t_probs, other_outputs
+
+    def _forward_train(self, batch):
+        """Train-mode forward with gradients (main.py:53-61): ``StageTrainFunction`` runs the training engine's kernels and its
+        backward hands every parameter its gradient, so ``loss.backward()`` / ``optimizer.step()`` of the reference's loop
+        work unchanged.  Return convention of model/stage.py:345-348."""
+        from ..train import StageTrainFunction, TrainEngine
+        eng = getattr(self, "_train_engine", None)
+        if eng is None:
+            eng = self._train_engine = TrainEngine(self)
+        self.bsz = len(batch.qid)
+        offsets = None
+        if self.use_sup_att and self.vfeat_flag and getattr(batch, "att_labels", None) is not None:
+            pos, neg = self._att_pairs(batch.att_labels, batch.target, batch.anno_st_idx, self.num_negatives,
+                                       batch.use_hard_negatives, self.drop_topk)
+            N, Lq = batch.qas_bert.shape[0], batch.qas_bert.shape[2]
+            offsets = eng.att_offsets_from_pairs(pos, neg, N, batch.vid.shape[1], Lq, batch.vid.shape[2])
+        params = [p for _, p in self.named_parameters()]
+        out, att_loss, temporal_loss, t_scores, target = StageTrainFunction.apply(eng, batch, offsets, *params)
+        if offsets is None:
+            att_loss = 0
+        return [out, target], att_loss, None, temporal_loss, t_scores, {"temporal_scores": t_scores}
 
     def _forward_single_stream(self, batch, a_embed, qas_mask):
         """sub-only / vfeat-only models (model/stage.py:283-290): the statement is that stream's mixed tensor, its mask the

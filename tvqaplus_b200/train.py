@@ -1,0 +1,384 @@
+"""Training path of STAGE on the device: forward with saved activations, hand-written backward, clip + Adam.
+
+The reference trains through PyTorch autograd (main.py:53-66: ``loss.backward()``, ``clip_grad_norm_``, ``Adam.step()``) and
+``nn.DataParallel`` (main.py:204-206).  Here:
+
+* ``TrainEngine`` runs the train-mode forward (dropout = 0, train branch of ``get_proposals``) out of the primitives of
+  ``csrc/train.cuh`` and keeps what the backward needs; ``backward`` walks the same graph in reverse and accumulates every
+  parameter gradient into ONE flat fp32 buffer (state_dict order) - the buffer a data-parallel run all-reduces.
+* ``StageTrainFunction`` wraps the pair as a ``torch.autograd.Function`` so that the reference's own training loop
+  (``outputs, att_loss, _, temporal_loss, _ = model(batch)`` ... ``loss.backward()``; ``optimizer.step()``) runs unchanged
+  on ``tvqaplus_b200.model.STAGE`` in train mode.
+* ``Trainer`` is the fused step for one-process-per-GPU training: forward, cls / temporal / attention losses and their
+  gradients on the device (no host read), backward, one NCCL SUM all-reduce of the flat gradient buffer when
+  ``torch.distributed`` is initialised, global-norm clip + Adam in one kernel on the flat parameter buffer.
+
+Row order inside the engine: the attended tensors are (n, a, i, t) - question word before frame - so that every
+contraction of the context-query attention (S = C Q^T, U = P Q and their four gradient products) and the reductions over
+frames are plain strided batched GEMMs; the statement is permuted to the reference's (n, a, t, i) order once, in front of the
+cls encoder.  All arithmetic is fp32 (CUDA-core FMA): gradients are checked against autograd of the reference formulas at
+1e-4 (tests/test_train_gpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from . import train_ops as T
+
+
+class TrainEngine:
+    def __init__(self, model):
+        self.model = model
+        opt_ok = (model.sub_flag and model.vfeat_flag and model.add_local and model.t_iter == 0
+                  and all(b.num_heads == 0 for e in (model.input_encoder, model.cls_encoder) for b in e.stacked_encoderBlocks))
+        if not opt_ok:
+            raise NotImplementedError("tvqaplus_b200: the training path is built for the run_main.sh configuration "
+                                      "(sub + vfeat streams, add_local, t_iter = 0, encoder heads = 0)")
+        self.names = [n for n, _ in model.named_parameters()]
+        self.shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+        self.offsets, at = {}, 0
+        for n, p in model.named_parameters():  # every tensor starts on a 256-byte boundary (vector loads, bulk copies)
+            self.offsets[n] = at
+            at += (p.numel() + 63) // 64 * 64
+        self.n_params = at
+
+    # ---------------------------------------------------------------------------------------------- helpers
+    def _P(self) -> Dict[str, torch.Tensor]:
+        return {n: p.detach() for n, p in self.model.named_parameters()}
+
+    def new_grads(self, device):
+        flat = torch.zeros(self.n_params, device=device, dtype=torch.float32)
+        views = {n: flat[o:o + int(torch.Size(self.shapes[n]).numel())].view(self.shapes[n]) for n, o in self.offsets.items()}
+        return flat, views
+
+    # ---------------------------------------------------------------------------------------------- input projections
+    def _fc_fwd(self, P, x, pre):
+        h0, s0 = T.ln_fwd(x, P[pre + ".0.weight"], P[pre + ".0.bias"])
+        r1 = T.linear(h0, P[pre + ".2.weight"], P[pre + ".2.bias"], relu=True)
+        h1, s1 = T.ln_fwd(r1, P[pre + ".4.weight"], P[pre + ".4.bias"])
+        r2 = T.linear(h1, P["input_embedding.1.weight"], P["input_embedding.1.bias"], relu=True)
+        e0, s2 = T.ln_fwd(r2, P["input_embedding.3.weight"], P["input_embedding.3.bias"])
+        return e0, (x, h0, s0, r1, h1, s1, r2, s2, pre)
+
+    def _fc_bwd(self, P, G, de0, sv):
+        x, h0, s0, r1, h1, s1, r2, s2, pre = sv
+        dz2 = T.ln_bwd(de0, r2, s2, P["input_embedding.3.weight"], G["input_embedding.3.weight"], G["input_embedding.3.bias"], relu_x=True)
+        T.linear_bwd_w(dz2, h1, G["input_embedding.1.weight"], G["input_embedding.1.bias"])
+        dh1 = T.linear_bwd_x(dz2, P["input_embedding.1.weight"])
+        dz1 = T.ln_bwd(dh1, r1, s1, P[pre + ".4.weight"], G[pre + ".4.weight"], G[pre + ".4.bias"], relu_x=True)
+        T.linear_bwd_w(dz1, h0, G[pre + ".2.weight"], G[pre + ".2.bias"])
+        dh0 = T.linear_bwd_x(dz1, P[pre + ".2.weight"])
+        T.ln_bwd(dh0, x, s0, P[pre + ".0.weight"], G[pre + ".0.weight"], G[pre + ".0.bias"], want_dx=False)
+
+    # ---------------------------------------------------------------------------------------------- encoder blocks
+    def _enc_fwd(self, P, x, n_seq, L, enc, prefix):
+        blocks = []
+        cur_in = x
+        ksize = enc.stacked_encoderBlocks[0].kernel_size
+        for b, mod in enumerate(enc.stacked_encoderBlocks):
+            blk = "%s.stacked_encoderBlocks.%d" % (prefix, b)
+            pe = mod.position_encoding.pe[:L].contiguous()
+            cur = T.add(cur_in, pe, period=L * 128)
+            convs = []
+            for i in range(mod.n_conv):
+                nrm, st = T.ln_fwd(cur, P["%s.layer_norm.%d.weight" % (blk, i)], P["%s.layer_norm.%d.bias" % (blk, i)])
+                dw = T.dwconv_fwd(nrm, P["%s.conv.%d.depthwise_conv.weight" % (blk, i)], P["%s.conv.%d.depthwise_conv.bias" % (blk, i)],
+                                  n_seq, L, ksize)
+                pw = T.linear(dw, P["%s.conv.%d.pointwise_conv.weight" % (blk, i)], P["%s.conv.%d.pointwise_conv.bias" % (blk, i)], relu=True)
+                nxt = T.add(pw, cur)
+                convs.append((cur, st, nrm, dw, pw))
+                cur = nxt
+            out, stf = T.ln_fwd(cur, P[blk + ".final_layer_norm.weight"], P[blk + ".final_layer_norm.bias"])
+            blocks.append((convs, cur, stf, blk))
+            cur_in = out
+        return cur_in, (blocks, n_seq, L, ksize)
+
+    def _enc_bwd(self, P, G, dout, sv):
+        blocks, n_seq, L, k = sv
+        d = dout
+        for convs, last, stf, blk in reversed(blocks):
+            d = T.ln_bwd(d, last, stf, P[blk + ".final_layer_norm.weight"], G[blk + ".final_layer_norm.weight"], G[blk + ".final_layer_norm.bias"])
+            for i in reversed(range(len(convs))):
+                cur, st, nrm, dw, pw = convs[i]
+                pwn, dwn, lnn = "%s.conv.%d.pointwise_conv" % (blk, i), "%s.conv.%d.depthwise_conv" % (blk, i), "%s.layer_norm.%d" % (blk, i)
+                dpw = T.relu_bwd(d, pw)
+                T.linear_bwd_w(dpw, dw, G[pwn + ".weight"], G[pwn + ".bias"])
+                ddw = T.linear_bwd_x(dpw, P[pwn + ".weight"])
+                dn = T.dwconv_bwd(ddw, nrm, P[dwn + ".weight"], G[dwn + ".weight"], G[dwn + ".bias"], n_seq, L, k)
+                d = T.ln_bwd(dn, cur, st, P[lnn + ".weight"], G[lnn + ".weight"], G[lnn + ".bias"], add=d, out=d)
+        return d  # the position table has no gradient
+
+    # ---------------------------------------------------------------------------------------------- context-query attention
+    def _cqa_fwd(self, P, C, Cn, c_mask, Q, q_mask, N, Tn, Lq, Lc, scale):
+        ai, dev = 5 * Lq, C.device
+        Qn, qinv = T.l2norm_fwd(Q)
+        S = torch.empty(N * ai * Tn, Lc, device=dev, dtype=torch.float32)
+        T.gemm(Cn, Qn, S, ai, Tn * Lc, 128, (128, 1), (1, 128), Tn * Lc, batch=(N, 1), a_b=(ai * 128, 0), b_b=(Tn * Lc * 128, 0),
+               c_b=(ai * Tn * Lc, 0))
+        Pm = T.attn_softmax_fwd(S, c_mask, q_mask, N, ai, Tn, Lc, scale)
+        U = torch.empty(N * ai * Tn, 128, device=dev, dtype=torch.float32)
+        T.gemm(Pm, Q, U, ai, 128, Lc, (Tn * Lc, 1), (128, 1), Tn * 128, batch=(N, Tn), a_b=(ai * Tn * Lc, Lc), b_b=(Tn * Lc * 128, Lc * 128),
+               c_b=(ai * Tn * 128, 128))
+        cat = T.cat3_fwd(C, U, Tn)
+        l, st = T.ln_fwd(cat, P["c2q_down_projection.0.weight"], P["c2q_down_projection.0.bias"])
+        att = T.linear(l, P["c2q_down_projection.2.weight"], P["c2q_down_projection.2.bias"], relu=True)
+        return att, S, (C, Cn, Q, Qn, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale)
+
+    def _cqa_bwd(self, P, G, datt, sv, dC, dCn, att_grad=None):
+        C, Cn, Q, Qn, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale = sv
+        ai, dev = 5 * Lq, C.device
+        dpre = T.relu_bwd(datt, att, out=datt)
+        T.linear_bwd_w(dpre, l, G["c2q_down_projection.2.weight"], G["c2q_down_projection.2.bias"])
+        dl = T.linear_bwd_x(dpre, P["c2q_down_projection.2.weight"])
+        dcat = T.ln_bwd(dl, cat, st, P["c2q_down_projection.0.weight"], G["c2q_down_projection.0.weight"], G["c2q_down_projection.0.bias"], out=dl)
+        dU = T.cat3_bwd(dcat, C, U, dC, Tn, True)
+        del dcat, dl
+        dP = torch.empty_like(Pm)
+        T.gemm(dU, Q, dP, ai, Lc, 128, (Tn * 128, 1), (1, 128), Tn * Lc, batch=(N, Tn), a_b=(ai * Tn * 128, 128), b_b=(Tn * Lc * 128, Lc * 128),
+               c_b=(ai * Tn * Lc, Lc))
+        dQ = torch.empty_like(Q)
+        T.gemm(Pm, dU, dQ, Lc, 128, ai, (1, Tn * Lc), (Tn * 128, 1), 128, batch=(N, Tn), a_b=(ai * Tn * Lc, Lc), b_b=(ai * Tn * 128, 128),
+               c_b=(Tn * Lc * 128, Lc * 128))
+        dS = T.attn_softmax_bwd_(dP, Pm, Lc, scale)
+        if att_grad is not None:  # the ranking loss reads the masked raw scores of the vid stream (model/stage.py:317-341)
+            att_grad(S, dS)
+        T.gemm(dS, Qn, dCn, ai, 128, Tn * Lc, (Tn * Lc, 1), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(Tn * Lc * 128, 0),
+               c_b=(ai * 128, 0), mode=2, split_k=max(1, min(64, 592 // max(1, N * ((ai + 127) // 128)))))
+        dQn = torch.empty_like(Q)
+        T.gemm(dS, Cn, dQn, Tn * Lc, 128, ai, (1, Tn * Lc), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(ai * 128, 0),
+               c_b=(Tn * Lc * 128, 0))
+        T.l2norm_bwd(dQn, Qn, qinv, dQ, True)
+        return dQ
+
+    # ---------------------------------------------------------------------------------------------- forward
+    def forward(self, batch, att_offsets=None) -> dict:
+        """batch: the reference's model inputs on the device.  att_offsets = (pos, neg) int64 element offsets of the sampled
+        attention pairs in the ENGINE's score layout (see ``att_offsets_from_pairs``), or None (no attention loss).
+        Returns the outputs and ``ctx`` for ``backward``."""
+        m = self.model
+        P = self._P()
+        N, Lq = batch.qas_bert.shape[0], batch.qas_bert.shape[2]
+        Tn, Ls = batch.sub_bert.shape[1:3]
+        R = batch.vid.shape[2]
+        qas_mask = batch.qas_mask.float().contiguous()
+        sub_mask = batch.sub_mask.float().contiguous()
+        vid_mask = batch.vid_mask.float().contiguous()
+        ts_mask = batch.ts_label_mask.float().contiguous()
+        target = batch.target.to(torch.int64).contiguous()
+        st_lab, ed_lab = batch.ts_label["st"].to(torch.int64).contiguous(), batch.ts_label["ed"].to(torch.int64).contiguous()
+        ctx = {}
+
+        # 1. input projections + input encoder, three streams (model/stage.py:351-363)
+        qa0, ctx["fc_q"] = self._fc_fwd(P, batch.qas_bert.float().reshape(N * 5 * Lq, -1), "bert_word_encoding_fc")
+        C, ctx["enc_q"] = self._enc_fwd(P, qa0, N * 5, Lq, m.input_encoder, "input_encoder")
+        sub0, ctx["fc_s"] = self._fc_fwd(P, batch.sub_bert.float().reshape(N * Tn * Ls, -1), "bert_word_encoding_fc")
+        Qs, ctx["enc_s"] = self._enc_fwd(P, sub0, N * Tn, Ls, m.input_encoder, "input_encoder")
+        vn, _ = T.l2norm_fwd(batch.vid.float().reshape(N * Tn * R, -1), want_inv=False)  # model/stage.py:256
+        vid0, ctx["fc_v"] = self._fc_fwd(P, vn, "vid_fc")
+        Qv, ctx["enc_v"] = self._enc_fwd(P, vid0, N * Tn, R, m.input_encoder, "input_encoder")
+        del qa0, sub0, vid0, vn
+
+        # 2. context-query attention + c2q projection per stream, rows (n, a, i, t) (model/stage.py:365-387)
+        Cn, cinv = T.l2norm_fwd(C)
+        ctx["c"] = (C, Cn, cinv)
+        att_s, _, ctx["cqa_s"] = self._cqa_fwd(P, C, Cn, qas_mask, Qs, sub_mask, N, Tn, Lq, Ls, m.scale)
+        att_v, S_vid, ctx["cqa_v"] = self._cqa_fwd(P, C, Cn, qas_mask, Qv, vid_mask, N, Tn, Lq, R, m.scale)
+
+        # 3. concat_fc (model/stage.py:276-279), then the reference's (n, a, t, i) row order for the cls encoder
+        cat2 = T.cat3_fwd(att_s, att_v, 1)
+        l2, st2 = T.ln_fwd(cat2, P["concat_fc.0.weight"], P["concat_fc.0.bias"])
+        r = T.linear(l2, P["concat_fc.2.weight"], P["concat_fc.2.bias"], relu=True)
+        stm, st4 = T.ln_fwd(r, P["concat_fc.4.weight"], P["concat_fc.4.bias"])
+        ctx["cat"] = (att_s, att_v, cat2, l2, st2, r, st4)
+        stm_p = T.permute_it(stm, N * 5, Lq, Tn)
+        del stm
+        frame_on = (vid_mask.view(N, Tn, R).sum(-1) != 0).float()                      # statement mask = the vid stream's (stage.py:280-282)
+        sm = (qas_mask.view(N, 5, 1, Lq) * frame_on.view(N, 1, Tn, 1)).contiguous()     # (N, 5, T, Lq)
+        mm = (sm.sum(-1) != 0).float().contiguous()                                     # max_statement_mask (N, 5, T)
+
+        # 4. cls encoder + masked max over the question words (model/stage.py:499-505)
+        enc, ctx["enc_c"] = self._enc_fwd(P, stm_p, N * 5 * Tn, Lq, m.cls_encoder, "cls_encoder")
+        ms, arg = T.maxpool_fwd(enc, sm.view(-1, Lq), N * 5 * Tn, Lq)
+        del enc, stm_p
+
+        # 5. residual temporal predictor, span scores, temporal loss (model/stage.py:469-482,521,539-555)
+        pj, stl, edl, cl = "cls_projection_layers.0.conv", "temporal_scoring_st_layers.0.conv", "temporal_scoring_ed_layers.0.conv", "classifier.conv"
+        l0, s0 = T.ln_fwd(ms, P[pj + ".0.weight"], P[pj + ".0.bias"])
+        p0 = T.linear(l0, P[pj + ".2.weight"], P[pj + ".2.bias"], relu=True)
+        x1 = T.add(ms, p0)
+        ls, sst = T.ln_fwd(x1, P[stl + ".0.weight"], P[stl + ".0.bias"])
+        le, sed = T.ln_fwd(x1, P[edl + ".0.weight"], P[edl + ".0.bias"])
+        ts = torch.empty(N * 5 * Tn, 2, device=ms.device, dtype=torch.float32)
+        T.linear(ls, P[stl + ".2.weight"], P[stl + ".2.bias"], out=ts, ldc=2, c_off=0)
+        T.linear(le, P[edl + ".2.weight"], P[edl + ".2.bias"], out=ts, ldc=2, c_off=1)
+        t_scores = ops.mask_logits_fwd(ts.view(N, 5, Tn, 2), ts_mask.view(N, 1, Tn).expand(N, 5, Tn).contiguous())
+        terms, probs, dts = T.ts_loss_grad(t_scores, ts_mask, target, st_lab, ed_lab)
+        temporal_loss = terms.sum() * 0.5
+
+        # 6. train branch of get_proposals + classifier (model/stage.py:407-438,536)
+        spans, conf = ops.find_max_span(probs[0], probs[1])
+        feat, parg, valid, row_target = T.proposal_pool_fwd(x1, mm, target, st_lab, ed_lab, spans, conf, N, Tn, m.extra_span_length, 0.01)
+        lc, sc = T.ln_fwd(feat, P[cl + ".0.weight"], P[cl + ".0.bias"])
+        rows = T.linear(lc, P[cl + ".2.weight"], P[cl + ".2.bias"]).view(2 * N, 5)
+        ctx["head"] = (ms, arg, sm, mm, l0, s0, p0, x1, ls, sst, le, sed, dts, feat, parg, valid, lc, sc, N, Tn, Lq)
+
+        # 7. attention ranking loss on the vid stream's raw scores (model/stage.py:317-341,731-746)
+        att_loss = None
+        if att_offsets is not None:
+            pos, neg = (o.to(device=S_vid.device, dtype=torch.int64).contiguous() for o in att_offsets)
+            att_loss = ops.att_loss_fwd(S_vid, pos, neg, loss_type=m.att_loss_type, alpha=m.alpha, margin=m.margin)
+            ctx["att"] = (pos, neg)
+        return dict(answer_rows=rows, row_valid=valid, row_target=row_target, t_scores=t_scores, temporal_loss=temporal_loss,
+                    att_loss=att_loss, vid_raw_s=S_vid, ctx=ctx)
+
+    def att_offsets_from_pairs(self, pos, neg, N, Tn, Lq, R):
+        """(batch, answer, image, word, region) index rows of ``STAGE._att_pairs`` -> element offsets into the engine's
+        (N, 5, Lq, T, R) score tensor."""
+        strides = torch.tensor([5 * Lq * Tn * R, Lq * Tn * R, R, Tn * R, 1], dtype=torch.long)
+        return (pos * strides).sum(1), (neg * strides).sum(1)
+
+    # ---------------------------------------------------------------------------------------------- backward
+    def backward(self, ctx, d_rows, g_ts, g_att=None):
+        """d_rows (2N, 5): gradient w.r.t. ``answer_rows`` (zero on invalid rows); g_ts / g_att: one-element device tensors,
+        the upstream gradients of ``temporal_loss`` / ``att_loss``.  Returns the flat gradient buffer (state_dict order)."""
+        m = self.model
+        P = self._P()
+        dev = d_rows.device
+        flat, G = self.new_grads(dev)
+        ms, arg, sm, mm, l0, s0, p0, x1, ls, sst, le, sed, dts, feat, parg, valid, lc, sc, N, Tn, Lq = ctx["head"]
+        pj, stl, edl, cl = "cls_projection_layers.0.conv", "temporal_scoring_st_layers.0.conv", "temporal_scoring_ed_layers.0.conv", "classifier.conv"
+
+        # classifier and the pooled proposal features
+        dr = d_rows.contiguous().view(-1, 1)
+        T.linear_bwd_w(dr, lc, G[cl + ".2.weight"], G[cl + ".2.bias"])
+        dlc = T.linear_bwd_x(dr, P[cl + ".2.weight"])
+        dfeat = T.ln_bwd(dlc, feat, sc, P[cl + ".0.weight"], G[cl + ".0.weight"], G[cl + ".0.bias"])
+        dx1 = torch.zeros_like(x1)
+        T.proposal_pool_bwd(dfeat, parg, valid, mm, N, Tn, dx1)
+        # span scores (temporal loss)
+        dts = T.scale_(dts.view(-1, 2).clone(), g_ts)
+        T.linear_bwd_w(dts, ls, G[stl + ".2.weight"], G[stl + ".2.bias"], dy_ld=2, dy_off=0, n=1)
+        dls = T.linear_bwd_x(dts, P[stl + ".2.weight"], dy_ld=2, dy_off=0, n=1)
+        T.ln_bwd(dls, x1, sst, P[stl + ".0.weight"], G[stl + ".0.weight"], G[stl + ".0.bias"], add=dx1, out=dx1)
+        T.linear_bwd_w(dts, le, G[edl + ".2.weight"], G[edl + ".2.bias"], dy_ld=2, dy_off=1, n=1)
+        dle = T.linear_bwd_x(dts, P[edl + ".2.weight"], dy_ld=2, dy_off=1, n=1)
+        T.ln_bwd(dle, x1, sed, P[edl + ".0.weight"], G[edl + ".0.weight"], G[edl + ".0.bias"], add=dx1, out=dx1)
+        # residual projection
+        dp0 = T.relu_bwd(dx1, p0)
+        T.linear_bwd_w(dp0, l0, G[pj + ".2.weight"], G[pj + ".2.bias"])
+        dl0 = T.linear_bwd_x(dp0, P[pj + ".2.weight"])
+        dms = T.ln_bwd(dl0, ms, s0, P[pj + ".0.weight"], G[pj + ".0.weight"], G[pj + ".0.bias"], add=dx1)
+
+        # max-pool, cls encoder, back to (n, a, i, t)
+        denc = T.maxpool_bwd(dms, sm.view(-1, Lq), arg, N * 5 * Tn, Lq)
+        dstm_p = self._enc_bwd(P, G, denc, ctx["enc_c"])
+        dstm = T.permute_it(dstm_p, N * 5, Tn, Lq)
+        del dstm_p, denc
+
+        # concat_fc
+        att_s, att_v, cat2, l2, st2, r, st4 = ctx["cat"]
+        dr2 = T.ln_bwd(dstm, r, st4, P["concat_fc.4.weight"], G["concat_fc.4.weight"], G["concat_fc.4.bias"], relu_x=True, out=dstm)
+        T.linear_bwd_w(dr2, l2, G["concat_fc.2.weight"], G["concat_fc.2.bias"])
+        dl2 = T.linear_bwd_x(dr2, P["concat_fc.2.weight"])
+        dcat2 = T.ln_bwd(dl2, cat2, st2, P["concat_fc.0.weight"], G["concat_fc.0.weight"], G["concat_fc.0.bias"], out=dl2)
+        datt_s = torch.empty_like(att_s)
+        datt_v = T.cat3_bwd(dcat2, att_s, att_v, datt_s, 1, False)
+        del dcat2, dl2, dr2, dstm
+
+        # context-query attention, both streams; dC / dCn collect both
+        C, Cn, cinv = ctx["c"]
+        dC, dCn = torch.zeros_like(C), torch.zeros_like(C)
+        att_grad = None
+        if g_att is not None and "att" in ctx:
+            pos, neg = ctx["att"]
+
+            def att_grad(S, dS):
+                T.att_loss_bwd(S, pos, neg, 0 if m.att_loss_type == "lse" else 1, m.alpha, m.margin, g_att, dS)
+        dQv = self._cqa_bwd(P, G, datt_v, ctx["cqa_v"], dC, dCn, att_grad)
+        dQs = self._cqa_bwd(P, G, datt_s, ctx["cqa_s"], dC, dCn)
+        T.l2norm_bwd(dCn, Cn, cinv, dC, True)
+
+        # input encoders and projections
+        for dq, e, f in ((dQv, "enc_v", "fc_v"), (dQs, "enc_s", "fc_s"), (dC, "enc_q", "fc_q")):
+            self._fc_bwd(P, G, self._enc_bwd(P, G, dq, ctx[e]), ctx[f])
+        return flat
+
+
+class StageTrainFunction(torch.autograd.Function):
+    """``(answer_rows[valid], att_loss, temporal_loss, t_scores) = StageTrainFunction.apply(engine, batch, att_offsets, *params)``
+    with a backward that runs the engine's kernels and hands every parameter its gradient."""
+
+    @staticmethod
+    def forward(actx, engine, batch, att_offsets, *params):
+        out = engine.forward(batch, att_offsets)
+        keep = out["row_valid"].bool()  # N_new is data dependent: the one host sync of the train-mode forward
+        idx = torch.nonzero(keep).squeeze(1)
+        actx.engine, actx.saved, actx.idx, actx.n_rows = engine, out["ctx"], idx, keep.numel()
+        actx.has_att = out["att_loss"] is not None
+        att = out["att_loss"] if actx.has_att else torch.zeros((), device=keep.device)
+        actx.mark_non_differentiable(out["t_scores"])
+        return out["answer_rows"][idx], att, out["temporal_loss"], out["t_scores"], out["row_target"][idx]
+
+    @staticmethod
+    def backward(actx, d_rows, d_att, d_ts, _d_scores, _d_target):
+        eng = actx.engine
+        dev = actx.idx.device
+        full = torch.zeros(actx.n_rows, 5, device=dev, dtype=torch.float32)
+        if d_rows is not None:
+            full[actx.idx] = d_rows.float()
+        g_ts = (d_ts if d_ts is not None else torch.zeros((), device=dev)).reshape(1).float().contiguous()
+        g_att = d_att.reshape(1).float().contiguous() if (actx.has_att and d_att is not None) else None
+        flat = eng.backward(actx.saved, full, g_ts, g_att)
+        actx.saved = None
+        grads = tuple(flat[o:o + int(torch.Size(eng.shapes[n]).numel())].view(eng.shapes[n]) for n, o in eng.offsets.items())
+        return (None, None, None) + grads
+
+
+class Trainer:
+    """One-process-per-GPU training step: ``step(batch)`` = forward, losses, backward, gradient all-reduce (when
+    ``torch.distributed`` is initialised), global-norm clip + Adam (main.py:53-66, 204-212) without a host read.
+
+    The parameters are re-pointed at views of one flat buffer (like DDP's buckets) so that clip + Adam is one kernel and the
+    gradient of a step is one contiguous tensor - the single collective of data-parallel training (SUM: the losses are sums
+    over examples, so the summed gradient is the large-batch gradient)."""
+
+    def __init__(self, model, lr: float = 1e-3, wd: float = 3e-7, clip: float = 10.0, att_weight: float = 0.1, ts_weight: float = 0.5,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model, self.engine = model, TrainEngine(model)
+        dev = next(model.parameters()).device
+        self.flat = torch.zeros(self.engine.n_params, device=dev, dtype=torch.float32)
+        for n, p in model.named_parameters():
+            o = self.engine.offsets[n]
+            self.flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+            p.data = self.flat[o:o + p.numel()].view(p.shape)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.lr, self.wd, self.clip, self.betas, self.eps = lr, wd, clip, betas, eps
+        self.g_ts = torch.full((1,), ts_weight, device=dev)
+        self.g_att = torch.full((1,), att_weight, device=dev)
+        self.att_weight, self.ts_weight = att_weight, ts_weight
+        self.steps = 0
+        self.last_grad = None
+
+    def step(self, batch, att_offsets=None) -> dict:
+        eng = self.engine
+        out = eng.forward(batch, att_offsets)
+        n = batch.qas_bert.shape[0]
+        cls, d_rows = T.answer_ce(out["answer_rows"], out["row_valid"], out["row_target"], n)
+        grad = eng.backward(out["ctx"], d_rows, self.g_ts, self.g_att if out["att_loss"] is not None else None)
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM)
+        self.steps += 1
+        ss = torch.zeros(1, device=grad.device)
+        T.grad_sumsq(grad, ss)
+        T.adam_step(self.flat, grad, self.m, self.v, ss, max_norm=self.clip, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                    eps=self.eps, wd=self.wd, step=self.steps)
+        self.model.invalidate_weight_cache()  # the eval kernels' packed weight images are keyed on the version counter
+        self.last_grad = grad
+        loss = cls[0] + self.ts_weight * out["temporal_loss"]
+        if out["att_loss"] is not None:
+            loss = loss + self.att_weight * out["att_loss"]
+        return dict(loss=loss, cls_loss=cls[0], n_rows=cls[1], n_correct=cls[2], temporal_loss=out["temporal_loss"],
+                    att_loss=out["att_loss"], grad_sumsq=ss)
