@@ -35,7 +35,9 @@ SHAPE = dict(T=300, R=20, Lq=100, Ls=100)
 # BASELINE.json configs: cfg2 = configs[1] (the headline line), cfg5 = configs[4] (long-context stress)
 CONFIGS = {"cfg2": dict(T=300, R=20, Lq=100, Ls=100, batch=32, name="configs[1]"),
            "cfg5": dict(T=600, R=40, Lq=100, Ls=100, batch=8, name="configs[4] long-context"),
-           "cfg1": dict(T=40, R=25, Lq=40, Ls=50, batch=2, name="configs[0] debug shapes")}
+           "cfg1": dict(T=40, R=25, Lq=40, Ls=50, batch=2, name="configs[0] debug shapes"),
+           # configs[2] / configs[3]: full train step (forward + backward + clip + Adam [+ NCCL gradient all-reduce when N > 1])
+           "cfg3": dict(T=300, R=20, Lq=100, Ls=100, batch=16, name="configs[2] train step", train=True)}
 H = 128
 
 
@@ -159,6 +161,224 @@ def cpu_port(batch, opt, sd, steps, warmup, threads, device="cpu"):
     return times, out
 
 
+def cpu_train_port(batch, opt, sd, steps, warmup, threads, device="cpu"):
+    """One training step of the reference's loop (main.py:53-66) on the oracle port with torch autograd: forward, the three
+    losses, backward, clip_grad_norm_(10), Adam(lr 1e-3, wd 3e-7).  Returns the step times."""
+    import torch.nn.functional as F
+    from oracle import stage_oracle as O
+    torch.set_num_threads(threads)
+    ref = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(".pe") else v.clone()) for k, v in sd.items()}
+    params = [v for v in ref.values() if v.requires_grad]
+    optim = torch.optim.Adam(params, lr=1e-3, weight_decay=3e-7)
+    n = len(batch["qid"])
+    times = []
+    for i in range(warmup + steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.enable_grad():
+            out = O.stage_forward.__wrapped__(ref, opt, batch, training=True)
+            loss = F.cross_entropy(out["answer"], out["target"], reduction="sum") * (1.0 * n / len(out["target"])) + 0.5 * out["temporal_loss"]
+            if batch.get("att_labels") is not None:
+                loss = loss + 0.1 * O.get_att_loss(out["vid_raw_s"], batch["att_labels"], batch["target"], batch["anno_st_idx"],
+                                                   opt.num_negatives, opt.att_loss_type, opt.alpha, opt.margin)
+        optim.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        optim.step()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def train_main(args, cfg, rank, local_rank, world, cores):
+    """--config cfg3: examples/s of the full training step (BASELINE.json configs[2]; configs[3] when launched on N > 1 GPUs:
+    one NCCL SUM all-reduce of the flat gradient buffer per step)."""
+    from tvqaplus_b200 import host
+    from tvqaplus_b200.model import STAGE
+    shape = {k: cfg[k] for k in ("T", "R", "Lq", "Ls")}
+    T, R, Lq, Ls = shape["T"], shape["R"], shape["Lq"], shape["Ls"]
+    N = args.batch or cfg["batch"]
+    metric = "QA-examples/sec full train step (forward+backward+clip+Adam%s; synthetic T=%d,R=%d,L=%d,H=128)" % (
+        "+NCCL grad all-reduce" if world > 1 else "", T, R, Lq)
+    opt = host.default_opt(dropout=0.0)
+    config = dict(workload="%s: train mode, add_local, use_sup_att, sub+vfeat, heads=0, dropout=0 (the training kernels have no dropout), "
+                           "batch=%d/GPU, T=%d, R=%d, Lq=%d, Ls=%d, H=128, dense masks; fp32 throughout (the reference's dtype; BASELINE says bf16)"
+                  % (cfg["name"] if world == 1 else "configs[3] data-parallel train step", N, T, R, Lq, Ls),
+                  global_batch=N * world, per_gpu_batch=N,
+                  parallelism="dp%d (one process per GPU, %s)" % (world, "NCCL SUM all-reduce of the flat 2.2 MB gradient buffer" if world > 1 else "no collective"),
+                  l2="activations (tens of GB per step) exceed the 126 MB L2; no flush needed")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        W = max(1, min(args.warmup, 1))
+        torch.manual_seed(2018)
+        sd = STAGE(opt).state_dict()
+        one = take_examples(make_host_batch(2, False, shape), [0])
+        one["att_labels"], one["anno_st_idx"] = host.synthetic_att_labels(one, seed=1)
+        times = cpu_train_port(one, opt, sd, args.steps, W, cores)
+        v = 1.0 / statistics.mean(times)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "examples/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": W, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(config, sample="1 example of the shape per step"),
+                          "cpu_baseline": {"value": v, "unit": "examples/s", "cores": cores, "kind": "port",
+                                           "sample": "CPU oracle port + torch autograd + clip + Adam, 1 example/step, %d steps" % args.steps},
+                          "e2e": {"value": v, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    from tvqaplus_b200 import _lib, ops
+    from tvqaplus_b200.train import Trainer
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the STAGE kernels)")
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.lib()
+    torch.manual_seed(2018)
+    model = STAGE(opt).to(dev).train()
+    trainer = Trainer(model)
+    hbatch = make_host_batch(N, pin=True, shape=shape)
+    hbatch["target"] = (hbatch["target"] + rank) % 5  # ranks see different examples
+    hbatch["att_labels"], hbatch["anno_st_idx"] = host.synthetic_att_labels(hbatch, seed=1 + rank)
+    dbatch = to_device(hbatch, dev)
+    for k in ("att_labels", "anno_st_idx"):
+        dbatch[k] = hbatch[k]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def one_step(b):
+        # the sampled (positive, negative) pairs are drawn on the host every step, like the reference (model/stage.py:613-694)
+        pos, neg = model._att_pairs(b["att_labels"], hbatch["target"], b["anno_st_idx"], model.num_negatives, False, model.drop_topk)
+        return trainer.step(b, trainer.engine.att_offsets_from_pairs(pos, neg, N, T, Lq, R), graph=not args.no_graph)
+
+    from tvqaplus_b200 import train_ops
+    losses = []
+    ops.LAUNCHES = train_ops.LAUNCHES = 0
+    losses.append(float(one_step(dbatch)["loss"]))  # eager, and (with graphs) the capture of the step for the replays below
+    per_step_launches = (ops.LAUNCHES + train_ops.LAUNCHES) // (1 if args.no_graph else 2)
+    for _ in range(args.warmup - 1):
+        losses.append(float(one_step(dbatch)["loss"]))
+    barrier()
+    peak0 = torch.cuda.max_memory_allocated(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            last = one_step(dbatch)["loss"]
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = N * world * args.steps / (ms_total * 1e-3)
+    losses.append(float(last))
+
+    # end to end: the batch travels from pinned host memory every step, the loss is read back every step
+    e2e = None
+    if not args.no_e2e:
+        copy_stream, main_stream = torch.cuda.Stream(), torch.cuda.current_stream()
+        bufs = [{k: torch.empty_like(dbatch[k]) for k in TENSOR_KEYS} for _ in range(2)]
+        for b in bufs:
+            b["ts_label"] = dbatch["ts_label"]
+        ready, freed = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.empty(1).pin_memory()
+        h2d = sum(hbatch[k].numel() * hbatch[k].element_size() for k in TENSOR_KEYS)
+
+        def run_e2e(steps):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(copy_stream):
+                s0.record()
+                to_device(hbatch, dev, non_blocking=True, into=bufs[0])
+                ready[0].record()
+            for i in range(steps):
+                cur = i % 2
+                if i + 1 < steps:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(freed[1 - cur])
+                        to_device(hbatch, dev, non_blocking=True, into=bufs[1 - cur])
+                        ready[1 - cur].record()
+                main_stream.wait_event(ready[cur])
+                b = host.Batch(hbatch)
+                b.update(bufs[cur])
+                res = one_step(b)
+                loss_host.copy_(res["loss"].reshape(1), non_blocking=True)
+                freed[cur].record()
+            s1.record()
+            torch.cuda.synchronize()
+            return s0.elapsed_time(s1)
+
+        run_e2e(2)
+        barrier()
+        ms_e2e = max_over_ranks(run_e2e(args.steps))
+        barrier()
+        e2e = {"value": N * world * args.steps / (ms_e2e * 1e-3), "unit": "examples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / args.steps,
+               "note": "pinned host inputs, double-buffered H2D on a copy stream, the loss read back every step"}
+        del bufs
+
+    pk = peaks()
+    flops = 3 * alg_flops_total(N, T, R, Lq, Ls)  # forward + two gradient products per contraction
+    achieved = flops * args.steps / (ms_total * 1e-3) / 1e12 if world == 1 else flops * world * args.steps / (ms_total * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "sgemm_kernel (all GEMMs of the step)", "achieved": achieved / world, "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / world / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "note": "per GPU; algorithmic FLOPs of the step = 3 x forward (%.1f GFLOP/example); the training GEMMs run in exact fp32 "
+                        "on the CUDA cores (FFMA peak of a B200 is ~75 TFLOP/s), not on the tensor cores" % (flops / N / 1e9)}
+    cpu = eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        one = take_examples(hbatch, [0])
+        one["att_labels"], one["anno_st_idx"] = [hbatch["att_labels"][0]], [hbatch["anno_st_idx"][0]]
+        times = cpu_train_port(one, opt, sd_cpu, 2, 1, cores)
+        cpu = {"value": 1.0 / statistics.mean(times), "unit": "examples/s", "cores": cores, "kind": "port",
+               "sample": "CPU oracle port + torch autograd + clip + Adam on example 0 of the timed batch, 1 warm-up + 2 timed steps"}
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            sd_dev = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            del trainer
+            torch.cuda.empty_cache()
+            nb = min(N, 8)
+            sub = take_examples(hbatch, list(range(nb)))
+            sub["att_labels"], sub["anno_st_idx"] = hbatch["att_labels"][:nb], hbatch["anno_st_idx"][:nb]
+            sub = to_device(sub, dev)
+            sub["att_labels"], sub["anno_st_idx"] = hbatch["att_labels"][:nb], hbatch["anno_st_idx"][:nb]
+            times = cpu_train_port(sub, opt, sd_dev, 2, 1, cores, device="cuda")
+            eager = {"value": nb / statistics.mean(times), "unit": "examples/s", "ms_per_step": 1e3 * statistics.mean(times), "batch": nb, "kind": "port",
+                     "note": "the oracle port with torch autograd, clip_grad_norm_ and torch.optim.Adam, eager on this GPU, fp32 with "
+                             "allow_tf32=False, batch %d (autograd keeps every intermediate: batch 16 needs ~93 GB), 1 warm-up + 2 timed" % nb}
+        except Exception as e:
+            eager = {"unavailable": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": config, "clocks": clk.summary(), "e2e": e2e,
+                          "gpu_launches": per_step_launches * args.steps,
+                          "launch_mode": "eager (one Python call per kernel)" if args.no_graph else "the whole step replayed from one CUDA graph (%d kernel launches per step)" % per_step_launches,
+                          "roofline": roofline, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
+                          "loss_first_last": [losses[0], losses[-1]], "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,12 +391,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train configs: launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     cfg = CONFIGS[args.config]
+    if cfg.get("train"):
+        return train_main(args, cfg, rank, local_rank, world, cores)
     shape = {k: cfg[k] for k in ("T", "R", "Lq", "Ls")}
     T, R, Lq, Ls = shape["T"], shape["R"], shape["Lq"], shape["Ls"]
     N = args.batch or cfg["batch"]

@@ -79,6 +79,11 @@ typedef struct {
   const float* ln_out_b;
   float* y;              /* [m,n] */
   long long* timeline;   /* optional debug: [32][8] SM clock stamps of CTA 0 (tools/linear_timeline.py), else NULL */
+  int64_t ldy;           /* row stride of y in floats; 0 = n (y may be a column slice of a wider tensor) */
+  const float* x_rowmax; /* optional [m] = max |x| of every row (stage_row_absmax): each row is scaled by an exact power of two
+                            into fp16's normal range in front of the split and its result scaled back - for gradient tensors
+                            (dX = dY W in the backward), whose rows sit far below 6e-5 and orders of magnitude apart.
+                            Not with LN_in / l2norm_in. */
 } StageLinearArgs;
 int stage_linear_fwd(const StageLinearArgs* a, void* stream);
 
@@ -310,6 +315,8 @@ int stage_ln_fwd(const float* x, const float* g, const float* b, float* y, float
  * dg += sum dy*xhat, db += sum dy.  dx may be NULL (parameter gradients only); add may alias dx. */
 int stage_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* g, const float* add, float* dx,
                  float* dg, float* db, int64_t rows, int d, int relu_x, void* stream);
+/* out[r] = max_c |x[r, c]| */
+int stage_row_absmax(const float* x, int64_t rows, int d, float* out, void* stream);
 /* out[c] += sum_r x[r*ld + c] (bias gradients) */
 int stage_colsum(const float* x, int64_t rows, int d, int64_t ld, float* out, void* stream);
 int stage_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
@@ -356,9 +363,11 @@ int stage_answer_ce(const float* rows, const int32_t* valid, const int64_t* row_
 /* out[0] += sum g^2 (caller zeroes out): the global norm of clip_grad_norm_ (main.py:65) */
 int stage_grad_sumsq(const float* g, int64_t n, float* out, void* stream);
 /* clip (coef = min(1, max_norm / (sqrt(*sumsq)*grad_scale + 1e-6)); max_norm <= 0: off) + torch.optim.Adam with L2 weight
- * decay on flat buffers (main.py:209-212); bc1 = 1 - beta1^step, bc2 = 1 - beta2^step.  g is left holding the clipped grad. */
+ * decay on flat buffers (main.py:209-212); bc1 = 1 - beta1^step, bc2 = 1 - beta2^step - or, with step_dev != NULL, computed
+ * from the device-resident step count (so the launch can sit in a CUDA graph).  g is left holding the clipped grad. */
 int stage_adam_step(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm, float lr, float beta1, float beta2,
-                    float eps, float wd, float bc1, float bc2, float grad_scale, void* stream);
+                    float eps, float wd, float bc1, float bc2, float grad_scale, const int32_t* step_dev, void* stream);
+int stage_counter_inc(int32_t* counter, void* stream);
 
 /* ---- UMMA layout probe (test-only; pins the descriptor conventions the kernels rely on) ------------------------------ */
 typedef struct {

@@ -111,3 +111,45 @@ def test_att_loss_restatement_matches_live_reference(loss_type):
     torch.manual_seed(7)
     got = O.get_att_loss(scores, labels, batch.target, starts, 2, loss_type, opt.alpha, opt.margin)
     assert torch.equal(want, got)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference not present on this host")
+def test_oracle_gradients_match_live_reference_training_step():
+    """The training parity tests compare the CUDA backward with autograd of the oracle; this pins that oracle: the unmodified
+    reference in train mode (dropout 0, use_sup_att) with main.py:53-61's loss, ``loss.backward()`` - loss and every
+    parameter gradient bit-identical to autograd through the restatement."""
+    import contextlib
+    import io
+    import torch.nn.functional as F
+    from oracle.make_golden import load_reference
+    ref_stage = load_reference()
+    opt = O.default_opt(dropout=0.0, use_sup_att=True)
+    torch.manual_seed(2018)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_stage.STAGE(opt)
+    ref.train()
+    N = 3
+    batch = O.make_synthetic_batch(N, 12, 9, 10, 8, seed=4)
+    batch["att_labels"], batch["anno_st_idx"] = O.make_att_labels(batch, seed=1)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+
+    torch.manual_seed(7)
+    (out, target), att_loss, _, t_loss, _ = ref(batch)
+    loss = F.cross_entropy(out, target, reduction="sum") * (1.0 * N / len(target)) + 0.1 * att_loss + 0.5 * t_loss
+    loss.backward()
+
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(".pe") else v.clone()) for k, v in sd.items()}
+    with torch.enable_grad():
+        mine = O.stage_forward.__wrapped__(sdg, opt, batch, training=True)
+        torch.manual_seed(7)
+        att = O.get_att_loss(mine["vid_raw_s"], batch.att_labels, batch.target, batch.anno_st_idx, opt.num_negatives,
+                             opt.att_loss_type, opt.alpha, opt.margin)
+        mine_loss = (F.cross_entropy(mine["answer"], mine["target"], reduction="sum") * (1.0 * N / len(mine["target"]))
+                     + 0.1 * att + 0.5 * mine["temporal_loss"])
+        mine_loss.backward()
+    assert torch.equal(mine_loss.detach(), loss.detach())
+    n = 0
+    for k, p in ref.named_parameters():
+        assert p.grad is not None and torch.allclose(sdg[k].grad, p.grad, rtol=0, atol=1e-6 * float(p.grad.abs().max()) + 1e-12), k
+        n += 1
+    assert n == 70

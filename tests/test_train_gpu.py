@@ -136,3 +136,37 @@ def test_trainer_step_matches_reference_training_loop():
         got = model(H.batch_to(batches[0], torch.device("cuda:0")))[0].cpu()
     want = O.stage_forward({k: v.detach() for k, v in ref.items()}, opt, batches[0])["answer"]
     assert H.max_rel(got, want) < 5e-3
+
+
+def test_graph_replay_equals_eager_steps():
+    """Trainer.step(graph=True): the first call runs eagerly and records the step; the following ones replay the CUDA graph
+    on new data of the same geometry.  Same parameters as three eager steps (up to the order of the atomic accumulations)."""
+    from tvqaplus_b200.train import Trainer
+    opt = O.default_opt(dropout=0.0, use_sup_att=True)
+    dev = torch.device("cuda:0")
+    batches = []
+    for s_ in (1, 2, 3):
+        b = O.make_synthetic_batch(3, 10, 6, 8, 9, seed=s_)
+        b["att_labels"], b["anno_st_idx"] = O.make_att_labels(batch=b, seed=4)  # same label geometry -> same number of pairs
+        batches.append(b)
+    finals = []
+    for use_graph in (False, True):
+        model, sd = _model_and_state(opt)
+        model = model.to(dev).train()
+        tr = Trainer(model)
+        for i, b in enumerate(batches):
+            torch.manual_seed(100 + i)
+            pos, neg = model._att_pairs(b["att_labels"], b["target"], b["anno_st_idx"], model.num_negatives, False, model.drop_topk)
+            offs = tr.engine.att_offsets_from_pairs(pos, neg, 3, 10, 8, 6)
+            res = tr.step(H.batch_to(b, dev), offs, graph=use_graph)
+            loss = float(res["loss"])
+            assert loss == loss
+        finals.append({k: p.detach().cpu().clone() for k, p in model.named_parameters()})
+        if use_graph:
+            assert len(tr._graphs) == 1 and tr.steps == 3 and int(tr.step_dev.item()) == 3
+    for k in finals[0]:
+        if k in ZERO_GRAD_BIASES:
+            continue
+        upd = float((finals[0][k] - sd[k]).norm())
+        err = float((finals[1][k] - finals[0][k]).norm())
+        assert err <= 0.02 * upd + 1e-7, "%s: graph vs eager %.3e, update %.3e" % (k, err, upd)

@@ -234,3 +234,19 @@ def test_adam_step_matches_torch_optimizer():
         T.grad_sumsq(g, ss)
         T.adam_step(p, g, m, v, ss, max_norm=10.0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, wd=3e-7, step=step)
         _close(p, ref.detach(), 1e-6)
+
+
+@pytest.mark.parametrize("m,n,k,gscale", [(5000, 128, 384, 1e-6), (4100, 300, 768, 3e-9), (4500, 128, 128, 1.0), (4099, 128, 300, 1e-4)])
+def test_tensor_core_linear_pair_for_training(m, n, k, gscale):
+    """lin_fwd / lin_bwd_x of the training engine on the tcgen05 kernel: forward at fp32 grade, and the input gradient of a
+    tensor whose entries are far below fp16's normal range (the power-of-two scaling through x_absmax)."""
+    from tvqaplus_b200.train import lin_bwd_x, lin_fwd
+    _ops()
+    g = torch.Generator(device="cuda").manual_seed(n + k)
+    x = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) * 0.1
+    b = torch.randn(n, device="cuda", generator=g)
+    _close(lin_fwd(x, w, b, relu=True), F.relu(F.linear(x, w, b)), 3e-5)
+    dy = torch.randn(m, n, device="cuda", generator=g) * gscale
+    dy[::7] *= 1e-3  # rows three orders of magnitude below the tensor's maximum
+    _close(lin_bwd_x(dy, w), dy @ w, 3e-5)

@@ -20,7 +20,7 @@ _f = C.c_void_p  # device pointers travel as integers
 class LinearArgs(C.Structure):
     _fields_ = [("m", C.c_int64), ("k", C.c_int), ("n", C.c_int), ("kc", C.c_int), ("l2norm_in", C.c_int),
                 ("relu", C.c_int), ("x", _f), ("w_packed", _f), ("bias", _f), ("ln_in_cs", _f), ("ln_in_cb", _f),
-                ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f), ("timeline", _f)]
+                ("ln_out_g", _f), ("ln_out_b", _f), ("y", _f), ("timeline", _f), ("ldy", C.c_int64), ("x_rowmax", _f)]
 
 
 class EncoderArgs(C.Structure):
@@ -114,6 +114,7 @@ SYMBOLS = {
     "stage_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "stage_ln_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "stage_ln_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "stage_row_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "stage_colsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "stage_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stage_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
@@ -135,7 +136,8 @@ SYMBOLS = {
     "stage_att_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stage_answer_ce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stage_grad_sumsq": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "stage_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "stage_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "stage_counter_inc": (C.c_int, [C.c_void_p, C.c_void_p]),
     "stage_umma_probe": (C.c_int, [C.POINTER(ProbeArgs), C.c_void_p]),
 }
 

@@ -76,7 +76,16 @@ struct LinearDev {
   long long* timeline;    // optional debug: [32 tiles][8] SM clock stamps of block 0 (tools/linear_timeline.py)
   int out_blocked;        // 1: y is written as [m / rows_per_block][n / 4][rows_per_block] float4 (see cqa.cuh, Za)
   int rows_per_block;
+  long long ldy;          // row stride of y in floats (>= n; a column slice of a wider tensor)
+  const float* x_rowmax;  // optional [m]: max |x| of every row; the row is multiplied by 2^-ceil(log2(max)) in front of the fp16
+                          // split and its result scaled back - gradient rows sit far below fp16's normal range and differ by
+                          // orders of magnitude from row to row
 };
+
+// exact power-of-two scale that brings a row's largest magnitude into (0.5, 1]
+__device__ __forceinline__ float pow2_scale(float m) {
+  return (m > 0.f && m < 3.0e38f) ? exp2f(-ceilf(log2f(m))) : 1.f;
+}
 
 template <int NPAD, int KC, int STAGES>
 __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) linear_kernel(LinearDev p) {
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
       const uint32_t trow = tbase + b * Cfg::ACC_STRIDE + ((qw * 32u) << 16);
       // input-side scalars of my row:  pre[c] = ga * acc[c] + gm * cs[c] + cb[c]   (acc is the GEMM of the SHIFTED row x - c)
       float ga = 1.f, gm = 0.f;
+      if (p.x_rowmax != nullptr && row0 + lane < p.m) ga = 1.f / pow2_scale(__ldg(p.x_rowmax + row0 + lane));
       if (need_stats) {
         const uint32_t sb = tile_it & 1u;
         const float s1 = row_s1[sb][r], s2 = row_s2[sb][r], c = row_c[sb][r];
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
       {
         // after the 32x32 transpose lane = (row % 4 group, 4-column slot); its 8 rows' output offsets are fixed per tile
         const int c4 = lane & 7, rsub = lane >> 3;
-        const bool vec_ok = p.out_blocked || (p.n & 3) == 0;
+        const bool vec_ok = p.out_blocked || ((p.n & 3) == 0 && (p.ldy & 3) == 0);
         long long off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
             const long long bk = gr / p.rows_per_block;
             off[i] = (bk * (p.n >> 2) * p.rows_per_block + (gr - bk * p.rows_per_block)) * 4;
           } else {
-            off[i] = gr * p.n;
+            off[i] = gr * p.ldy;
           }
         }
         const int cmul = p.out_blocked ? p.rows_per_block * 4 : 4;
@@ -329,6 +339,9 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
     const long long total = my_tiles * p.n_chunks;  // flat (tile, chunk) sequence of this CTA
 
     float4 buf[PREF][NI][2];
+    float xsr[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) xsr[i] = 1.f;
     const bool wide = (p.k & 7) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 31u) == 0;  // rows and slots are 32-byte aligned
     long long ptl = 0;  // (tile, chunk) of the next prefetch
     int pc = 0;
@@ -404,6 +417,14 @@ __global__ void __launch_bounds__((LinearCfg<NPAD, KC, STAGES>::THREADS), 1) lin
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
             float2 v0 = lo2(buf[d][i][0]), v1 = hi2(buf[d][i][0]), v2 = lo2(buf[d][i][1]), v3 = hi2(buf[d][i][1]);
+            if (p.x_rowmax != nullptr) {
+              if (c == 0) {
+                const long long gr = (blockIdx.x + tl * gridDim.x) * 128 + rbase + i * (256 / K8);
+                xsr[i] = gr < p.m ? pow2_scale(__ldg(p.x_rowmax + gr)) : 1.f;
+              }
+              const float2 xs2 = dup2(xsr[i]);
+              v0 = mul2(v0, xs2); v1 = mul2(v1, xs2); v2 = mul2(v2, xs2); v3 = mul2(v3, xs2);
+            }
             if (need_stats) {
               if (c == 0) {
                 // with LN_in the row is shifted by its first element (held by the k8 == 0 lane) BEFORE it meets the tensor

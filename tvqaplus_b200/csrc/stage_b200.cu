@@ -152,6 +152,10 @@ int stage_linear_fwd(const StageLinearArgs* a, void* stream) {
   d.ln_out_g = a->ln_out_g; d.ln_out_b = a->ln_out_b;
   d.y = a->y; d.m = a->m; d.k = a->k; d.n = a->n; d.n_chunks = g.n_chunks; d.l2norm_in = a->l2norm_in; d.relu = a->relu;
   d.out_blocked = 0; d.rows_per_block = 1; d.timeline = a->timeline;
+  d.ldy = a->ldy > 0 ? a->ldy : a->n;
+  d.x_rowmax = a->x_rowmax;
+  STG_REQUIRE(d.ldy >= a->n, STAGE_E_BADARG, "linear: ldy=%lld < n=%d", (long long)d.ldy, a->n);
+  STG_REQUIRE(a->x_rowmax == nullptr || (a->ln_in_cs == nullptr && !a->l2norm_in), STAGE_E_UNSUPPORTED, "linear: x_rowmax cannot be combined with LN_in / l2norm_in");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->n <= 128) return launch_linear<128, 64, 2>(d, s);
   return launch_linear<304, 32, 3>(d, s);
@@ -317,6 +321,7 @@ int stage_cqa_fused_fwd(const StageCqaArgs* a, void* stream) {
     d.x = a->a_embed; d.w = wb + WB_WA; d.bias = vec + 512; d.cs = nullptr; d.cb = nullptr;
     d.ln_out_g = nullptr; d.ln_out_b = nullptr; d.y = za; d.m = static_cast<long long>(a->n) * 5 * a->lq;
     d.k = 128; d.n = 128; d.n_chunks = 2; d.l2norm_in = 0; d.relu = 0; d.out_blocked = 1; d.rows_per_block = 5 * a->lq; d.timeline = nullptr;
+    d.ldy = 128; d.x_rowmax = nullptr;
     int rc = launch_linear<128, 64, 2>(d, s);
     if (rc) return rc;
   }

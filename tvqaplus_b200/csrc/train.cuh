@@ -173,6 +173,105 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(GemmDev d) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int LN_MAXPL = 24;
 
+// ---- d % 128 == 0 (128, 256, 384, 768): NV float4 per lane, lane l holds columns (i*32 + l)*4 .. +3
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ g, const float4* __restrict__ b,
+                                                         float4* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o, long long rows) {
+  constexpr int D4 = NV * 32;
+  const int lane = threadIdx.x & 31;
+  const float inv_d = 1.f / (D4 * 4);
+  float4 gv[NV], bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { gv[i] = __ldg(g + i * 32 + lane); bv[i] = __ldg(b + i * 32 + lane); }
+  const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = w0; r < rows; r += nw) {
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = __ldg(x + r * D4 + i * 32 + lane);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = wsum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = 1.f / sqrtf(wsum(q) * inv_d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      y[r * D4 + i * 32 + lane] = make_float4(v[i].x * rstd * gv[i].x + bv[i].x, v[i].y * rstd * gv[i].y + bv[i].y,
+                                              v[i].z * rstd * gv[i].z + bv[i].z, v[i].w * rstd * gv[i].w + bv[i].w);
+    if (lane == 0) { mean_o[r] = mean; rstd_o[r] = rstd; }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float* __restrict__ mean_i,
+                                                         const float* __restrict__ rstd_i, const float4* __restrict__ g, const float4* add,
+                                                         float4* dx, float* __restrict__ dg, float* __restrict__ db, long long rows, int relu_x) {
+  constexpr int D4 = NV * 32;
+  __shared__ float sg[D4 * 4], sb[D4 * 4];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float inv_d = 1.f / (D4 * 4);
+  for (int c = tid; c < D4 * 4; c += 256) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  float4 gv[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gv[i] = __ldg(g + i * 32 + lane);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + tid) >> 5, nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = w0; r < rows; r += nw) {
+    const float mean = __ldg(mean_i + r), rstd = __ldg(rstd_i + r);
+    float4 xh[NV], dg_[NV];
+    float s1 = 0.f, s2 = 0.f;
+    unsigned pm = 0u;  // x > 0 per held column (the ReLU mask when x is a ReLU output)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 xv = __ldg(x + r * D4 + i * 32 + lane), dv = __ldg(dy + r * D4 + i * 32 + lane);
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      dg_[i] = make_float4(dv.x * gv[i].x, dv.y * gv[i].y, dv.z * gv[i].z, dv.w * gv[i].w);
+      s1 += (dg_[i].x + dg_[i].y) + (dg_[i].z + dg_[i].w);
+      s2 += (dg_[i].x * xh[i].x + dg_[i].y * xh[i].y) + (dg_[i].z * xh[i].z + dg_[i].w * xh[i].w);
+      ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+      ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      pm |= ((xv.x > 0.f ? 1u : 0u) | (xv.y > 0.f ? 2u : 0u) | (xv.z > 0.f ? 4u : 0u) | (xv.w > 0.f ? 8u : 0u)) << (4 * i);
+    }
+    if (dx != nullptr) {
+      const float c1 = wsum(s1) * inv_d, c2 = wsum(s2) * inv_d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 o = make_float4(rstd * (dg_[i].x - c1 - xh[i].x * c2), rstd * (dg_[i].y - c1 - xh[i].y * c2),
+                               rstd * (dg_[i].z - c1 - xh[i].z * c2), rstd * (dg_[i].w - c1 - xh[i].w * c2));
+        if (relu_x) {
+          const unsigned b4 = pm >> (4 * i);
+          o.x = (b4 & 1u) ? o.x : 0.f; o.y = (b4 & 2u) ? o.y : 0.f; o.z = (b4 & 4u) ? o.z : 0.f; o.w = (b4 & 8u) ? o.w : 0.f;
+        }
+        if (add != nullptr) {
+          const float4 a = add[r * D4 + i * 32 + lane];
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        dx[r * D4 + i * 32 + lane] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    atomicAdd(sg + c, ag[i].x); atomicAdd(sg + c + 1, ag[i].y); atomicAdd(sg + c + 2, ag[i].z); atomicAdd(sg + c + 3, ag[i].w);
+    atomicAdd(sb + c, ab[i].x); atomicAdd(sb + c + 1, ab[i].y); atomicAdd(sb + c + 2, ab[i].z); atomicAdd(sb + c + 3, ab[i].w);
+  }
+  __syncthreads();
+  for (int c = tid; c < D4 * 4; c += 256) { atomicAdd(dg + c, sg[c]); atomicAdd(db + c, sb[c]); }
+}
+
+// ---- any d <= 768 (300): scalar columns, PL per lane
+template <int PL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                                                      float* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o,
                                                      long long rows, int d) {
@@ -180,10 +279,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = w0; r < rows; r += nw) {
     const float* xr = x + r * d;
-    float v[LN_MAXPL];
+    float v[PL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXPL; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       v[i] = c < d ? __ldg(xr + c) : 0.f;
       s += v[i];
@@ -191,7 +290,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float mean = wsum(s) / d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXPL; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       const float e = c < d ? v[i] - mean : 0.f;
       q += e * e;
@@ -199,7 +298,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float rstd = 1.f / sqrtf(wsum(q) / d + 1e-5f);
     float* yr = y + r * d;
 #pragma unroll
-    for (int i = 0; i < LN_MAXPL; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       if (c < d) yr[c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
     }
@@ -209,17 +308,18 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 
 // dx = [add +] rstd*(dy*g - mean(dy*g) - xhat*mean(dy*g*xhat)) [* (x > 0)], dg += sum dy*xhat, db += sum dy.
 // relu_x: x is the output of a ReLU whose input gradient is wanted (the mask is x > 0).
+template <int PL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_i,
                                                      const float* __restrict__ rstd_i, const float* __restrict__ g, const float* add,
                                                      float* dx, float* __restrict__ dg, float* __restrict__ db, long long rows, int d,
                                                      int relu_x) {
-  __shared__ float sg[768], sb[768];
+  __shared__ float sg[PL * 32], sb[PL * 32];
   const int tid = threadIdx.x, lane = tid & 31;
   for (int c = tid; c < d; c += 256) { sg[c] = 0.f; sb[c] = 0.f; }
   __syncthreads();
-  float ag[LN_MAXPL], ab[LN_MAXPL], gv[LN_MAXPL];
+  float ag[PL], ab[PL], gv[PL];
 #pragma unroll
-  for (int i = 0; i < LN_MAXPL; ++i) {
+  for (int i = 0; i < PL; ++i) {
     ag[i] = 0.f; ab[i] = 0.f;
     const int c = lane + 32 * i;
     gv[i] = c < d ? __ldg(g + c) : 0.f;
@@ -227,10 +327,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const long long w0 = (static_cast<long long>(blockIdx.x) * blockDim.x + tid) >> 5, nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long r = w0; r < rows; r += nw) {
     const float mean = __ldg(mean_i + r), rstd = __ldg(rstd_i + r);
-    float xh[LN_MAXPL], dg_[LN_MAXPL];
+    float xh[PL], dg_[PL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXPL; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       const float xv = c < d ? __ldg(x + r * d + c) : mean, dv = c < d ? __ldg(dy + r * d + c) : 0.f;
       xh[i] = (xv - mean) * rstd;
@@ -243,7 +343,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     if (dx != nullptr) {
       const float c1 = wsum(s1) / d, c2 = wsum(s2) / d;
 #pragma unroll
-      for (int i = 0; i < LN_MAXPL; ++i) {
+      for (int i = 0; i < PL; ++i) {
         const int c = lane + 32 * i;
         if (c < d) {
           float o = rstd * (dg_[i] - c1 - xh[i] * c2);
@@ -255,12 +355,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAXPL; ++i) {
+  for (int i = 0; i < PL; ++i) {
     const int c = lane + 32 * i;
     if (c < d) { atomicAdd(sg + c, ag[i]); atomicAdd(sb + c, ab[i]); }
   }
   __syncthreads();
   for (int c = tid; c < d; c += 256) { atomicAdd(dg + c, sg[c]); atomicAdd(db + c, sb[c]); }
+}
+
+// out[r] = max_c |x[r, c]|: one warp per row
+__global__ void __launch_bounds__(256) row_absmax_kernel(const float* __restrict__ x, long long rows, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    float m = 0.f;
+    for (int c = lane; c < d; c += 32) m = fmaxf(m, fabsf(__ldg(x + r * d + c)));
+    m = wmax(m);
+    if (lane == 0) out[r] = m;
+  }
 }
 
 // out[c] += sum over rows of x[r, c] (bias gradients)
@@ -715,11 +826,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     atomicAdd(out, t);
   }
 }
+__global__ void counter_inc_kernel(int* c) { *c += 1; }
 // clip coefficient = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_); torch.optim.Adam with weight_decay
 // (grad += wd * p), bias corrections passed in as bc1 = 1 - beta1^t, bc2 = 1 - beta2^t.
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                             const float* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2, float eps, float wd,
-                            float bc1, float bc2, float grad_scale) {
+                            float bc1, float bc2, float grad_scale, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {  // step count kept on the device: the launch can be replayed from a CUDA graph
+    const float t = static_cast<float>(__ldg(step_dev));
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
   float coef = grad_scale;
   if (max_norm > 0.f) {
     const float nrm = sqrtf(__ldg(sumsq)) * grad_scale;

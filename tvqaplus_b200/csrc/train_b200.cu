@@ -54,7 +54,17 @@ int stage_gemm(const StageGemmArgs* a, void* stream) {
 int stage_ln_fwd(const float* x, const float* g, const float* b, float* y, float* mean, float* rstd, int64_t rows, int d, void* stream) {
   STG_REQUIRE(x && g && b && y && mean && rstd, STAGE_E_BADARG, "ln_fwd: null pointer");
   STG_REQUIRE(rows > 0 && d > 0 && d <= 768, STAGE_E_UNSUPPORTED, "ln_fwd: rows=%lld d=%d (d <= 768)", (long long)rows, d);
-  ln_fwd_kernel<<<grid_for(rows, 8), 256, 0, S(stream)>>>(x, g, b, y, mean, rstd, rows, d);
+  const int grid = grid_for(rows, 8);
+  cudaStream_t s = S(stream);
+  const bool vec = d % 128 == 0 && aligned16(x) && aligned16(y) && aligned16(g) && aligned16(b);
+  auto X = reinterpret_cast<const float4*>(x), G = reinterpret_cast<const float4*>(g), B = reinterpret_cast<const float4*>(b);
+  auto Y = reinterpret_cast<float4*>(y);
+  if (vec && d == 128) ln_fwd_vec_kernel<1><<<grid, 256, 0, s>>>(X, G, B, Y, mean, rstd, rows);
+  else if (vec && d == 256) ln_fwd_vec_kernel<2><<<grid, 256, 0, s>>>(X, G, B, Y, mean, rstd, rows);
+  else if (vec && d == 384) ln_fwd_vec_kernel<3><<<grid, 256, 0, s>>>(X, G, B, Y, mean, rstd, rows);
+  else if (vec && d == 768) ln_fwd_vec_kernel<6><<<grid, 256, 0, s>>>(X, G, B, Y, mean, rstd, rows);
+  else if (d <= 320) ln_fwd_kernel<10><<<grid, 256, 0, s>>>(x, g, b, y, mean, rstd, rows, d);
+  else ln_fwd_kernel<LN_MAXPL><<<grid, 256, 0, s>>>(x, g, b, y, mean, rstd, rows, d);
   return check_launch("ln_fwd");
 }
 int stage_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* g, const float* add, float* dx,
@@ -62,9 +72,24 @@ int stage_ln_bwd(const float* dy, const float* x, const float* mean, const float
   STG_REQUIRE(dy && x && mean && rstd && g && dg && db, STAGE_E_BADARG, "ln_bwd: null pointer");
   STG_REQUIRE(rows > 0 && d > 0 && d <= 768, STAGE_E_UNSUPPORTED, "ln_bwd: rows=%lld d=%d (d <= 768)", (long long)rows, d);
   const long long want = (rows + 63) / 64;  // at least 8 rows per warp: the column sums end in atomics
-  const int grid = static_cast<int>(want < 1 ? 1 : (want < num_sms() * 4 ? want : num_sms() * 4));
-  ln_bwd_kernel<<<grid, 256, 0, S(stream)>>>(dy, x, mean, rstd, g, add, dx, dg, db, rows, d, relu_x);
+  const int grid = static_cast<int>(want < 1 ? 1 : (want < num_sms() * 8 ? want : num_sms() * 8));
+  cudaStream_t s = S(stream);
+  const bool vec = d % 128 == 0 && aligned16(x) && aligned16(dy) && aligned16(g) && (!add || aligned16(add)) && (!dx || aligned16(dx));
+  auto DY = reinterpret_cast<const float4*>(dy), X = reinterpret_cast<const float4*>(x), G = reinterpret_cast<const float4*>(g);
+  auto AD = reinterpret_cast<const float4*>(add);
+  auto DX = reinterpret_cast<float4*>(dx);
+  if (vec && d == 128) ln_bwd_vec_kernel<1><<<grid, 256, 0, s>>>(DY, X, mean, rstd, G, AD, DX, dg, db, rows, relu_x);
+  else if (vec && d == 256) ln_bwd_vec_kernel<2><<<grid, 256, 0, s>>>(DY, X, mean, rstd, G, AD, DX, dg, db, rows, relu_x);
+  else if (vec && d == 384) ln_bwd_vec_kernel<3><<<grid, 256, 0, s>>>(DY, X, mean, rstd, G, AD, DX, dg, db, rows, relu_x);
+  else if (vec && d == 768) ln_bwd_vec_kernel<6><<<grid, 256, 0, s>>>(DY, X, mean, rstd, G, AD, DX, dg, db, rows, relu_x);
+  else if (d <= 320) ln_bwd_kernel<10><<<grid, 256, 0, s>>>(dy, x, mean, rstd, g, add, dx, dg, db, rows, d, relu_x);
+  else ln_bwd_kernel<LN_MAXPL><<<grid, 256, 0, s>>>(dy, x, mean, rstd, g, add, dx, dg, db, rows, d, relu_x);
   return check_launch("ln_bwd");
+}
+int stage_row_absmax(const float* x, int64_t rows, int d, float* out, void* stream) {
+  STG_REQUIRE(x && out && rows > 0 && d > 0, STAGE_E_BADARG, "row_absmax: bad argument");
+  row_absmax_kernel<<<grid_for(rows, 8), 256, 0, S(stream)>>>(x, rows, d, out);
+  return check_launch("row_absmax");
 }
 int stage_colsum(const float* x, int64_t rows, int d, int64_t ld, float* out, void* stream) {
   STG_REQUIRE(x && out, STAGE_E_BADARG, "colsum: null pointer");
@@ -195,10 +220,15 @@ int stage_grad_sumsq(const float* g, int64_t n, float* out, void* stream) {
   return check_launch("grad_sumsq");
 }
 int stage_adam_step(float* p, float* g, float* m, float* v, int64_t n, const float* sumsq, float max_norm, float lr, float beta1, float beta2,
-                    float eps, float wd, float bc1, float bc2, float grad_scale, void* stream) {
+                    float eps, float wd, float bc1, float bc2, float grad_scale, const int32_t* step_dev, void* stream) {
   STG_REQUIRE(p && g && m && v && n > 0 && (max_norm <= 0.f || sumsq), STAGE_E_BADARG, "adam_step: bad argument");
-  adam_kernel<<<grid_for(n, 1024), 256, 0, S(stream)>>>(p, g, m, v, n, sumsq, max_norm, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale);
+  adam_kernel<<<grid_for(n, 1024), 256, 0, S(stream)>>>(p, g, m, v, n, sumsq, max_norm, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, step_dev);
   return check_launch("adam_step");
+}
+int stage_counter_inc(int32_t* counter, void* stream) {
+  STG_REQUIRE(counter, STAGE_E_BADARG, "counter_inc: null pointer");
+  counter_inc_kernel<<<1, 1, 0, S(stream)>>>(counter);
+  return check_launch("counter_inc");
 }
 
 }  // extern "C"

@@ -56,6 +56,28 @@ def synthetic_batch(N: int, T: int, R: int, Lq: int, Ls: int, *, seed: int = 201
                  image_indices=None, boxes=None, use_hard_negatives=False, eval_object_word_ids=None)
 
 
+def synthetic_att_labels(batch: Dict[str, Any], n_img_max: int = 4, seed: int = 0, density: float = 0.08):
+    """Synthetic ``att_labels`` / ``anno_st_idx`` for a synthetic batch, in the form tvqa_dataset.py:362-420 builds them from the
+    bounding-box annotations: per example a few annotated frames inside the clip, each a (Lq_valid, R_valid) 0/1 matrix."""
+    g = torch.Generator().manual_seed(seed)
+    n = batch["qas_mask"].shape[0]
+    labels, starts = [], []
+    for b in range(n):
+        n_frames = int(batch["ts_label_mask"][b].sum())
+        n_img = int(torch.randint(1, min(n_img_max, n_frames) + 1, (1,), generator=g))
+        st = int(torch.randint(0, n_frames - n_img + 1, (1,), generator=g))
+        q_len = int(batch["qas_mask"][b, int(batch["target"][b])].sum())
+        cur = []
+        for i in range(n_img):
+            r_valid = max(2, int(batch["vid_mask"][b, st + i].sum()))
+            lab = (torch.rand(q_len, r_valid, generator=g) < density).float()
+            lab[0, 0], lab[0, 1] = 1.0, 0.0  # at least one positive and one negative on one word
+            cur.append(lab)
+        labels.append(cur)
+        starts.append(st)
+    return labels, starts
+
+
 def batch_to(batch: Dict[str, Any], device, non_blocking: bool = False) -> Batch:
     """``prepare_inputs``' final ``.to(device)`` step (tvqa_dataset.py:660-688) for an already padded batch."""
     out = Batch(batch)

@@ -94,7 +94,8 @@ def pack_weight_ln(w: torch.Tensor, bias: torch.Tensor, ln_g: torch.Tensor, ln_b
 @_guarded
 def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], n: int, *, kc: Optional[int] = None,
                ln_in=None, ln_out=None, l2norm_in: bool = False, relu: bool = False,
-               timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
+               timeline: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, ldy: int = 0, y_off: int = 0,
+               x_rowmax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = LN_out(relu?(LN_in(l2norm?(x)) W^T + b)) over the last axis of x (stage_linear_fwd).
 
     ``ln_in`` is the (cs, cb) pair ``pack_weight_ln`` returned together with ``w_packed`` (the LayerNorm is folded into
@@ -102,12 +103,13 @@ def linear_fwd(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Ten
     x = _f32(x)
     k = x.shape[-1]
     m = x.numel() // k
-    y = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device)
+    y = torch.empty(x.shape[:-1] + (n,), dtype=torch.float32, device=x.device) if out is None else out
     a = _lib.LinearArgs(m=m, k=k, n=n, kc=kc or kc_for(n), l2norm_in=int(l2norm_in), relu=int(relu),
                         x=ptr(x), w_packed=ptr(w_packed), bias=ptr(_f32(bias)) if bias is not None else None,
                         ln_in_cs=ptr(_f32(ln_in[0])) if ln_in else None, ln_in_cb=ptr(_f32(ln_in[1])) if ln_in else None,
                         ln_out_g=ptr(_f32(ln_out[0])) if ln_out else None,
-                        ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y), timeline=ptr(timeline))
+                        ln_out_b=ptr(_f32(ln_out[1])) if ln_out else None, y=ptr(y) + 4 * y_off, timeline=ptr(timeline),
+                        ldy=ldy, x_rowmax=ptr(x_rowmax))
     check(lib().stage_linear_fwd(C.byref(a), current_stream()), "stage_linear_fwd")
     _count()
     return y

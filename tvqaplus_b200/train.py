@@ -29,6 +29,42 @@ from . import ops
 from . import train_ops as T
 
 
+TC_MIN_ROWS = 4096  # below this the exact fp32 CUDA-core GEMM is as fast as a tensor-core launch
+
+
+def _zeros(n, device):
+    return torch.zeros(n, device=device, dtype=torch.float32)
+
+
+def lin_fwd(x, w, b, relu=False):
+    """y = x W^T + b: the split-fp16 tcgen05 kernel of the inference path (csrc/linear.cuh, fp32-grade: three fp16 products,
+    fp32 accumulation) for the large row counts, the exact fp32 GEMM otherwise."""
+    m, k = x.shape
+    n = w.shape[0]
+    if m >= TC_MIN_ROWS and k % 4 == 0 and k <= 768 and 8 <= n <= 304:
+        return ops.linear_fwd(x, ops.pack_weight(w), b, n, relu=relu)
+    return T.linear(x, w, b, relu=relu)
+
+
+def lin_bwd_x(dy, w):
+    """dx = dy W (W is [N, K]): the same tensor-core kernel with the transposed weight, column chunks of at most 256 outputs
+    written as slices of dx.  Every gradient row is scaled by an exact power of two into fp16's normal range first
+    (x_rowmax: one max pass over dy) - the rows are far below 6e-5 and orders of magnitude apart."""
+    m, n = dy.shape
+    k = w.numel() // n
+    if not (m >= TC_MIN_ROWS and n % 4 == 0 and n <= 768 and k % 4 == 0):
+        return T.linear_bwd_x(dy, w)
+    wt = w.reshape(n, k).t().contiguous()  # [K, N]: row c = the weights of output column c of dx
+    step = 128 if k % 128 == 0 and k <= 384 else (256 if k > 304 else k)
+    dx = torch.empty(m, k, device=dy.device, dtype=torch.float32)
+    rmax = T.row_absmax(dy)
+    zero = _zeros(step, dy.device)
+    for c0 in range(0, k, step):
+        c1 = min(k, c0 + step)
+        ops.linear_fwd(dy, ops.pack_weight(wt[c0:c1].contiguous()), zero[:c1 - c0], c1 - c0, out=dx, ldy=k, y_off=c0, x_rowmax=rmax)
+    return dx
+
+
 class TrainEngine:
     def __init__(self, model):
         self.model = model
@@ -57,9 +93,9 @@ class TrainEngine:
     # ---------------------------------------------------------------------------------------------- input projections
     def _fc_fwd(self, P, x, pre):
         h0, s0 = T.ln_fwd(x, P[pre + ".0.weight"], P[pre + ".0.bias"])
-        r1 = T.linear(h0, P[pre + ".2.weight"], P[pre + ".2.bias"], relu=True)
+        r1 = lin_fwd(h0, P[pre + ".2.weight"], P[pre + ".2.bias"], relu=True)
         h1, s1 = T.ln_fwd(r1, P[pre + ".4.weight"], P[pre + ".4.bias"])
-        r2 = T.linear(h1, P["input_embedding.1.weight"], P["input_embedding.1.bias"], relu=True)
+        r2 = lin_fwd(h1, P["input_embedding.1.weight"], P["input_embedding.1.bias"], relu=True)
         e0, s2 = T.ln_fwd(r2, P["input_embedding.3.weight"], P["input_embedding.3.bias"])
         return e0, (x, h0, s0, r1, h1, s1, r2, s2, pre)
 
@@ -67,10 +103,10 @@ class TrainEngine:
         x, h0, s0, r1, h1, s1, r2, s2, pre = sv
         dz2 = T.ln_bwd(de0, r2, s2, P["input_embedding.3.weight"], G["input_embedding.3.weight"], G["input_embedding.3.bias"], relu_x=True)
         T.linear_bwd_w(dz2, h1, G["input_embedding.1.weight"], G["input_embedding.1.bias"])
-        dh1 = T.linear_bwd_x(dz2, P["input_embedding.1.weight"])
+        dh1 = lin_bwd_x(dz2, P["input_embedding.1.weight"])
         dz1 = T.ln_bwd(dh1, r1, s1, P[pre + ".4.weight"], G[pre + ".4.weight"], G[pre + ".4.bias"], relu_x=True)
         T.linear_bwd_w(dz1, h0, G[pre + ".2.weight"], G[pre + ".2.bias"])
-        dh0 = T.linear_bwd_x(dz1, P[pre + ".2.weight"])
+        dh0 = lin_bwd_x(dz1, P[pre + ".2.weight"])
         T.ln_bwd(dh0, x, s0, P[pre + ".0.weight"], G[pre + ".0.weight"], G[pre + ".0.bias"], want_dx=False)
 
     # ---------------------------------------------------------------------------------------------- encoder blocks
@@ -87,7 +123,7 @@ class TrainEngine:
                 nrm, st = T.ln_fwd(cur, P["%s.layer_norm.%d.weight" % (blk, i)], P["%s.layer_norm.%d.bias" % (blk, i)])
                 dw = T.dwconv_fwd(nrm, P["%s.conv.%d.depthwise_conv.weight" % (blk, i)], P["%s.conv.%d.depthwise_conv.bias" % (blk, i)],
                                   n_seq, L, ksize)
-                pw = T.linear(dw, P["%s.conv.%d.pointwise_conv.weight" % (blk, i)], P["%s.conv.%d.pointwise_conv.bias" % (blk, i)], relu=True)
+                pw = lin_fwd(dw, P["%s.conv.%d.pointwise_conv.weight" % (blk, i)].reshape(128, 128), P["%s.conv.%d.pointwise_conv.bias" % (blk, i)], relu=True)
                 nxt = T.add(pw, cur)
                 convs.append((cur, st, nrm, dw, pw))
                 cur = nxt
@@ -106,7 +142,7 @@ class TrainEngine:
                 pwn, dwn, lnn = "%s.conv.%d.pointwise_conv" % (blk, i), "%s.conv.%d.depthwise_conv" % (blk, i), "%s.layer_norm.%d" % (blk, i)
                 dpw = T.relu_bwd(d, pw)
                 T.linear_bwd_w(dpw, dw, G[pwn + ".weight"], G[pwn + ".bias"])
-                ddw = T.linear_bwd_x(dpw, P[pwn + ".weight"])
+                ddw = lin_bwd_x(dpw, P[pwn + ".weight"].reshape(128, 128))
                 dn = T.dwconv_bwd(ddw, nrm, P[dwn + ".weight"], G[dwn + ".weight"], G[dwn + ".bias"], n_seq, L, k)
                 d = T.ln_bwd(dn, cur, st, P[lnn + ".weight"], G[lnn + ".weight"], G[lnn + ".bias"], add=d, out=d)
         return d  # the position table has no gradient
@@ -124,7 +160,7 @@ class TrainEngine:
                c_b=(ai * Tn * 128, 128))
         cat = T.cat3_fwd(C, U, Tn)
         l, st = T.ln_fwd(cat, P["c2q_down_projection.0.weight"], P["c2q_down_projection.0.bias"])
-        att = T.linear(l, P["c2q_down_projection.2.weight"], P["c2q_down_projection.2.bias"], relu=True)
+        att = lin_fwd(l, P["c2q_down_projection.2.weight"], P["c2q_down_projection.2.bias"], relu=True)
         return att, S, (C, Cn, Q, Qn, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale)
 
     def _cqa_bwd(self, P, G, datt, sv, dC, dCn, att_grad=None):
@@ -132,7 +168,7 @@ class TrainEngine:
         ai, dev = 5 * Lq, C.device
         dpre = T.relu_bwd(datt, att, out=datt)
         T.linear_bwd_w(dpre, l, G["c2q_down_projection.2.weight"], G["c2q_down_projection.2.bias"])
-        dl = T.linear_bwd_x(dpre, P["c2q_down_projection.2.weight"])
+        dl = lin_bwd_x(dpre, P["c2q_down_projection.2.weight"])
         dcat = T.ln_bwd(dl, cat, st, P["c2q_down_projection.0.weight"], G["c2q_down_projection.0.weight"], G["c2q_down_projection.0.bias"], out=dl)
         dU = T.cat3_bwd(dcat, C, U, dC, Tn, True)
         del dcat, dl
@@ -190,7 +226,7 @@ class TrainEngine:
         # 3. concat_fc (model/stage.py:276-279), then the reference's (n, a, t, i) row order for the cls encoder
         cat2 = T.cat3_fwd(att_s, att_v, 1)
         l2, st2 = T.ln_fwd(cat2, P["concat_fc.0.weight"], P["concat_fc.0.bias"])
-        r = T.linear(l2, P["concat_fc.2.weight"], P["concat_fc.2.bias"], relu=True)
+        r = lin_fwd(l2, P["concat_fc.2.weight"], P["concat_fc.2.bias"], relu=True)
         stm, st4 = T.ln_fwd(r, P["concat_fc.4.weight"], P["concat_fc.4.bias"])
         ctx["cat"] = (att_s, att_v, cat2, l2, st2, r, st4)
         stm_p = T.permute_it(stm, N * 5, Lq, Tn)
@@ -207,7 +243,7 @@ class TrainEngine:
         # 5. residual temporal predictor, span scores, temporal loss (model/stage.py:469-482,521,539-555)
         pj, stl, edl, cl = "cls_projection_layers.0.conv", "temporal_scoring_st_layers.0.conv", "temporal_scoring_ed_layers.0.conv", "classifier.conv"
         l0, s0 = T.ln_fwd(ms, P[pj + ".0.weight"], P[pj + ".0.bias"])
-        p0 = T.linear(l0, P[pj + ".2.weight"], P[pj + ".2.bias"], relu=True)
+        p0 = lin_fwd(l0, P[pj + ".2.weight"], P[pj + ".2.bias"], relu=True)
         x1 = T.add(ms, p0)
         ls, sst = T.ln_fwd(x1, P[stl + ".0.weight"], P[stl + ".0.bias"])
         le, sed = T.ln_fwd(x1, P[edl + ".0.weight"], P[edl + ".0.bias"])
@@ -269,7 +305,7 @@ class TrainEngine:
         # residual projection
         dp0 = T.relu_bwd(dx1, p0)
         T.linear_bwd_w(dp0, l0, G[pj + ".2.weight"], G[pj + ".2.bias"])
-        dl0 = T.linear_bwd_x(dp0, P[pj + ".2.weight"])
+        dl0 = lin_bwd_x(dp0, P[pj + ".2.weight"])
         dms = T.ln_bwd(dl0, ms, s0, P[pj + ".0.weight"], G[pj + ".0.weight"], G[pj + ".0.bias"], add=dx1)
 
         # max-pool, cls encoder, back to (n, a, i, t)
@@ -282,7 +318,7 @@ class TrainEngine:
         att_s, att_v, cat2, l2, st2, r, st4 = ctx["cat"]
         dr2 = T.ln_bwd(dstm, r, st4, P["concat_fc.4.weight"], G["concat_fc.4.weight"], G["concat_fc.4.bias"], relu_x=True, out=dstm)
         T.linear_bwd_w(dr2, l2, G["concat_fc.2.weight"], G["concat_fc.2.bias"])
-        dl2 = T.linear_bwd_x(dr2, P["concat_fc.2.weight"])
+        dl2 = lin_bwd_x(dr2, P["concat_fc.2.weight"])
         dcat2 = T.ln_bwd(dl2, cat2, st2, P["concat_fc.0.weight"], G["concat_fc.0.weight"], G["concat_fc.0.bias"], out=dl2)
         datt_s = torch.empty_like(att_s)
         datt_v = T.cat3_bwd(dcat2, att_s, att_v, datt_s, 1, False)
@@ -360,9 +396,12 @@ class Trainer:
         self.g_att = torch.full((1,), att_weight, device=dev)
         self.att_weight, self.ts_weight = att_weight, ts_weight
         self.steps = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)  # the step count Adam's bias corrections use
         self.last_grad = None
+        self._graphs = {}
 
-    def step(self, batch, att_offsets=None) -> dict:
+    # ---- one step, eager: every kernel launched from Python (about 360 launches)
+    def _step_core(self, batch, att_offsets):
         eng = self.engine
         out = eng.forward(batch, att_offsets)
         n = batch.qas_bert.shape[0]
@@ -370,15 +409,59 @@ class Trainer:
         grad = eng.backward(out["ctx"], d_rows, self.g_ts, self.g_att if out["att_loss"] is not None else None)
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM)
-        self.steps += 1
         ss = torch.zeros(1, device=grad.device)
         T.grad_sumsq(grad, ss)
+        T.counter_inc(self.step_dev)
         T.adam_step(self.flat, grad, self.m, self.v, ss, max_norm=self.clip, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                    eps=self.eps, wd=self.wd, step=self.steps)
-        self.model.invalidate_weight_cache()  # the eval kernels' packed weight images are keyed on the version counter
-        self.last_grad = grad
+                    eps=self.eps, wd=self.wd, step_dev=self.step_dev)
         loss = cls[0] + self.ts_weight * out["temporal_loss"]
         if out["att_loss"] is not None:
             loss = loss + self.att_weight * out["att_loss"]
         return dict(loss=loss, cls_loss=cls[0], n_rows=cls[1], n_correct=cls[2], temporal_loss=out["temporal_loss"],
-                    att_loss=out["att_loss"], grad_sumsq=ss)
+                    att_loss=out["att_loss"], grad_sumsq=ss, grad=grad)
+
+    _STATIC = ("qas_bert", "sub_bert", "vid", "qas_mask", "sub_mask", "vid_mask", "ts_label_mask", "target")
+
+    def _capture(self, batch, att_offsets):
+        """Record the whole step (forward, losses, backward, all-reduce, clip + Adam) into a CUDA graph over static copies of
+        the inputs; nothing executes during the capture."""
+        from .host import Batch
+        static = Batch(batch)
+        for k in self._STATIC:
+            static[k] = batch[k].clone()
+        static["ts_label"] = {k: v.clone() for k, v in batch["ts_label"].items()}
+        offs = None if att_offsets is None else tuple(o.to(self.flat.device, torch.int64).contiguous().clone() for o in att_offsets)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._step_core(static, offs)
+        return static, offs, g, out
+
+    def step(self, batch, att_offsets=None, graph: bool = False) -> dict:
+        """``graph=True``: the step is replayed from a CUDA graph captured for this batch geometry (the first call with a new
+        geometry runs eagerly and records the graph for the following ones).  The returned tensors of a replay are the
+        graph's static outputs: read them before the next step."""
+        if not graph:
+            out = self._step_core(batch, att_offsets)
+        else:
+            key = tuple(tuple(batch[k].shape) for k in self._STATIC) + (None if att_offsets is None else int(att_offsets[0].numel()),)
+            rec = self._graphs.get(key)
+            if rec is None:
+                out = self._step_core(batch, att_offsets)
+                self._graphs[key] = self._capture(batch, att_offsets)
+            else:
+                static, offs, g, out = rec
+                for k in self._STATIC:
+                    if static[k].data_ptr() != batch[k].data_ptr():
+                        static[k].copy_(batch[k], non_blocking=True)
+                for k, v in batch["ts_label"].items():
+                    static["ts_label"][k].copy_(v, non_blocking=True)
+                if offs is not None:
+                    for dst, src in zip(offs, att_offsets):
+                        dst.copy_(src, non_blocking=True)
+                g.replay()
+        self.steps += 1
+        self.model.invalidate_weight_cache()  # the eval kernels' packed weight images are keyed on the version counter
+        self.last_grad = out["grad"]
+        return out

@@ -11,7 +11,15 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, current_stream, lib, on_device
+from ._lib import GemmArgs, current_stream, lib, on_device
+
+LAUNCHES = 0  # kernels launched through this module (bench.py's gpu_launches claim for the training step)
+
+
+def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.check(rc, what)
 
 
 def _p(t: Optional[torch.Tensor], off: int = 0) -> Optional[int]:
@@ -70,6 +78,14 @@ def linear_bwd_w(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Option
     if db is not None:
         with on_device(dy, db):
             check(lib().stage_colsum(_p(dy, dy_off), m, n, ld, _p(db), current_stream()), "stage_colsum")
+
+
+def row_absmax(x: torch.Tensor) -> torch.Tensor:
+    rows, d = x.shape
+    out = torch.empty(rows, device=x.device, dtype=torch.float32)
+    with on_device(x):
+        check(lib().stage_row_absmax(_p(x), rows, d, _p(out), current_stream()), "stage_row_absmax")
+    return out
 
 
 def ln_fwd(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
@@ -251,9 +267,15 @@ def grad_sumsq(g, out):
     return out
 
 
-def adam_step(p, g, m, v, sumsq, *, max_norm: float, lr: float, beta1: float, beta2: float, eps: float, wd: float, step: int,
-              grad_scale: float = 1.0):
+def adam_step(p, g, m, v, sumsq, *, max_norm: float, lr: float, beta1: float, beta2: float, eps: float, wd: float, step: int = 1,
+              grad_scale: float = 1.0, step_dev: Optional[torch.Tensor] = None):
+    """``step_dev``: int32 device tensor holding the step count (bias corrections computed on the device; graph-capturable)."""
     bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
     with on_device(p, g, m, v):
         check(lib().stage_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq), max_norm, lr, beta1, beta2, eps, wd, bc1,
-                                    bc2, grad_scale, current_stream()), "stage_adam_step")
+                                    bc2, grad_scale, _p(step_dev), current_stream()), "stage_adam_step")
+
+
+def counter_inc(c: torch.Tensor):
+    with on_device(c):
+        check(lib().stage_counter_inc(_p(c), current_stream()), "stage_counter_inc")
