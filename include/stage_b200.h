@@ -324,6 +324,11 @@ int stage_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* 
 int stage_add(const float* a, const float* b, float* y, int64_t n, int64_t period, void* stream);
 /* x *= (*scalar) * mult: chain rule with a device-resident upstream gradient, no host read */
 int stage_scale(float* x, int64_t n, const float* scalar, float mult, void* stream);
+/* nn.Dropout / F.dropout in train mode (inverted dropout): y[i] = keep(i) ? x[i] / (1 - p) : 0 with
+ * keep(i) = hash(seed_dev[0], seed_dev[1], site, i) >= p * 2^32 (seed_dev: two int32 on the device - the run's seed and the
+ * forward-call counter; `site` names the dropout module).  Stateless: the backward applies the same call to the gradient.
+ * y may alias x.  The distribution is the reference's, the random stream is not torch's. */
+int stage_dropout(const float* x, float* y, int64_t n, float p, const int32_t* seed_dev, uint32_t site, void* stream);
 /* (groups, I, T, d) -> (groups, T, I, d) */
 int stage_permute_it(const float* x, float* y, int64_t groups, int i_dim, int t_dim, int d, void* stream);
 /* depthwise Conv1d(groups = d, padding = k/2) of DepthwiseSeparableConv (model/cnn.py:25-28), d = 128, odd k <= 7 */

@@ -28,6 +28,17 @@ import torch.nn.functional as F
 
 NEG = -1e10  # model/model_utils.py:14-15 and model/context_query_attention.py:100
 
+# Train-mode dropout (the reference's nn.Dropout / F.dropout sites): torch's random stream cannot be shared with the CUDA path,
+# so the oracle takes the masks from the caller - ``DROP(tag, x)`` returns x with the site's mask applied (tests build the
+# masks with the product's own generator and check loss + gradients against autograd through this restatement).  None = eval
+# / dropout 0.  ``DROP_PREFIX`` names the stream ("q", "s", "v", "c") the shared modules are currently applied to.
+DROP = None
+DROP_PREFIX = ""
+
+
+def _drop(tag, x):
+    return x if DROP is None else DROP(tag, x)
+
 
 # ----------------------------------------------------------------------------------------------
 # options / synthetic data
@@ -165,9 +176,12 @@ def multi_headed_attention(x: torch.Tensor, mask: Optional[torch.Tensor], sd, pr
 def encoder_block(x: torch.Tensor, mask: torch.Tensor, sd, prefix: str, n_conv: int, k: int, nh: int) -> torch.Tensor:
     """PE → n_conv×[LN → DWSepConv → +res] → optional [LN → MHA → +res] → LN — model/encoder.py:29-52 (eval: no dropout)."""
     out = x + sd[prefix + ".position_encoding.pe"][: x.shape[-2], :]
+    blk = prefix.rsplit(".", 1)[-1]
     for i in range(n_conv):
         res = out
         out = _ln(out, sd, "%s.layer_norm.%d" % (prefix, i))
+        if i % 2 == 0:  # model/encoder.py:41-42
+            out = _drop("%s.enc.%s.%d" % (DROP_PREFIX, blk, i), out)
         out = depthwise_separable_conv(out, sd, "%s.conv.%d" % (prefix, i), k)
         out = out + res
     if nh != 0:
@@ -187,21 +201,21 @@ def stacked_encoder(x, mask, sd, prefix: str, n_blocks: int, n_conv: int, k: int
 
 def text_init_fc(x, sd):
     """bert_word_encoding_fc: LN768 → Lin768→300 → ReLU → LN300 — model/stage.py:85-91."""
-    y = _ln(x, sd, "bert_word_encoding_fc.0")
+    y = _drop(DROP_PREFIX + ".fc", _ln(x, sd, "bert_word_encoding_fc.0"))
     y = F.relu(_lin(y, sd, "bert_word_encoding_fc.2"))
     return _ln(y, sd, "bert_word_encoding_fc.4")
 
 
 def vid_init_fc(x, sd):
     """vid_fc: LN300 → Lin300→300 → ReLU → LN300 — model/stage.py:98-104."""
-    y = _ln(x, sd, "vid_fc.0")
+    y = _drop(DROP_PREFIX + ".fc", _ln(x, sd, "vid_fc.0"))
     y = F.relu(_lin(y, sd, "vid_fc.2"))
     return _ln(y, sd, "vid_fc.4")
 
 
 def input_embedding(x, sd):
     """Lin300→128 → ReLU → LN128 — model/stage.py:115-120."""
-    return _ln(F.relu(_lin(x, sd, "input_embedding.1")), sd, "input_embedding.3")
+    return _ln(F.relu(_lin(_drop(DROP_PREFIX + ".emb", x), sd, "input_embedding.1")), sd, "input_embedding.3")
 
 
 def base_encoder(x, mask, sd, opt, kind: str):
@@ -218,8 +232,8 @@ def structured_attention(C, Q, c_mask, q_mask, scale: float):
     C (N,5,1|Li,Lqa,D), Q (N,1,Li,Lr,D), c_mask (N,5,1|Li,Lqa), q_mask (N,1,Li,Lr)
     → A (N,5,Li,Lqa,D), S (masked raw cosine), S_mask, S_ (masked softmax weights).
     """
-    Cn = F.normalize(C, p=2, dim=-1)
-    Qn = F.normalize(Q, p=2, dim=-1)
+    Cn = _drop(DROP_PREFIX + ".cn", F.normalize(C, p=2, dim=-1))  # context_query_attention.py:95-96
+    Qn = _drop(DROP_PREFIX + ".qn", F.normalize(Q, p=2, dim=-1))
     S_mask = torch.matmul(c_mask.unsqueeze(-1), q_mask.unsqueeze(-2))
     S = torch.matmul(Cn, Qn.transpose(-2, -1))
     S = S - 1e10 * (1 - S_mask)
@@ -234,7 +248,7 @@ def qa_ctx_attention(qa_embed, ctx_embed, qa_mask, ctx_mask, sd, opt):
     u_a, raw_s, s_mask, s_norm = structured_attention(qa_embed, ctx_embed, qa_mask, ctx_mask, opt.scale)
     qa_rep = qa_embed.repeat(1, 1, num_img, 1, 1)
     mixed = torch.cat([qa_rep, u_a, qa_rep * u_a], dim=-1)
-    mixed = F.relu(_lin(_ln(mixed, sd, "c2q_down_projection.0"), sd, "c2q_down_projection.2"))
+    mixed = F.relu(_lin(_drop(DROP_PREFIX + ".c2q", _ln(mixed, sd, "c2q_down_projection.0")), sd, "c2q_down_projection.2"))
     mixed_mask = (s_mask.sum(-1) != 0).float()
     return mixed, mixed_mask, raw_s, s_norm
 
@@ -242,13 +256,17 @@ def qa_ctx_attention(qa_embed, ctx_embed, qa_mask, ctx_mask, sd, opt):
 def concat_fc(sub_mix, vid_mix, sd):
     """cat[s, v, s⊙v] → LN384 → Lin384→128 → ReLU → LN128 — model/stage.py:107-113,276-279."""
     x = torch.cat([sub_mix, vid_mix, sub_mix * vid_mix], dim=-1)
-    x = F.relu(_lin(_ln(x, sd, "concat_fc.0"), sd, "concat_fc.2"))
+    x = F.relu(_lin(_drop("cat", _ln(x, sd, "concat_fc.0")), sd, "concat_fc.2"))
     return _ln(x, sd, "concat_fc.4")
+
+
+_WRAPPER_TAGS = {"cls_projection_layers.0": "proj", "temporal_scoring_st_layers.0": "st", "temporal_scoring_ed_layers.0": "ed",
+                 "classifier": "cls"}
 
 
 def linear_wrapper(x, sd, prefix: str, relu: bool):
     """LN → (dropout) → Linear [→ ReLU] — model/stage.py:15-32 (layer_norm=True)."""
-    y = _lin(_ln(x, sd, prefix + ".conv.0"), sd, prefix + ".conv.2")
+    y = _lin(_drop(_WRAPPER_TAGS.get(prefix, prefix), _ln(x, sd, prefix + ".conv.0")), sd, prefix + ".conv.2")
     return F.relu(y) if relu else y
 
 
@@ -418,8 +436,10 @@ def stage_forward(sd: Dict[str, torch.Tensor], opt, batch, training: bool = Fals
     ``answer`` (N|N_new,5), ``target``, ``t_scores`` (masked raw logits, N,5,T,2), ``t_probs`` (softmax over T),
     ``temporal_loss``; with ``keep=True`` also the intermediates used by the kernel-level parity tests.
     """
+    global DROP_PREFIX
     bsz, num_a, hsz = len(batch.qid), 5, opt.hsz
     inter: dict = {}
+    DROP_PREFIX = "q"
     a_embed = base_encoder(batch.qas_bert.view(bsz * num_a, -1, opt.embedding_size),
                            batch.qas_mask.view(bsz * num_a, -1), sd, opt, "text")
     a_embed = a_embed.view(bsz, num_a, 1, -1, hsz)
@@ -427,6 +447,7 @@ def stage_forward(sd: Dict[str, torch.Tensor], opt, batch, training: bool = Fals
     att_sub = att_vid = att_vid_mask = att_sub_mask = None
     if opt.sub_flag:
         T, Ls = batch.sub_bert.shape[1:3]
+        DROP_PREFIX = "s"
         sub_embed = base_encoder(batch.sub_bert.view(bsz * T, Ls, -1), batch.sub_mask.view(bsz * T, Ls), sd, opt, "text")
         sub_embed = sub_embed.contiguous().view(bsz, 1, T, Ls, -1)
         att_sub, att_sub_mask, sub_raw_s, sub_norm_s = qa_ctx_attention(
@@ -435,6 +456,7 @@ def stage_forward(sd: Dict[str, torch.Tensor], opt, batch, training: bool = Fals
             inter.update(sub_embed=sub_embed, sub_raw_s=sub_raw_s, sub_normalized_s=sub_norm_s, attended_sub=att_sub)
     if opt.vfeat_flag:
         T, R = batch.vid.shape[1:3]
+        DROP_PREFIX = "v"
         v = F.normalize(batch.vid, p=2, dim=-1)  # model/stage.py:256
         vid_embed = base_encoder(v.view(bsz * T, R, -1), batch.vid_mask.view(bsz * T, R), sd, opt, "vid")
         vid_embed = vid_embed.contiguous().view(bsz, 1, T, R, -1)
@@ -451,6 +473,7 @@ def stage_forward(sd: Dict[str, torch.Tensor], opt, batch, training: bool = Fals
     else:
         statement, statement_mask = att_vid, att_vid_mask
     head_inter = {} if keep else None
+    DROP_PREFIX = "c"
     answer, target, t_scores = classifier_head(statement, statement_mask, batch.target, batch.ts_label,
                                                batch.ts_label_mask, sd, opt, training, head_inter)
     out = dict(answer=answer, target=target, t_scores=t_scores, t_probs=F.softmax(t_scores, dim=2),

@@ -71,10 +71,14 @@ def test_position_table_matches_oracle():
 
 
 def test_train_mode_with_dropout_fails_loudly():
-    """dropout > 0 in train mode needs the reference's RNG stream: refused, never approximated."""
+    """dropout > 0 in train mode exists only in the training engine (gradients enabled, CUDA tensors): without gradients it
+    is refused, and with them a CPU batch fails like every other call - never a silent CPU path."""
+    import torch
     from tvqaplus_b200.model import STAGE
     m = STAGE(O.default_opt()).train()
-    with pytest.raises(NotImplementedError, match="dropout"):
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="dropout"):
+        m(O.make_synthetic_batch(1, 2, 2, 3, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
         m(O.make_synthetic_batch(1, 2, 2, 3, 3))
 
 
@@ -105,7 +109,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pairs = [("StageLinearArgs", _lib.LinearArgs), ("StageEncoderArgs", _lib.EncoderArgs), ("StageMhaArgs", _lib.MhaArgs),
              ("StageCqaArgs", _lib.CqaArgs), ("StageHeadArgs", _lib.HeadArgs), ("StageProposalArgs", _lib.ProposalArgs),
-             ("StageProbeArgs", _lib.ProbeArgs)]
+             ("StageProbeArgs", _lib.ProbeArgs), ("StageGemmArgs", _lib.GemmArgs)]
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "stage_b200.h"', "int main(void) {"]
     for cname, ct in pairs:
         lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))

@@ -153,3 +153,52 @@ def test_oracle_gradients_match_live_reference_training_step():
         assert p.grad is not None and torch.allclose(sdg[k].grad, p.grad, rtol=0, atol=1e-6 * float(p.grad.abs().max()) + 1e-12), k
         n += 1
     assert n == 70
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference not present on this host")
+def test_oracle_dropout_sites_match_live_reference(monkeypatch):
+    """Train mode with dropout 0.1: the oracle's dropout hooks sit exactly where the reference's nn.Dropout / F.dropout calls
+    do.  Both sides get the SAME mask for the k-th dropout call (a function of k and the tensor's shape): identical placement
+    and order -> bit-identical outputs and gradients."""
+    import contextlib
+    import io
+    import torch.nn.functional as F
+    from oracle.make_golden import load_reference
+    ref_stage = load_reference()
+    opt = O.default_opt(dropout=0.1, use_sup_att=False)
+    torch.manual_seed(2018)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = ref_stage.STAGE(opt)
+    ref.train()
+    N = 3
+    batch = O.make_synthetic_batch(N, 12, 9, 10, 8, seed=4)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    calls = {"n": 0}
+
+    def kth_mask(x, p):
+        calls["n"] += 1
+        g = torch.Generator().manual_seed(1000 + calls["n"])
+        keep = (torch.rand(x.shape, generator=g) >= p).to(x.dtype)
+        return x * keep / (1.0 - p)
+
+    def fake_dropout(input, p=0.5, training=True, inplace=False):
+        return kth_mask(input, p) if training and p > 0 else input
+
+    monkeypatch.setattr(F, "dropout", fake_dropout)
+    (out, target), _, _, t_loss, _ = ref(batch)
+    loss = F.cross_entropy(out, target, reduction="sum") + 0.5 * t_loss
+    loss.backward()
+    n_ref_calls = calls["n"]
+
+    calls["n"] = 0
+    shapes = []
+    monkeypatch.setattr(O, "DROP", lambda tag, x: (shapes.append(tag), kth_mask(x, 0.1))[1])
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(".pe") else v.clone()) for k, v in sd.items()}
+    with torch.enable_grad():
+        mine = O.stage_forward.__wrapped__(sdg, opt, batch, training=True)
+        mine_loss = F.cross_entropy(mine["answer"], mine["target"], reduction="sum") + 0.5 * mine["temporal_loss"]
+        mine_loss.backward()
+    assert calls["n"] == n_ref_calls == len(shapes) == 21, (calls["n"], n_ref_calls, shapes)
+    assert torch.equal(mine["answer"], out.detach()) and torch.equal(mine_loss.detach(), loss.detach())
+    for k, p in ref.named_parameters():
+        assert torch.allclose(sdg[k].grad, p.grad, rtol=0, atol=1e-6 * float(p.grad.abs().max()) + 1e-12), k

@@ -10,12 +10,15 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-# max-norm relative, per parameter tensor (fp32 on both sides, different summation orders).  The small cases sit at 2e-5; at
-# cfg1 size a max-pool argmax / ReLU sign decided by the last bit differs between the two fp32 forwards now and then and
-# re-routes one channel's gradient (tools/grad_error_probe.py: 1.9e-4 on the cls encoder's first conv against an fp64
-# oracle, everything further from the pool below 2e-5), hence the looser bound there.
+# max-norm relative, per parameter tensor (fp32 on both sides, different summation orders).  The small cases sit at 1e-5 to
+# 6e-5.  At cfg1 size a ReLU sign / max-pool argmax decided by the last bit differs between the two fp32 forwards now and
+# then and moves one whole gradient entry; the gradient is concentrated on the few rows the max-pool routes it to, so one
+# such flip is visible at 1e-3 in the weight right in front of that ReLU (tools/grad_error_probe.py against an fp64 oracle:
+# c2q_down_projection.2 / the cls encoder's first conv at 2e-4 .. 2e-3 depending on the summation order of the build,
+# everything further away below 2e-5; the CPU fp32 oracle itself is at 2e-6) - hence the looser bound there.
 GRAD_TOL = 2e-4
-GRAD_TOL_LARGE = 1e-3
+GRAD_TOL_LARGE = 3e-3
+GRAD_TOL_TC = 5e-3
 ZERO_GRAD_BIASES = ("classifier.conv.2.bias", "temporal_scoring_st_layers.0.conv.2.bias", "temporal_scoring_ed_layers.0.conv.2.bias")
 
 
@@ -72,8 +75,15 @@ def _model_and_state(opt, seed=2018, perturb=True):
     return model, sd
 
 
-@pytest.mark.parametrize("N,T,R,Lq,Ls,seed,sup", [(3, 9, 5, 7, 8, 4, False), (4, 14, 9, 12, 10, 9, True), (2, 40, 25, 40, 50, 2018, True)])
-def test_backward_matches_autograd_of_the_oracle(N, T, R, Lq, Ls, seed, sup):
+@pytest.mark.parametrize("N,T,R,Lq,Ls,seed,sup,tc", [(3, 9, 5, 7, 8, 4, False, False), (4, 14, 9, 12, 10, 9, True, False),
+                                                     (2, 40, 25, 40, 50, 2018, True, False), (2, 40, 25, 40, 50, 2018, True, True)])
+def test_backward_matches_autograd_of_the_oracle(N, T, R, Lq, Ls, seed, sup, tc, monkeypatch):
+    """tc=False: every GEMM of the step in exact fp32 (the tensor-core threshold moved out of reach); tc=True: the engine as it
+    runs (split-fp16 tcgen05 GEMMs for the large row counts, 1e-5 forward error): a ReLU / max-pool decision within 1e-5 of
+    its threshold then falls the other way now and then and moves whole gradient entries, so the bound is looser there; the
+    tensor-core products themselves are checked at 3e-5 in test_train_ops_gpu.py."""
+    import tvqaplus_b200.train as train_mod
+    monkeypatch.setattr(train_mod, "TC_MIN_ROWS", 4096 if tc else 1 << 60)
     opt = O.default_opt(dropout=0.0, use_sup_att=sup)
     batch = O.make_synthetic_batch(N, T, R, Lq, Ls, seed=seed)
     if sup:
@@ -91,7 +101,7 @@ def test_backward_matches_autograd_of_the_oracle(N, T, R, Lq, Ls, seed, sup):
     assert abs(loss.item() - want_loss.item()) <= 1e-4 * abs(want_loss.item()), (loss.item(), want_loss.item())
     loss.backward()
     got = {k: p.grad for k, p in model.named_parameters()}
-    worst = compare_grads(got, want, GRAD_TOL_LARGE if N * T * Lq > 2000 else GRAD_TOL)
+    worst = compare_grads(got, want, GRAD_TOL_TC if tc else (GRAD_TOL_LARGE if N * T * Lq > 2000 else GRAD_TOL))
     print("worst gradient error %.2e (%s)" % worst)
 
 
@@ -146,8 +156,12 @@ def test_graph_replay_equals_eager_steps():
     dev = torch.device("cuda:0")
     batches = []
     for s_ in (1, 2, 3):
-        b = O.make_synthetic_batch(3, 10, 6, 8, 9, seed=s_)
-        b["att_labels"], b["anno_st_idx"] = O.make_att_labels(batch=b, seed=4)  # same label geometry -> same number of pairs
+        b = O.make_synthetic_batch(3, 10, 6, 8, 9, seed=s_, dense=True)
+        b["target"] = torch.tensor([1, 4, 2])
+        if batches:  # the same labels -> the same number of sampled pairs -> one graph serves all three batches
+            b["att_labels"], b["anno_st_idx"] = batches[0]["att_labels"], batches[0]["anno_st_idx"]
+        else:
+            b["att_labels"], b["anno_st_idx"] = O.make_att_labels(batch=b, seed=4)
         batches.append(b)
     finals = []
     for use_graph in (False, True):
@@ -170,3 +184,78 @@ def test_graph_replay_equals_eager_steps():
         upd = float((finals[0][k] - sd[k]).norm())
         err = float((finals[1][k] - finals[0][k]).norm())
         assert err <= 0.02 * upd + 1e-7, "%s: graph vs eager %.3e, update %.3e" % (k, err, upd)
+
+
+def test_dropout_kernel_statistics_and_determinism():
+    from tvqaplus_b200 import train_ops as T
+    x = torch.ones(1 << 20, device="cuda")
+    seed = torch.tensor([7, 3], dtype=torch.int32, device="cuda")
+    a = T.dropout(x, 0.1, seed, 11, out=torch.empty_like(x))
+    assert abs(float((a == 0).float().mean()) - 0.1) < 2e-3 and abs(float(a.max()) - 1 / 0.9) < 1e-6
+    assert torch.equal(a, T.dropout(x, 0.1, seed, 11, out=torch.empty_like(x)))                      # a pure function of its key
+    b = T.dropout(x, 0.1, seed, 12, out=torch.empty_like(x))                                          # another site
+    c = T.dropout(x, 0.1, torch.tensor([7, 4], dtype=torch.int32, device="cuda"), 11, out=torch.empty_like(x))  # the next call
+    for other in (b, c):
+        both = float(((a == 0) & (other == 0)).float().mean())
+        assert abs(both - 0.01) < 1e-3                                                                # independent masks
+    assert torch.equal(T.dropout(x, 0.0, seed, 11, out=torch.empty_like(x)), x)
+
+
+def test_training_with_dropout_matches_the_oracle_given_the_same_masks():
+    """Train mode with the reference's default dropout 0.1 (config.py:105): the masks are those of the product's generator
+    (rebuilt here site by site with the same key), handed to the oracle through its DROP hook - whose placement is pinned to
+    the live reference in tests/test_oracle.py - and loss + every gradient compared with autograd."""
+    import zlib
+    from tvqaplus_b200 import train_ops as T
+    from tvqaplus_b200.train import TrainEngine
+    N, Tn, R, Lq, Ls = 3, 9, 5, 7, 8
+    opt = O.default_opt(dropout=0.1, use_sup_att=True)
+    batch = O.make_synthetic_batch(N, Tn, R, Lq, Ls, seed=4)
+    batch["att_labels"], batch["anno_st_idx"] = O.make_att_labels(batch, seed=2)
+    model, sd = _model_and_state(opt)
+    dev = torch.device("cuda:0")
+    model = model.to(dev).train()
+    eng = model._train_engine = TrainEngine(model)
+    eng.seed_dev = torch.tensor([123, 0], dtype=torch.int32, device=dev)
+    torch.manual_seed(7)
+    (out, target), att_loss, _, t_loss, _ = model(H.batch_to(batch, dev))
+    loss = F.cross_entropy(out, target, reduction="sum") * (1.0 * N / len(target)) + 0.5 * t_loss + 0.1 * att_loss
+    loss.backward()
+    assert int(eng.seed_dev[1]) == 1
+    key = torch.tensor([123, 1], dtype=torch.int32, device=dev)
+
+    def ours_mask(tag, numel):
+        ones = torch.ones(numel, device=dev)
+        return T.dropout(ones, 0.1, key, zlib.crc32(tag.encode()), out=torch.empty_like(ones)).cpu()
+
+    tgt = target.cpu().tolist()
+
+    def drop(tag, x):
+        if tag == "cls":  # oracle rows = valid proposals only, ours = all 2N rows
+            full = ours_mask(tag, 2 * N * 5 * 256).view(2 * N, 5, 256)
+            return x * full[drop.valid_rows].view_as(x)
+        m = ours_mask(tag, x.numel())
+        if tag.endswith(".c2q") or tag == "cat":  # ours (n, a, i, t), the reference's (n, a, t, i)
+            m = m.view(N, 5, Lq, Tn, 384).permute(0, 1, 3, 2, 4)
+        return x * m.reshape(x.shape)
+
+    # which proposal rows exist (the predicted span passes the IoU test or not): the engine's own record of that forward
+    drop.valid_rows = eng.last_row_valid.bool().cpu()
+    assert int(drop.valid_rows.sum()) == len(tgt)
+
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(".pe") else v.clone()) for k, v in sd.items()}
+    O.DROP = drop
+    try:
+        with torch.enable_grad():
+            want = O.stage_forward.__wrapped__(sdg, opt, batch, training=True)
+            torch.manual_seed(7)
+            att = O.get_att_loss(want["vid_raw_s"], batch.att_labels, batch.target, batch.anno_st_idx, opt.num_negatives,
+                                 opt.att_loss_type, opt.alpha, opt.margin)
+            want_loss = reference_loss(want, N, att)
+            want_loss.backward()
+    finally:
+        O.DROP = None
+    assert torch.equal(want["target"], target.cpu())
+    assert abs(loss.item() - want_loss.item()) <= 1e-4 * abs(want_loss.item()), (loss.item(), want_loss.item())
+    worst = compare_grads({k: p.grad for k, p in model.named_parameters()}, {k: v.grad for k, v in sdg.items() if v.requires_grad})
+    print("worst gradient error with dropout %.2e (%s)" % worst)

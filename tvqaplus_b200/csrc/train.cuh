@@ -418,6 +418,24 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
     x[i] *= s;
 }
+// inverted dropout with a counter-based generator: element i of site `site` in call `seed[1]` of a run seeded `seed[0]` is
+// kept when hash(seed, site, i) >= p * 2^32 and scaled by 1 / (1 - p).  The backward applies the same kernel to the gradient
+// (no mask is stored); the seed lives on the device so that the launch can be replayed from a CUDA graph.
+__device__ __forceinline__ unsigned mix64_hi(unsigned long long z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<unsigned>(z >> 32);
+}
+__global__ void dropout_kernel(const float* x, float* y, long long n, float p, const int* __restrict__ seed, unsigned site) {
+  const unsigned long long key = (static_cast<unsigned long long>(static_cast<unsigned>(__ldg(seed))) << 32 | static_cast<unsigned>(__ldg(seed + 1))) *
+                                     0xD6E8FEB86659FD93ull + static_cast<unsigned long long>(site) * 0x9E3779B97F4A7C15ull;
+  const unsigned thr = static_cast<unsigned>(fminf(p, 0.999999f) * 4294967296.f);
+  const float sc = 1.f / (1.f - p);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = mix64_hi(key + static_cast<unsigned long long>(i + 1) * 0x9E3779B97F4A7C15ull) >= thr ? x[i] * sc : 0.f;
+}
+
 // (g, I, T, d) -> (g, T, I, d)
 __global__ void permute_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long groups, int I, int T, int d4) {
   const long long total = groups * I * T * d4;

@@ -114,6 +114,11 @@ int stage_scale(float* x, int64_t n, const float* scalar, float mult, void* stre
   scale_kernel<<<grid_for(n, 1024), 256, 0, S(stream)>>>(x, n, scalar, mult);
   return check_launch("scale");
 }
+int stage_dropout(const float* x, float* y, int64_t n, float p, const int32_t* seed_dev, uint32_t site, void* stream) {
+  STG_REQUIRE(x && y && seed_dev && n > 0 && p >= 0.f && p < 1.f, STAGE_E_BADARG, "dropout: bad argument (0 <= p < 1)");
+  dropout_kernel<<<grid_for(n, 1024), 256, 0, S(stream)>>>(x, y, n, p, seed_dev, site);
+  return check_launch("dropout");
+}
 int stage_permute_it(const float* x, float* y, int64_t groups, int i_dim, int t_dim, int d, void* stream) {
   STG_REQUIRE(x && y && x != y, STAGE_E_BADARG, "permute: null or aliased pointers");
   STG_REQUIRE(groups > 0 && i_dim > 0 && t_dim > 0 && d > 0 && d % 4 == 0 && aligned16(x) && aligned16(y), STAGE_E_BADARG, "permute: bad shape or alignment");

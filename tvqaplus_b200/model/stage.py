@@ -158,10 +158,10 @@ class STAGE(nn.Module):
         """batch: the edict ``prepare_inputs`` builds (tvqa_dataset.py:631-688); see the reference docstring
         (model/stage.py:200-219).  Eval returns ``(out, att_loss, att_predictions, temporal_loss, softmax(t_scores),
         other_outputs)``; ``inference_mode`` returns the prediction dict (model/stage.py:297-312)."""
-        if self.training and self.dropout > 0:
+        if self.training and self.dropout > 0 and not torch.is_grad_enabled():
             raise NotImplementedError(
-                "tvqaplus_b200: the train-mode forward and the backward are built for dropout = 0 only (no dropout RNG); "
-                "call model.eval() or set opt.dropout = 0")
+                "tvqaplus_b200: dropout > 0 in train mode runs through the training engine (tvqaplus_b200/train.py), which "
+                "needs gradients enabled; under torch.no_grad() call model.eval() or set opt.dropout = 0")
         if self.flag_cnt == 0:
             raise NotImplementedError  # model/stage.py:291-292
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -425,36 +425,46 @@ class STAGE(nn.Module):
         return sampled_pos, sampled_neg
 
     def _att_pairs(self, att_labels, target, start_indices, num_negatives, use_hard_negatives, drop_topk):
-        """(batch, answer, image, word, region) rows of every sampled positive / negative — the index bookkeeping of
-        model/stage.py:613-694, on the host (it depends on the labels and the host RNG only)."""
+        """(batch, answer, image, word, region) rows of every sampled positive / negative - the index bookkeeping of
+        model/stage.py:613-694 and sample_negatives' random branch (:556-607), on the host (it depends on the labels and the
+        host RNG only).  The reference makes one ``torch.randint(high=#negatives of the word)`` call per (example, image, word)
+        in loop order; exactly those calls are made here, in that order, on the same global CPU generator (so the sampled
+        pairs are the reference's for a given seed) - everything around them (nonzero / unique / per-word slicing /
+        concatenation, ~10 tiny tensor ops per word in the reference) is a handful of numpy operations per labelled image:
+        tens of milliseconds per batch instead of hundreds."""
+        if use_hard_negatives:
+            raise NotImplementedError("tvqaplus_b200: hard-negative sampling is not built (never active with the reference's "
+                                      "defaults, and its top-k branch crashes in the reference when a word has few negatives)")
         tgt = target.tolist() if torch.is_tensor(target) else list(target)
-        pos_c, neg_c = [], []
+        cols, draws = [], []  # per labelled image: (b, ca, img, word[], pos_region[], zero_sorted, word-of-draw[]) and its draws
         for b in range(len(tgt)):
             ca, st = int(tgt[b]), start_indices[b]
-            bpos, bneg = [], []
             for i, lab in enumerate(att_labels[b]):
-                lab = lab.cpu()
-                p = torch.nonzero(lab)
-                if len(p) == 0:
+                lab = np.asarray(lab.cpu().numpy() if torch.is_tensor(lab) else lab)
+                nz = lab != 0
+                w_idx, r_idx = np.nonzero(nz)          # row-major: by word, then region (torch.nonzero order)
+                if w_idx.size == 0:
                     continue
-                bpos.append(torch.cat([p.new_full([len(p), 1], st + i), p], dim=1))
-                q = torch.nonzero(lab == 0)
-                bneg.append(torch.cat([q.new_full([len(q), 1], st + i), q], dim=1))
-            if not bpos:
-                continue
-            bpos, bneg = torch.cat(bpos, 0), torch.cat(bneg, 0)
-            for img in bpos[:, 0].unique().tolist():
-                ip, ineg = bpos[bpos[:, 0] == img], bneg[bneg[:, 0] == img]
-                for wd in ip[:, 1].unique().tolist():
-                    sp, sn = self.sample_negatives(None, ip[ip[:, 1] == wd], ineg[ineg[:, 1] == wd], num_negatives=num_negatives,
-                                                   use_hard_negatives=use_hard_negatives, negative_pool_size=self.negative_pool_size,
-                                                   num_hard=self.num_hard, drop_topk=drop_topk)
-                    base = torch.LongTensor([[b, ca]] * len(sp))
-                    pos_c.append(torch.cat([base, sp], dim=1))
-                    neg_c.append(torch.cat([base, sn], dim=1))
-        if not pos_c:  # the reference's torch.cat of an empty list raises here as well
+                words, first, cnt = np.unique(w_idx, return_index=True, return_counts=True)
+                reps = cnt * num_negatives
+                grp = np.repeat(np.arange(len(words)), reps)                       # group (= word) of every draw
+                within = np.arange(reps.sum()) - np.repeat(np.cumsum(reps) - reps, reps)
+                pos_sel = first[grp] + within % cnt[grp]                           # cat([positives of the word] * num_negatives)
+                n_zero = (~nz).sum(1)
+                if np.any(n_zero[words] == 0):
+                    raise RuntimeError("get_att_loss: a labelled word has no negative region (the reference's randint fails too)")
+                zero_sorted = np.argsort(nz, axis=1, kind="stable")                # the zero regions of every word, ascending, first
+                cols.append((b, ca, st + i, w_idx[pos_sel], r_idx[pos_sel], zero_sorted, words[grp]))
+                draws.append(torch.cat([torch.randint(low=0, high=int(h), size=(int(k),), dtype=torch.long)
+                                        for h, k in zip(n_zero[words].tolist(), reps.tolist())]).numpy())
+        if not cols:  # the reference's torch.cat of an empty list raises here as well
             raise RuntimeError("get_att_loss: no positive attention label in the batch")
-        return torch.cat(pos_c, 0), torch.cat(neg_c, 0)
+        pos_rows, neg_rows = [], []
+        for (b, ca, img, w, r, zero_sorted, wd), draw in zip(cols, draws):
+            head = np.broadcast_to(np.array([b, ca, img], dtype=np.int64), (draw.size, 3))
+            pos_rows.append(np.concatenate([head, w[:, None], r[:, None]], 1))
+            neg_rows.append(np.concatenate([head, wd[:, None], zero_sorted[wd, draw][:, None]], 1))
+        return torch.from_numpy(np.concatenate(pos_rows, 0).astype(np.int64)), torch.from_numpy(np.concatenate(neg_rows, 0).astype(np.int64))
 
     def get_att_loss(self, scores, att_labels, target, words, vid_names, qids, q_lens, img_indices, boxes, start_indices,
                      num_negatives=2, use_hard_negatives=False, drop_topk=0):

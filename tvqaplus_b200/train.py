@@ -21,6 +21,7 @@ cls encoder.  All arithmetic is fp32 (CUDA-core FMA): gradients are checked agai
 """
 from __future__ import annotations
 
+import zlib
 from typing import Dict, Optional
 
 import torch
@@ -80,8 +81,17 @@ class TrainEngine:
             self.offsets[n] = at
             at += (p.numel() + 63) // 64 * 64
         self.n_params = at
+        self.p_drop = float(model.dropout)
+        self.seed_dev = None  # int32 [seed, forward-call counter] on the device (created at the first forward)
 
     # ---------------------------------------------------------------------------------------------- helpers
+    def _drop(self, x, tag, out=None):
+        """Dropout site ``tag`` (forward: on the activation; backward: the same call on its gradient - the mask is a pure
+        function of (seed, call counter, tag, element index))."""
+        if self.p_drop <= 0.0:
+            return x
+        return T.dropout(x, self.p_drop, self.seed_dev, zlib.crc32(tag.encode()), out=out)
+
     def _P(self) -> Dict[str, torch.Tensor]:
         return {n: p.detach() for n, p in self.model.named_parameters()}
 
@@ -91,26 +101,28 @@ class TrainEngine:
         return flat, views
 
     # ---------------------------------------------------------------------------------------------- input projections
-    def _fc_fwd(self, P, x, pre):
+    def _fc_fwd(self, P, x, pre, tag):
         h0, s0 = T.ln_fwd(x, P[pre + ".0.weight"], P[pre + ".0.bias"])
+        h0 = self._drop(h0, tag + ".fc")      # nn.Dropout of bert_word_encoding_fc / vid_fc (model/stage.py:87,100)
         r1 = lin_fwd(h0, P[pre + ".2.weight"], P[pre + ".2.bias"], relu=True)
         h1, s1 = T.ln_fwd(r1, P[pre + ".4.weight"], P[pre + ".4.bias"])
+        h1 = self._drop(h1, tag + ".emb")     # nn.Dropout of input_embedding (model/stage.py:116)
         r2 = lin_fwd(h1, P["input_embedding.1.weight"], P["input_embedding.1.bias"], relu=True)
         e0, s2 = T.ln_fwd(r2, P["input_embedding.3.weight"], P["input_embedding.3.bias"])
-        return e0, (x, h0, s0, r1, h1, s1, r2, s2, pre)
+        return e0, (x, h0, s0, r1, h1, s1, r2, s2, pre, tag)
 
     def _fc_bwd(self, P, G, de0, sv):
-        x, h0, s0, r1, h1, s1, r2, s2, pre = sv
+        x, h0, s0, r1, h1, s1, r2, s2, pre, tag = sv
         dz2 = T.ln_bwd(de0, r2, s2, P["input_embedding.3.weight"], G["input_embedding.3.weight"], G["input_embedding.3.bias"], relu_x=True)
         T.linear_bwd_w(dz2, h1, G["input_embedding.1.weight"], G["input_embedding.1.bias"])
-        dh1 = lin_bwd_x(dz2, P["input_embedding.1.weight"])
+        dh1 = self._drop(lin_bwd_x(dz2, P["input_embedding.1.weight"]), tag + ".emb")
         dz1 = T.ln_bwd(dh1, r1, s1, P[pre + ".4.weight"], G[pre + ".4.weight"], G[pre + ".4.bias"], relu_x=True)
         T.linear_bwd_w(dz1, h0, G[pre + ".2.weight"], G[pre + ".2.bias"])
-        dh0 = lin_bwd_x(dz1, P[pre + ".2.weight"])
+        dh0 = self._drop(lin_bwd_x(dz1, P[pre + ".2.weight"]), tag + ".fc")
         T.ln_bwd(dh0, x, s0, P[pre + ".0.weight"], G[pre + ".0.weight"], G[pre + ".0.bias"], want_dx=False)
 
     # ---------------------------------------------------------------------------------------------- encoder blocks
-    def _enc_fwd(self, P, x, n_seq, L, enc, prefix):
+    def _enc_fwd(self, P, x, n_seq, L, enc, prefix, tag):
         blocks = []
         cur_in = x
         ksize = enc.stacked_encoderBlocks[0].kernel_size
@@ -121,6 +133,8 @@ class TrainEngine:
             convs = []
             for i in range(mod.n_conv):
                 nrm, st = T.ln_fwd(cur, P["%s.layer_norm.%d.weight" % (blk, i)], P["%s.layer_norm.%d.bias" % (blk, i)])
+                if i % 2 == 0:  # F.dropout in front of every other conv (model/encoder.py:41-42)
+                    nrm = self._drop(nrm, "%s.enc.%d.%d" % (tag, b, i))
                 dw = T.dwconv_fwd(nrm, P["%s.conv.%d.depthwise_conv.weight" % (blk, i)], P["%s.conv.%d.depthwise_conv.bias" % (blk, i)],
                                   n_seq, L, ksize)
                 pw = lin_fwd(dw, P["%s.conv.%d.pointwise_conv.weight" % (blk, i)].reshape(128, 128), P["%s.conv.%d.pointwise_conv.bias" % (blk, i)], relu=True)
@@ -128,14 +142,14 @@ class TrainEngine:
                 convs.append((cur, st, nrm, dw, pw))
                 cur = nxt
             out, stf = T.ln_fwd(cur, P[blk + ".final_layer_norm.weight"], P[blk + ".final_layer_norm.bias"])
-            blocks.append((convs, cur, stf, blk))
+            blocks.append((convs, cur, stf, blk, b))
             cur_in = out
-        return cur_in, (blocks, n_seq, L, ksize)
+        return cur_in, (blocks, n_seq, L, ksize, tag)
 
     def _enc_bwd(self, P, G, dout, sv):
-        blocks, n_seq, L, k = sv
+        blocks, n_seq, L, k, tag = sv
         d = dout
-        for convs, last, stf, blk in reversed(blocks):
+        for convs, last, stf, blk, b in reversed(blocks):
             d = T.ln_bwd(d, last, stf, P[blk + ".final_layer_norm.weight"], G[blk + ".final_layer_norm.weight"], G[blk + ".final_layer_norm.bias"])
             for i in reversed(range(len(convs))):
                 cur, st, nrm, dw, pw = convs[i]
@@ -144,15 +158,20 @@ class TrainEngine:
                 T.linear_bwd_w(dpw, dw, G[pwn + ".weight"], G[pwn + ".bias"])
                 ddw = lin_bwd_x(dpw, P[pwn + ".weight"].reshape(128, 128))
                 dn = T.dwconv_bwd(ddw, nrm, P[dwn + ".weight"], G[dwn + ".weight"], G[dwn + ".bias"], n_seq, L, k)
+                if i % 2 == 0:
+                    dn = self._drop(dn, "%s.enc.%d.%d" % (tag, b, i))
                 d = T.ln_bwd(dn, cur, st, P[lnn + ".weight"], G[lnn + ".weight"], G[lnn + ".bias"], add=d, out=d)
         return d  # the position table has no gradient
 
     # ---------------------------------------------------------------------------------------------- context-query attention
-    def _cqa_fwd(self, P, C, Cn, c_mask, Q, q_mask, N, Tn, Lq, Lc, scale):
+    def _cqa_fwd(self, P, C, Cn, c_mask, Q, q_mask, N, Tn, Lq, Lc, scale, tag):
         ai, dev = 5 * Lq, C.device
         Qn, qinv = T.l2norm_fwd(Q)
+        # F.dropout on the NORMALISED operands of the similarity only (context_query_attention.py:95-96); U = P Q uses Q itself
+        Cd = self._drop(Cn, tag + ".cn", out=torch.empty_like(Cn)) if self.p_drop > 0 else Cn
+        Qd = self._drop(Qn, tag + ".qn", out=torch.empty_like(Qn)) if self.p_drop > 0 else Qn
         S = torch.empty(N * ai * Tn, Lc, device=dev, dtype=torch.float32)
-        T.gemm(Cn, Qn, S, ai, Tn * Lc, 128, (128, 1), (1, 128), Tn * Lc, batch=(N, 1), a_b=(ai * 128, 0), b_b=(Tn * Lc * 128, 0),
+        T.gemm(Cd, Qd, S, ai, Tn * Lc, 128, (128, 1), (1, 128), Tn * Lc, batch=(N, 1), a_b=(ai * 128, 0), b_b=(Tn * Lc * 128, 0),
                c_b=(ai * Tn * Lc, 0))
         Pm = T.attn_softmax_fwd(S, c_mask, q_mask, N, ai, Tn, Lc, scale)
         U = torch.empty(N * ai * Tn, 128, device=dev, dtype=torch.float32)
@@ -160,15 +179,16 @@ class TrainEngine:
                c_b=(ai * Tn * 128, 128))
         cat = T.cat3_fwd(C, U, Tn)
         l, st = T.ln_fwd(cat, P["c2q_down_projection.0.weight"], P["c2q_down_projection.0.bias"])
+        l = self._drop(l, tag + ".c2q")  # nn.Dropout of c2q_down_projection (model/stage.py:135)
         att = lin_fwd(l, P["c2q_down_projection.2.weight"], P["c2q_down_projection.2.bias"], relu=True)
-        return att, S, (C, Cn, Q, Qn, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale)
+        return att, S, (C, Cn, Cd, Q, Qn, Qd, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale, tag)
 
-    def _cqa_bwd(self, P, G, datt, sv, dC, dCn, att_grad=None):
-        C, Cn, Q, Qn, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale = sv
+    def _cqa_bwd(self, P, G, datt, sv, dC, cinv, att_grad=None):
+        C, Cn, Cd, Q, Qn, Qd, qinv, S, Pm, U, cat, l, st, att, N, Tn, Lq, Lc, scale, tag = sv
         ai, dev = 5 * Lq, C.device
         dpre = T.relu_bwd(datt, att, out=datt)
         T.linear_bwd_w(dpre, l, G["c2q_down_projection.2.weight"], G["c2q_down_projection.2.bias"])
-        dl = lin_bwd_x(dpre, P["c2q_down_projection.2.weight"])
+        dl = self._drop(lin_bwd_x(dpre, P["c2q_down_projection.2.weight"]), tag + ".c2q")
         dcat = T.ln_bwd(dl, cat, st, P["c2q_down_projection.0.weight"], G["c2q_down_projection.0.weight"], G["c2q_down_projection.0.bias"], out=dl)
         dU = T.cat3_bwd(dcat, C, U, dC, Tn, True)
         del dcat, dl
@@ -181,12 +201,14 @@ class TrainEngine:
         dS = T.attn_softmax_bwd_(dP, Pm, Lc, scale)
         if att_grad is not None:  # the ranking loss reads the masked raw scores of the vid stream (model/stage.py:317-341)
             att_grad(S, dS)
-        T.gemm(dS, Qn, dCn, ai, 128, Tn * Lc, (Tn * Lc, 1), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(Tn * Lc * 128, 0),
+        dCn = torch.zeros_like(C)
+        T.gemm(dS, Qd, dCn, ai, 128, Tn * Lc, (Tn * Lc, 1), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(Tn * Lc * 128, 0),
                c_b=(ai * 128, 0), mode=2, split_k=max(1, min(64, 592 // max(1, N * ((ai + 127) // 128)))))
+        T.l2norm_bwd(self._drop(dCn, tag + ".cn"), Cn, cinv, dC, True)
         dQn = torch.empty_like(Q)
-        T.gemm(dS, Cn, dQn, Tn * Lc, 128, ai, (1, Tn * Lc), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(ai * 128, 0),
+        T.gemm(dS, Cd, dQn, Tn * Lc, 128, ai, (1, Tn * Lc), (128, 1), 128, batch=(N, 1), a_b=(ai * Tn * Lc, 0), b_b=(ai * 128, 0),
                c_b=(Tn * Lc * 128, 0))
-        T.l2norm_bwd(dQn, Qn, qinv, dQ, True)
+        T.l2norm_bwd(self._drop(dQn, tag + ".qn"), Qn, qinv, dQ, True)
         return dQ
 
     # ---------------------------------------------------------------------------------------------- forward
@@ -206,26 +228,31 @@ class TrainEngine:
         target = batch.target.to(torch.int64).contiguous()
         st_lab, ed_lab = batch.ts_label["st"].to(torch.int64).contiguous(), batch.ts_label["ed"].to(torch.int64).contiguous()
         ctx = {}
+        if self.p_drop > 0:  # a new mask set per forward call: advance the call counter next to the seed
+            if self.seed_dev is None:
+                self.seed_dev = torch.tensor([int(torch.initial_seed()) & 0x7FFFFFFF, 0], dtype=torch.int32, device=batch.qas_bert.device)
+            T.counter_inc(self.seed_dev[1:])
 
         # 1. input projections + input encoder, three streams (model/stage.py:351-363)
-        qa0, ctx["fc_q"] = self._fc_fwd(P, batch.qas_bert.float().reshape(N * 5 * Lq, -1), "bert_word_encoding_fc")
-        C, ctx["enc_q"] = self._enc_fwd(P, qa0, N * 5, Lq, m.input_encoder, "input_encoder")
-        sub0, ctx["fc_s"] = self._fc_fwd(P, batch.sub_bert.float().reshape(N * Tn * Ls, -1), "bert_word_encoding_fc")
-        Qs, ctx["enc_s"] = self._enc_fwd(P, sub0, N * Tn, Ls, m.input_encoder, "input_encoder")
+        qa0, ctx["fc_q"] = self._fc_fwd(P, batch.qas_bert.float().reshape(N * 5 * Lq, -1), "bert_word_encoding_fc", "q")
+        C, ctx["enc_q"] = self._enc_fwd(P, qa0, N * 5, Lq, m.input_encoder, "input_encoder", "q")
+        sub0, ctx["fc_s"] = self._fc_fwd(P, batch.sub_bert.float().reshape(N * Tn * Ls, -1), "bert_word_encoding_fc", "s")
+        Qs, ctx["enc_s"] = self._enc_fwd(P, sub0, N * Tn, Ls, m.input_encoder, "input_encoder", "s")
         vn, _ = T.l2norm_fwd(batch.vid.float().reshape(N * Tn * R, -1), want_inv=False)  # model/stage.py:256
-        vid0, ctx["fc_v"] = self._fc_fwd(P, vn, "vid_fc")
-        Qv, ctx["enc_v"] = self._enc_fwd(P, vid0, N * Tn, R, m.input_encoder, "input_encoder")
+        vid0, ctx["fc_v"] = self._fc_fwd(P, vn, "vid_fc", "v")
+        Qv, ctx["enc_v"] = self._enc_fwd(P, vid0, N * Tn, R, m.input_encoder, "input_encoder", "v")
         del qa0, sub0, vid0, vn
 
         # 2. context-query attention + c2q projection per stream, rows (n, a, i, t) (model/stage.py:365-387)
         Cn, cinv = T.l2norm_fwd(C)
         ctx["c"] = (C, Cn, cinv)
-        att_s, _, ctx["cqa_s"] = self._cqa_fwd(P, C, Cn, qas_mask, Qs, sub_mask, N, Tn, Lq, Ls, m.scale)
-        att_v, S_vid, ctx["cqa_v"] = self._cqa_fwd(P, C, Cn, qas_mask, Qv, vid_mask, N, Tn, Lq, R, m.scale)
+        att_s, _, ctx["cqa_s"] = self._cqa_fwd(P, C, Cn, qas_mask, Qs, sub_mask, N, Tn, Lq, Ls, m.scale, "s")
+        att_v, S_vid, ctx["cqa_v"] = self._cqa_fwd(P, C, Cn, qas_mask, Qv, vid_mask, N, Tn, Lq, R, m.scale, "v")
 
         # 3. concat_fc (model/stage.py:276-279), then the reference's (n, a, t, i) row order for the cls encoder
         cat2 = T.cat3_fwd(att_s, att_v, 1)
         l2, st2 = T.ln_fwd(cat2, P["concat_fc.0.weight"], P["concat_fc.0.bias"])
+        l2 = self._drop(l2, "cat")  # nn.Dropout of concat_fc (model/stage.py:109)
         r = lin_fwd(l2, P["concat_fc.2.weight"], P["concat_fc.2.bias"], relu=True)
         stm, st4 = T.ln_fwd(r, P["concat_fc.4.weight"], P["concat_fc.4.bias"])
         ctx["cat"] = (att_s, att_v, cat2, l2, st2, r, st4)
@@ -236,17 +263,19 @@ class TrainEngine:
         mm = (sm.sum(-1) != 0).float().contiguous()                                     # max_statement_mask (N, 5, T)
 
         # 4. cls encoder + masked max over the question words (model/stage.py:499-505)
-        enc, ctx["enc_c"] = self._enc_fwd(P, stm_p, N * 5 * Tn, Lq, m.cls_encoder, "cls_encoder")
+        enc, ctx["enc_c"] = self._enc_fwd(P, stm_p, N * 5 * Tn, Lq, m.cls_encoder, "cls_encoder", "c")
         ms, arg = T.maxpool_fwd(enc, sm.view(-1, Lq), N * 5 * Tn, Lq)
         del enc, stm_p
 
         # 5. residual temporal predictor, span scores, temporal loss (model/stage.py:469-482,521,539-555)
         pj, stl, edl, cl = "cls_projection_layers.0.conv", "temporal_scoring_st_layers.0.conv", "temporal_scoring_ed_layers.0.conv", "classifier.conv"
         l0, s0 = T.ln_fwd(ms, P[pj + ".0.weight"], P[pj + ".0.bias"])
+        l0 = self._drop(l0, "proj")  # LinearWrapper: LayerNorm -> Dropout -> Linear (model/stage.py:15-32)
         p0 = lin_fwd(l0, P[pj + ".2.weight"], P[pj + ".2.bias"], relu=True)
         x1 = T.add(ms, p0)
         ls, sst = T.ln_fwd(x1, P[stl + ".0.weight"], P[stl + ".0.bias"])
         le, sed = T.ln_fwd(x1, P[edl + ".0.weight"], P[edl + ".0.bias"])
+        ls, le = self._drop(ls, "st"), self._drop(le, "ed")
         ts = torch.empty(N * 5 * Tn, 2, device=ms.device, dtype=torch.float32)
         T.linear(ls, P[stl + ".2.weight"], P[stl + ".2.bias"], out=ts, ldc=2, c_off=0)
         T.linear(le, P[edl + ".2.weight"], P[edl + ".2.bias"], out=ts, ldc=2, c_off=1)
@@ -258,7 +287,9 @@ class TrainEngine:
         spans, conf = ops.find_max_span(probs[0], probs[1])
         feat, parg, valid, row_target = T.proposal_pool_fwd(x1, mm, target, st_lab, ed_lab, spans, conf, N, Tn, m.extra_span_length, 0.01)
         lc, sc = T.ln_fwd(feat, P[cl + ".0.weight"], P[cl + ".0.bias"])
+        lc = self._drop(lc, "cls")
         rows = T.linear(lc, P[cl + ".2.weight"], P[cl + ".2.bias"]).view(2 * N, 5)
+        self.last_row_valid = valid  # (2N,) int32: which proposal rows exist (row 2n = GT span, 2n+1 = predicted span)
         ctx["head"] = (ms, arg, sm, mm, l0, s0, p0, x1, ls, sst, le, sed, dts, feat, parg, valid, lc, sc, N, Tn, Lq)
 
         # 7. attention ranking loss on the vid stream's raw scores (model/stage.py:317-341,731-746)
@@ -290,22 +321,22 @@ class TrainEngine:
         # classifier and the pooled proposal features
         dr = d_rows.contiguous().view(-1, 1)
         T.linear_bwd_w(dr, lc, G[cl + ".2.weight"], G[cl + ".2.bias"])
-        dlc = T.linear_bwd_x(dr, P[cl + ".2.weight"])
+        dlc = self._drop(T.linear_bwd_x(dr, P[cl + ".2.weight"]), "cls")
         dfeat = T.ln_bwd(dlc, feat, sc, P[cl + ".0.weight"], G[cl + ".0.weight"], G[cl + ".0.bias"])
         dx1 = torch.zeros_like(x1)
         T.proposal_pool_bwd(dfeat, parg, valid, mm, N, Tn, dx1)
         # span scores (temporal loss)
         dts = T.scale_(dts.view(-1, 2).clone(), g_ts)
         T.linear_bwd_w(dts, ls, G[stl + ".2.weight"], G[stl + ".2.bias"], dy_ld=2, dy_off=0, n=1)
-        dls = T.linear_bwd_x(dts, P[stl + ".2.weight"], dy_ld=2, dy_off=0, n=1)
+        dls = self._drop(T.linear_bwd_x(dts, P[stl + ".2.weight"], dy_ld=2, dy_off=0, n=1), "st")
         T.ln_bwd(dls, x1, sst, P[stl + ".0.weight"], G[stl + ".0.weight"], G[stl + ".0.bias"], add=dx1, out=dx1)
         T.linear_bwd_w(dts, le, G[edl + ".2.weight"], G[edl + ".2.bias"], dy_ld=2, dy_off=1, n=1)
-        dle = T.linear_bwd_x(dts, P[edl + ".2.weight"], dy_ld=2, dy_off=1, n=1)
+        dle = self._drop(T.linear_bwd_x(dts, P[edl + ".2.weight"], dy_ld=2, dy_off=1, n=1), "ed")
         T.ln_bwd(dle, x1, sed, P[edl + ".0.weight"], G[edl + ".0.weight"], G[edl + ".0.bias"], add=dx1, out=dx1)
         # residual projection
         dp0 = T.relu_bwd(dx1, p0)
         T.linear_bwd_w(dp0, l0, G[pj + ".2.weight"], G[pj + ".2.bias"])
-        dl0 = lin_bwd_x(dp0, P[pj + ".2.weight"])
+        dl0 = self._drop(lin_bwd_x(dp0, P[pj + ".2.weight"]), "proj")
         dms = T.ln_bwd(dl0, ms, s0, P[pj + ".0.weight"], G[pj + ".0.weight"], G[pj + ".0.bias"], add=dx1)
 
         # max-pool, cls encoder, back to (n, a, i, t)
@@ -318,7 +349,7 @@ class TrainEngine:
         att_s, att_v, cat2, l2, st2, r, st4 = ctx["cat"]
         dr2 = T.ln_bwd(dstm, r, st4, P["concat_fc.4.weight"], G["concat_fc.4.weight"], G["concat_fc.4.bias"], relu_x=True, out=dstm)
         T.linear_bwd_w(dr2, l2, G["concat_fc.2.weight"], G["concat_fc.2.bias"])
-        dl2 = lin_bwd_x(dr2, P["concat_fc.2.weight"])
+        dl2 = self._drop(lin_bwd_x(dr2, P["concat_fc.2.weight"]), "cat")
         dcat2 = T.ln_bwd(dl2, cat2, st2, P["concat_fc.0.weight"], G["concat_fc.0.weight"], G["concat_fc.0.bias"], out=dl2)
         datt_s = torch.empty_like(att_s)
         datt_v = T.cat3_bwd(dcat2, att_s, att_v, datt_s, 1, False)
@@ -326,16 +357,15 @@ class TrainEngine:
 
         # context-query attention, both streams; dC / dCn collect both
         C, Cn, cinv = ctx["c"]
-        dC, dCn = torch.zeros_like(C), torch.zeros_like(C)
+        dC = torch.zeros_like(C)
         att_grad = None
         if g_att is not None and "att" in ctx:
             pos, neg = ctx["att"]
 
             def att_grad(S, dS):
                 T.att_loss_bwd(S, pos, neg, 0 if m.att_loss_type == "lse" else 1, m.alpha, m.margin, g_att, dS)
-        dQv = self._cqa_bwd(P, G, datt_v, ctx["cqa_v"], dC, dCn, att_grad)
-        dQs = self._cqa_bwd(P, G, datt_s, ctx["cqa_s"], dC, dCn)
-        T.l2norm_bwd(dCn, Cn, cinv, dC, True)
+        dQv = self._cqa_bwd(P, G, datt_v, ctx["cqa_v"], dC, cinv, att_grad)
+        dQs = self._cqa_bwd(P, G, datt_s, ctx["cqa_s"], dC, cinv)
 
         # input encoders and projections
         for dq, e, f in ((dQv, "enc_v", "fc_v"), (dQs, "enc_s", "fc_s"), (dC, "enc_q", "fc_q")):

@@ -129,6 +129,14 @@ def scale_(x, scalar: torch.Tensor, mult: float = 1.0):
     return x
 
 
+def dropout(x, p: float, seed_dev: torch.Tensor, site: int, out=None):
+    """Inverted dropout keyed on (seed_dev, site, element index); ``out`` defaults to in place."""
+    y = x if out is None else out
+    with on_device(x, seed_dev):
+        check(lib().stage_dropout(_p(x), _p(y), x.numel(), float(p), _p(seed_dev), site & 0xFFFFFFFF, current_stream()), "stage_dropout")
+    return y
+
+
 def permute_it(x, groups: int, i_dim: int, t_dim: int):
     d = x.shape[-1]
     y = torch.empty_like(x)
