@@ -325,7 +325,7 @@ int stage_add(const float* a, const float* b, float* y, int64_t n, int64_t perio
 /* x *= (*scalar) * mult: chain rule with a device-resident upstream gradient, no host read */
 int stage_scale(float* x, int64_t n, const float* scalar, float mult, void* stream);
 /* nn.Dropout / F.dropout in train mode (inverted dropout): y[i] = keep(i) ? x[i] / (1 - p) : 0 with
- * keep(i) = hash(seed_dev[0], seed_dev[1], site, i) >= p * 2^32 (seed_dev: two int32 on the device - the run's seed and the
+ * keep(i) = 16 bits of hash(seed_dev[0], seed_dev[1], site, i / 4) >= p * 2^16 (seed_dev: two int32 on the device - the run's seed and the
  * forward-call counter; `site` names the dropout module).  Stateless: the backward applies the same call to the gradient.
  * y may alias x.  The distribution is the reference's, the random stream is not torch's. */
 int stage_dropout(const float* x, float* y, int64_t n, float p, const int32_t* seed_dev, uint32_t site, void* stream);

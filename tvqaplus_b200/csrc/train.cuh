@@ -427,13 +427,29 @@ __device__ __forceinline__ unsigned mix64_hi(unsigned long long z) {  // splitmi
   z ^= z >> 31;
   return static_cast<unsigned>(z >> 32);
 }
-__global__ void dropout_kernel(const float* x, float* y, long long n, float p, const int* __restrict__ seed, unsigned site) {
+// one 64-bit hash serves four consecutive elements (16 random bits each: p is resolved to 1 / 65536)
+__global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* y, long long n, float p, const int* __restrict__ seed, unsigned site, int vec) {
   const unsigned long long key = (static_cast<unsigned long long>(static_cast<unsigned>(__ldg(seed))) << 32 | static_cast<unsigned>(__ldg(seed + 1))) *
                                      0xD6E8FEB86659FD93ull + static_cast<unsigned long long>(site) * 0x9E3779B97F4A7C15ull;
-  const unsigned thr = static_cast<unsigned>(fminf(p, 0.999999f) * 4294967296.f);
+  const unsigned thr = static_cast<unsigned>(fminf(p, 0.99998f) * 65536.f);
   const float sc = 1.f / (1.f - p);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-    y[i] = mix64_hi(key + static_cast<unsigned long long>(i + 1) * 0x9E3779B97F4A7C15ull) >= thr ? x[i] * sc : 0.f;
+  const long long groups = (n + 3) >> 2;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    unsigned long long z = key + static_cast<unsigned long long>(g + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const unsigned lo = static_cast<unsigned>(z), hi = static_cast<unsigned>(z >> 32);
+    const float k0 = (lo & 0xFFFFu) >= thr ? sc : 0.f, k1 = (lo >> 16) >= thr ? sc : 0.f;
+    const float k2 = (hi & 0xFFFFu) >= thr ? sc : 0.f, k3 = (hi >> 16) >= thr ? sc : 0.f;
+    if (vec && 4 * g + 4 <= n) {
+      const float4 v = reinterpret_cast<const float4*>(x)[g];
+      reinterpret_cast<float4*>(y)[g] = make_float4(v.x * k0, v.y * k1, v.z * k2, v.w * k3);
+    } else {
+      const float kk[4] = {k0, k1, k2, k3};
+      for (int e = 0; e < 4 && 4 * g + e < n; ++e) y[4 * g + e] = x[4 * g + e] * kk[e];
+    }
+  }
 }
 
 // (g, I, T, d) -> (g, T, I, d)

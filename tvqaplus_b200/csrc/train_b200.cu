@@ -116,7 +116,7 @@ int stage_scale(float* x, int64_t n, const float* scalar, float mult, void* stre
 }
 int stage_dropout(const float* x, float* y, int64_t n, float p, const int32_t* seed_dev, uint32_t site, void* stream) {
   STG_REQUIRE(x && y && seed_dev && n > 0 && p >= 0.f && p < 1.f, STAGE_E_BADARG, "dropout: bad argument (0 <= p < 1)");
-  dropout_kernel<<<grid_for(n, 1024), 256, 0, S(stream)>>>(x, y, n, p, seed_dev, site);
+  dropout_kernel<<<grid_for((n + 3) / 4, 1024), 256, 0, S(stream)>>>(x, y, n, p, seed_dev, site, aligned16(x) && aligned16(y));
   return check_launch("dropout");
 }
 int stage_permute_it(const float* x, float* y, int64_t groups, int i_dim, int t_dim, int d, void* stream) {

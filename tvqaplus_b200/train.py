@@ -430,31 +430,50 @@ class Trainer:
         self.last_grad = None
         self._graphs = {}
 
-    # ---- one step, eager: every kernel launched from Python (about 360 launches)
-    def _step_core(self, batch, att_offsets):
+    # ---- one step = part A (forward, losses, backward -> the flat gradient) + [all-reduce] + part B (clip + Adam)
+    @staticmethod
+    def _world() -> int:
+        d = torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+    def _part_a(self, batch, att_offsets):
         eng = self.engine
         out = eng.forward(batch, att_offsets)
         n = batch.qas_bert.shape[0]
         cls, d_rows = T.answer_ce(out["answer_rows"], out["row_valid"], out["row_target"], n)
         grad = eng.backward(out["ctx"], d_rows, self.g_ts, self.g_att if out["att_loss"] is not None else None)
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM)
+        loss = cls[0] + self.ts_weight * out["temporal_loss"]
+        if out["att_loss"] is not None:
+            loss = loss + self.att_weight * out["att_loss"]
+        return dict(loss=loss, cls_loss=cls[0], n_rows=cls[1], n_correct=cls[2], temporal_loss=out["temporal_loss"],
+                    att_loss=out["att_loss"], grad=grad)
+
+    def _part_b(self, out):
+        grad = out["grad"]
         ss = torch.zeros(1, device=grad.device)
         T.grad_sumsq(grad, ss)
         T.counter_inc(self.step_dev)
         T.adam_step(self.flat, grad, self.m, self.v, ss, max_norm=self.clip, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
                     eps=self.eps, wd=self.wd, step_dev=self.step_dev)
-        loss = cls[0] + self.ts_weight * out["temporal_loss"]
-        if out["att_loss"] is not None:
-            loss = loss + self.att_weight * out["att_loss"]
-        return dict(loss=loss, cls_loss=cls[0], n_rows=cls[1], n_correct=cls[2], temporal_loss=out["temporal_loss"],
-                    att_loss=out["att_loss"], grad_sumsq=ss, grad=grad)
+        out["grad_sumsq"] = ss
+        return out
+
+    def _all_reduce(self, grad):
+        if self._world() > 1:  # SUM: the three losses are sums over examples, so this is the large-batch gradient
+            torch.distributed.all_reduce(grad, op=torch.distributed.ReduceOp.SUM)
+
+    def _step_core(self, batch, att_offsets):
+        out = self._part_a(batch, att_offsets)
+        self._all_reduce(out["grad"])
+        return self._part_b(out)
 
     _STATIC = ("qas_bert", "sub_bert", "vid", "qas_mask", "sub_mask", "vid_mask", "ts_label_mask", "target")
 
     def _capture(self, batch, att_offsets):
-        """Record the whole step (forward, losses, backward, all-reduce, clip + Adam) into a CUDA graph over static copies of
-        the inputs; nothing executes during the capture."""
+        """Record the step into CUDA graphs over static copies of the inputs; nothing executes during the capture.  One process:
+        ONE graph (forward, losses, backward, clip + Adam).  Data-parallel: TWO graphs with the NCCL all-reduce launched
+        eagerly between their replays - the collective stays out of the capture (the one attempt with the all-reduce inside
+        the captured graph, 8 ranks, deadlocked)."""
         from .host import Batch
         static = Batch(batch)
         for k in self._STATIC:
@@ -463,10 +482,17 @@ class Trainer:
         offs = None if att_offsets is None else tuple(o.to(self.flat.device, torch.int64).contiguous().clone() for o in att_offsets)
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            out = self._step_core(static, offs)
-        return static, offs, g, out
+        if self._world() == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._step_core(static, offs)
+            return static, offs, (g,), out
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, capture_error_mode="thread_local"):  # the process group's watchdog thread keeps running
+            out = self._part_a(static, offs)
+        with torch.cuda.graph(gb, pool=ga.pool(), capture_error_mode="thread_local"):
+            out = self._part_b(out)
+        return static, offs, (ga, gb), out
 
     def step(self, batch, att_offsets=None, graph: bool = False) -> dict:
         """``graph=True``: the step is replayed from a CUDA graph captured for this batch geometry (the first call with a new
@@ -481,7 +507,7 @@ class Trainer:
                 out = self._step_core(batch, att_offsets)
                 self._graphs[key] = self._capture(batch, att_offsets)
             else:
-                static, offs, g, out = rec
+                static, offs, graphs, out = rec
                 for k in self._STATIC:
                     if static[k].data_ptr() != batch[k].data_ptr():
                         static[k].copy_(batch[k], non_blocking=True)
@@ -490,7 +516,10 @@ class Trainer:
                 if offs is not None:
                     for dst, src in zip(offs, att_offsets):
                         dst.copy_(src, non_blocking=True)
-                g.replay()
+                graphs[0].replay()
+                if len(graphs) == 2:
+                    self._all_reduce(out["grad"])
+                    graphs[1].replay()
         self.steps += 1
         self.model.invalidate_weight_cache()  # the eval kernels' packed weight images are keyed on the version counter
         self.last_grad = out["grad"]
