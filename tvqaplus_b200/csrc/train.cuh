@@ -421,12 +421,6 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __
 // inverted dropout with a counter-based generator: element i of site `site` in call `seed[1]` of a run seeded `seed[0]` is
 // kept when hash(seed, site, i) >= p * 2^32 and scaled by 1 / (1 - p).  The backward applies the same kernel to the gradient
 // (no mask is stored); the seed lives on the device so that the launch can be replayed from a CUDA graph.
-__device__ __forceinline__ unsigned mix64_hi(unsigned long long z) {  // splitmix64 finaliser
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<unsigned>(z >> 32);
-}
 // one 64-bit hash serves four consecutive elements (16 random bits each: p is resolved to 1 / 65536)
 __global__ void __launch_bounds__(256) dropout_kernel(const float* x, float* y, long long n, float p, const int* __restrict__ seed, unsigned site, int vec) {
   const unsigned long long key = (static_cast<unsigned long long>(static_cast<unsigned>(__ldg(seed))) << 32 | static_cast<unsigned>(__ldg(seed + 1))) *

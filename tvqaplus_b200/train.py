@@ -391,6 +391,9 @@ class StageTrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(actx, d_rows, d_att, d_ts, _d_scores, _d_target):
         eng = actx.engine
+        if actx.saved is None:
+            raise RuntimeError("tvqaplus_b200: backward through the STAGE training graph a second time (the saved activations "
+                               "are released after the first backward; run the forward again)")
         dev = actx.idx.device
         full = torch.zeros(actx.n_rows, 5, device=dev, dtype=torch.float32)
         if d_rows is not None:
