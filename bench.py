@@ -239,8 +239,10 @@ def train_main(args, cfg, rank, local_rank, world, cores):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the STAGE kernels)")
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a short collective timeout: a rank that stops answering aborts the run in minutes instead of holding 8 GPUs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.lib()
