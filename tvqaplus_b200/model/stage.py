@@ -2,18 +2,21 @@
 
 Same constructor (``STAGE(opt)``), ``forward(batch)`` contract, sub-module names and ``state_dict`` keys as the reference,
 so ``main.py`` / ``inference.py`` can import this class instead of ``model.stage.STAGE``.  The eval / inference forward is
-fourteen kernel launches (csrc/*.cuh):
+sixteen kernel launches (csrc/*.cuh):
 
     linear x2 (text)  ->  encoder        a_embed   (5N, Lq, 128)
     linear x2 (text)  ->  encoder        sub_embed (N*T, Ls, 128)        [written straight into the CQA operand images]
     linear x2 (vid)   ->  encoder        vid_embed (N*T, R, 128)
-    cqa_fused                            statement (N, 5, T, Lq, 128)   [S, P, U, both mixed tensors never leave the SM]
-    encoder (cls, masked max-pool)       max_statement (5N*T, 128)
-    span_head                            t_scores, spans, answer        [no device->host sync]
+    cqa_prep, a.Wa, cqa_fused            statement (N, 5, T, Lq, 128)   [S, P, U, both mixed tensors never leave the SM]
+    fill, encoder (cls, masked max-pool) max_statement (5N*T, 128)
+    span_head, ts_loss_sum               t_scores, spans, answer, temporal loss        [no device->host sync]
 
-Train mode runs the same kernels plus the train branch of ``get_proposals`` (N_new >= N rows) as long as ``opt.dropout``
-is 0; there is no backward (the kernels are forward-only).  What is not built raises ``NotImplementedError`` (never a
-silent CPU path): dropout > 0 in train mode, ``add_non_visual``.
+Train mode with gradients enabled runs the training engine instead (``tvqaplus_b200/train.py``: forward with saved
+activations, dropout, train branch of ``get_proposals``; the returned tensors carry an autograd graph whose backward is the
+hand-written backward kernels, so the reference's ``loss.backward()`` / ``optimizer.step()`` loop works unchanged).  Train
+mode under ``torch.no_grad()`` runs the fused forward kernels plus the train branch of ``get_proposals`` (dropout must be 0).
+What is not built raises ``NotImplementedError`` (never a silent CPU path): ``add_non_visual``, hard negatives, and - in
+the training engine - attention heads, ``t_iter > 0``, single-stream models.
 """
 from __future__ import annotations
 

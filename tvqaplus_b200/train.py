@@ -3,7 +3,7 @@
 The reference trains through PyTorch autograd (main.py:53-66: ``loss.backward()``, ``clip_grad_norm_``, ``Adam.step()``) and
 ``nn.DataParallel`` (main.py:204-206).  Here:
 
-* ``TrainEngine`` runs the train-mode forward (dropout = 0, train branch of ``get_proposals``) out of the primitives of
+* ``TrainEngine`` runs the train-mode forward (dropout included, train branch of ``get_proposals``) out of the primitives of
   ``csrc/train.cuh`` and keeps what the backward needs; ``backward`` walks the same graph in reverse and accumulates every
   parameter gradient into ONE flat fp32 buffer (state_dict order) - the buffer a data-parallel run all-reduces.
 * ``StageTrainFunction`` wraps the pair as a ``torch.autograd.Function`` so that the reference's own training loop
@@ -230,7 +230,10 @@ class TrainEngine:
         ctx = {}
         if self.p_drop > 0:  # a new mask set per forward call: advance the call counter next to the seed
             if self.seed_dev is None:
-                self.seed_dev = torch.tensor([int(torch.initial_seed()) & 0x7FFFFFFF, 0], dtype=torch.int32, device=batch.qas_bert.device)
+                d = torch.distributed
+                rank = d.get_rank() if d.is_available() and d.is_initialized() else 0  # data-parallel ranks draw different masks
+                self.seed_dev = torch.tensor([(int(torch.initial_seed()) + 7919 * rank) & 0x7FFFFFFF, 0], dtype=torch.int32,
+                                             device=batch.qas_bert.device)
             T.counter_inc(self.seed_dev[1:])
 
         # 1. input projections + input encoder, three streams (model/stage.py:351-363)

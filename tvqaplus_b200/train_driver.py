@@ -128,6 +128,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=2018)
     ap.add_argument("--synthetic", type=int, nargs=5, metavar=("N_TRAIN", "T", "R", "LQ", "LS"), default=[64, 30, 10, 16, 20])
     ap.add_argument("--n-valid", type=int, default=16)
+    ap.add_argument("--dropout", type=float, default=0.1, help="config.py:105")
     args = ap.parse_args(argv)
 
     import torch.distributed as dist
@@ -140,7 +141,7 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(args.seed)  # same initial weights on every rank
-    model = STAGE(host.default_opt(dropout=0.0, use_sup_att=False)).to(device)
+    model = STAGE(host.default_opt(dropout=args.dropout, use_sup_att=False)).to(device)  # synthetic items carry no attention labels
     trainer = Trainer(model, lr=args.lr, wd=args.wd, clip=args.clip)
     n_train, T, R, Lq, Ls = args.synthetic
     train_items = collate.synthetic_items(n_train, T, R, Lq, Ls, seed=args.seed)
