@@ -105,3 +105,27 @@ def test_ranks_apply_the_summed_gradient():
         assert p.exitcode == 0
     assert all(r[1] < 1e-5 for r in res), res            # every rank's Adam saw (clipped) sum of both ranks' gradients
     assert abs(res[0][2] - res[1][2]) < 1e-6, res        # and the replicas stay identical
+
+
+def test_att_offsets_address_the_engine_score_layout():
+    """The pair rows are (batch, answer, image, word, region) indices into the reference's (N, 5, T, Lq, R) score tensor; the
+    training engine keeps its scores as (N, 5, Lq, T, R).  The offsets must pick the same elements."""
+    from tvqaplus_b200 import host, train
+    from tvqaplus_b200.model import STAGE
+    eng = train.TrainEngine(STAGE(host.default_opt(dropout=0.0)))
+    N, T, Lq, R = 3, 7, 5, 4
+    ref = torch.arange(N * 5 * T * Lq * R, dtype=torch.float32).view(N, 5, T, Lq, R)
+    ours = ref.permute(0, 1, 3, 2, 4).contiguous().reshape(-1)
+    g = torch.Generator().manual_seed(0)
+    rows = torch.stack([torch.randint(0, hi, (50,), generator=g) for hi in (N, 5, T, Lq, R)], 1)
+    pos, neg = eng.att_offsets_from_pairs(rows, rows.flip(0), N, T, Lq, R)
+    assert torch.equal(ours[pos], ref[rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4]])
+    r2 = rows.flip(0)
+    assert torch.equal(ours[neg], ref[r2[:, 0], r2[:, 1], r2[:, 2], r2[:, 3], r2[:, 4]])
+    # flat parameter / gradient buffer: state_dict order, every tensor on a 256-byte boundary, nothing overlaps
+    prev_end = 0
+    for n, p in eng.model.named_parameters():
+        o = eng.offsets[n]
+        assert o % 64 == 0 and o >= prev_end
+        prev_end = o + p.numel()
+    assert prev_end <= eng.n_params
