@@ -22,7 +22,7 @@ cls encoder.  All arithmetic is fp32 (CUDA-core FMA): gradients are checked agai
 from __future__ import annotations
 
 import zlib
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 
