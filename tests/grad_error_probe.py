@@ -1,4 +1,5 @@
-"""Per-parameter gradient error of the CUDA backward and of the fp32 CPU oracle, both against the fp64 CPU oracle
+"""(test infrastructure, run by hand: python tests/grad_error_probe.py [N T R Lq Ls seed])
+Per-parameter gradient error of the CUDA backward and of the fp32 CPU oracle, both against the fp64 CPU oracle
 (how much of the CUDA-vs-oracle difference is fp32 rounding amplified by softmax(10 s) and exp(20 d))."""
 import sys
 import torch

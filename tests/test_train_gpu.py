@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 # max-norm relative, per parameter tensor (fp32 on both sides, different summation orders).  The small cases sit at 1e-5 to
 # 6e-5.  At cfg1 size a ReLU sign / max-pool argmax decided by the last bit differs between the two fp32 forwards now and
 # then and moves one whole gradient entry; the gradient is concentrated on the few rows the max-pool routes it to, so one
-# such flip is visible at 1e-3 in the weight right in front of that ReLU (tools/grad_error_probe.py against an fp64 oracle:
+# such flip is visible at 1e-3 in the weight right in front of that ReLU (tests/grad_error_probe.py against an fp64 oracle:
 # c2q_down_projection.2 / the cls encoder's first conv at 2e-4 .. 2e-3 depending on the summation order of the build,
 # everything further away below 2e-5; the CPU fp32 oracle itself is at 2e-6) - hence the looser bound there.
 GRAD_TOL = 2e-4
