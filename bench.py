@@ -13,6 +13,11 @@ Prints ONE JSON line (rank 0):
   roofline  the dominant kernel (cqa_kernel) timed live on its own stream: algorithmic FLOPs / duration vs the measured
             tensor peak in MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle port (same torch ops as the reference) on the host cores, bounded sample
+  eager_cuda_baseline / parity_at_bench_config  the reference's eager path on this GPU; the timed batch checked against the oracle
+  train_step    (N=1, default config) the line of `bench.py --config cfg3` - BASELINE configs[2], the full training step - run
+                as a child process with a 300 s timeout
+`--config cfg5` / `--heads 4` / `--config cfg3` select the other BASELINE configurations (long context, self-attention
+encoders, training step: forward + backward + clip + Adam, one NCCL gradient all-reduce per step when N > 1).
 `--impl reference` times only that CPU port (all host threads), one example per step.
 Inputs (3.3 GB / batch) are far larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
 """
@@ -400,6 +405,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the configs[2] training-step line that rides along as `train_step`")
     ap.add_argument("--dropout", type=float, default=0.1, help="train configs: dropout probability (config.py:105)")
     ap.add_argument("--graph-multi", action="store_true", help="train configs on N > 1 GPUs: replay two CUDA graphs around the eager all-reduce (untested)")
     ap.add_argument("--no-graph", action="store_true", help="train configs: launch every kernel from Python instead of replaying a CUDA graph")
@@ -665,13 +671,37 @@ def main():
         except Exception as e:  # e.g. out of memory at a large config: report, never fail the bench line
             eager = {"unavailable": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
 
+    # ---------------------------------------------------------------- the training step (BASELINE configs[2]) beside the headline
+    # `bench.py --config cfg3` run as a child process with a hard timeout (its own line, minus the slow baselines), so that a
+    # problem there can never cost the headline line; rank 0 at N=1 on the default configuration only.
+    train_step = None
+    if rank == 0 and world == 1 and args.config == "cfg2" and args.heads == 0 and not args.no_train_step:
+        try:
+            del dbatch, hbatch
+            torch.cuda.empty_cache()
+            cmd = [sys.executable, os.path.abspath(__file__), "--config", "cfg3", "--steps", "5", "--warmup", "3",
+                   "--no-cpu-baseline", "--no-eager-baseline", "--no-train-step"]
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+            rows = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            if res.returncode == 0 and rows:
+                t = json.loads(rows[-1])
+                train_step = {k: t.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "e2e", "launch_mode",
+                                                    "gpu_launches", "loss_first_last", "peak_memory_gb", "clocks")}
+            else:
+                train_step = {"unavailable": "exit code %d: %s" % (res.returncode, (res.stderr.strip().splitlines() or ["no output"])[-1][:200])}
+        except subprocess.TimeoutExpired:
+            train_step = {"unavailable": "timed out after 300 s"}
+        except Exception as e:
+            train_step = {"unavailable": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
+
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 (split-fp16 x3 tensor-core GEMMs, fp32 accumulate)", "data": "synthetic",
                 "config": config, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "parity_at_bench_config": parity, "eager_cuda_baseline": eager,
-                "alg_tflops_whole_path": alg_flops_total(N * world, T, R, Lq, Ls, heads=args.heads) * args.steps / (ms_total * 1e-3) / 1e12}
+                "alg_tflops_whole_path": alg_flops_total(N * world, T, R, Lq, Ls, heads=args.heads) * args.steps / (ms_total * 1e-3) / 1e12,
+                "train_step": train_step}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
